@@ -1,0 +1,336 @@
+#!/usr/bin/env python3
+"""bench.py — T-DEED hot-path benchmark on B200 (contract: see DESIGN.md §Measurement).
+
+Workload (BASELINE.json configs[1]): FigureSkatingComp_small (RegNetY-200MF + GSF, SGP enc-dec L=3 ks=5,
+K=5, displacement head) batched inference + NMS.  One STEP = one synthetic video of 4 275 frames:
+169 overlapping clips of 100 x 3 x 224 x 398 uint8 (center-cropped to 224^2 inside the stem kernel),
+run in batches through the sm_100a engine, accumulated per video on the device, then event extraction,
+NMS (window 1) and soft-NMS (window 3).  metric = clips/s (frames/s = 100 x).
+
+  value : device-resident — the video's frames already sit in HBM (4.5 GB > L2, so no L2 flush needed)
+  e2e   : the same work through the host-facing path: pinned host uint8 clips -> H2D -> engine ->
+          post-processing -> D2H of the event lists, all inside the timed region
+  --impl reference : the CPU oracle (port of the reference's PyTorch path) on the host cores
+
+Multi-GPU (torchrun): clip-sharded inference, every rank processes its own videos (weak scaling, no
+data-path collective); time = max over ranks.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from argparse import Namespace
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, 't-deed_b200'))
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+CONFIG = dict(name='FigureSkatingComp_small', feature_arch='rny002_gsf', clip_len=100, n_layers=3, sgp_ks=5, sgp_r=4,
+              num_classes=4, radi_displacement=1, crop_dim=224)
+FRAME_H, FRAME_W = 224, 398
+VIDEO_FRAMES = 4275
+NMS_WINDOW, SNMS_WINDOW = 1, 3
+
+
+def clip_starts(num_frames, clip_len=100, overlap=75, stride=1, pad=5):
+    return [s // stride for s in range(-pad * stride, max(0, num_frames - overlap * stride), (clip_len - overlap) * stride)]
+
+
+def model_args():
+    c = CONFIG
+    return Namespace(modality='rgb', temporal_arch='ed_sgp_mixer', radi_displacement=c['radi_displacement'],
+                     feature_arch=c['feature_arch'], clip_len=c['clip_len'], n_layers=c['n_layers'], sgp_ks=c['sgp_ks'],
+                     sgp_r=c['sgp_r'], num_classes=c['num_classes'], crop_dim=c['crop_dim'])
+
+
+def randomize_(module, seed=0):
+    """Random-init weights of the right architecture with non-degenerate BN statistics / gammas (no pretrained
+    checkpoint is available offline)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for name, buf in module.named_buffers():
+            if name.endswith('running_mean'):
+                buf.copy_(torch.randn(buf.shape, generator=g) * 0.1)
+            elif name.endswith('running_var'):
+                buf.copy_(torch.rand(buf.shape, generator=g) + 0.5)
+        for name, p in module.named_parameters():
+            if '.bn.' in name and name.endswith('weight'):
+                p.copy_(torch.rand(p.shape, generator=g) + 0.5)
+            elif name.endswith('.bias'):
+                p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
+        if not sm:
+            return None
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith('active')})
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(self.rows[0][1]), 'reasons': reasons, 'samples': len(sm)}
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+        return dict(hbm=p['hbm_gbs'], tf=p['bf16_tflops_sustained'], src='measured')
+    except Exception:
+        return dict(hbm=6650.0, tf=1400.0, src='fallback')
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """CPU oracle (port of the reference's PyTorch fp32 path) on the host cores: 1 clip per step."""
+    if int(os.environ.get('RANK', '0')) != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import tdeed_oracle as O
+    import postproc_oracle as P
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    cfg = O.named_config(CONFIG['name'])
+    sd = O.random_state(cfg, 0)
+    g = torch.Generator().manual_seed(0)
+    frames = torch.randint(0, 256, (1, 100, 3, FRAME_H, FRAME_W), generator=g, dtype=torch.uint8)
+    starts = clip_starts(VIDEO_FRAMES)
+    scores = np.zeros((VIDEO_FRAMES, cfg.num_classes + 1), np.float32)
+    support = np.zeros(VIDEO_FRAMES, np.int32)
+    for _ in range(args.warmup):
+        O.predict(sd, cfg, frames)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        _, probs = O.predict(sd, cfg, frames)
+        P.accumulate_batched(scores, support, probs[0], starts[i % len(starts)])
+    t_fwd = time.perf_counter() - t0
+    # post-processing of one full video, charged pro rata (steps / clips-per-video)
+    rng = np.random.default_rng(0)
+    vs = rng.random((VIDEO_FRAMES, cfg.num_classes + 1)).astype(np.float32) ** 8
+    t1 = time.perf_counter()
+    _, _, hr = P.frame_predictions(vs, np.ones(VIDEO_FRAMES, np.int32), 0.01)
+    P.nms(*hr, window=NMS_WINDOW, threshold=0.01)
+    P.soft_nms(*hr, window=SNMS_WINDOW, threshold=0.01)
+    t_post = (time.perf_counter() - t1) * args.steps / len(starts)
+    total = t_fwd + t_post
+    value = args.steps / total
+    sample = '%d steps x 1 clip (100x3x224x398 u8) through the CPU oracle fp32 forward + numpy accumulate; ' \
+             'NMS/SNMS of one 4275-frame video charged pro rata' % args.steps
+    print(json.dumps({
+        'impl': 'reference', 'metric': 'clips_per_s', 'value': value, 'unit': 'clips/s', 'frames_per_s': value * 100,
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total / args.steps * 1e3,
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': CONFIG['name'] + ' batched inference + NMS', 'clips_per_step': 1},
+        'cpu_baseline': {'value': value, 'unit': 'clips/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+        'e2e': {'value': value, 'unit': 'clips/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours')
+    ap.add_argument('--clips-per-batch', type=int, default=13)
+    ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+
+    from model.model import TDEEDModel
+    from tdeed_b200 import ops
+    from tdeed_b200.pipeline import VideoScores, nms_events
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = TDEEDModel(device='cuda:%d' % local, args=model_args())
+    randomize_(model._model, seed=0)
+    model._model.eval()
+    eng = model._model.engine(args.precision)
+    K = CONFIG['num_classes'] + 1
+    B = args.clips_per_batch
+    starts = clip_starts(VIDEO_FRAMES)
+    n_clips = len(starts)                       # 169
+    batches = [(i, min(i + B, n_clips)) for i in range(0, n_clips, B)]
+
+    # synthetic video resident in HBM (4.5 GB) + one pinned host batch for the e2e path
+    video = torch.empty((n_clips, 100, 3, FRAME_H, FRAME_W), dtype=torch.uint8, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    for i in range(n_clips):
+        video[i] = torch.randint(0, 256, video.shape[1:], generator=gen, dtype=torch.uint8, device=dev)
+    host_batch = torch.empty((B, 100, 3, FRAME_H, FRAME_W), dtype=torch.uint8).pin_memory()
+    host_batch.copy_(video[:B].cpu())
+
+    def postproc(vs, readback):
+        ev = vs.events(0.01)
+        if readback:
+            a = nms_events(ev, K, NMS_WINDOW, 0.01, False)
+            b = nms_events(ev, K, SNMS_WINDOW, 0.01, True)
+            return len(a[0]) + len(b[0]), sum(x.nbytes for x in a) + sum(x.nbytes for x in b)
+        ops.nms(ev['hr_frame'], ev['hr_label'], ev['hr_score'], ev['counts'][1:2], K, NMS_WINDOW, 0.01, False)
+        ops.nms(ev['hr_frame'], ev['hr_label'], ev['hr_score'], ev['counts'][1:2], K, SNMS_WINDOW, 0.01, True)
+        return 0, 0
+
+    def step_device(graph=True):
+        vs = VideoScores(VIDEO_FRAMES, K, dev)
+        for lo, hi in batches:
+            fwd = eng.forward_graphed if graph else eng.forward
+            _, _, probs = fwd(video[lo:hi])
+            vs.add(probs, starts[lo:hi])
+        postproc(vs, False)
+
+    d2h = [0]
+
+    def step_e2e():
+        vs = VideoScores(VIDEO_FRAMES, K, dev)
+        for lo, hi in batches:
+            x = host_batch[:hi - lo].to(dev, non_blocking=True)          # H2D of this batch's clips
+            _, _, probs = eng.forward_graphed(x)
+            vs.add(probs, starts[lo:hi])
+        _, nbytes = postproc(vs, True)                                    # D2H of the event lists
+        d2h[0] = nbytes
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+        return x
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step_device()
+    e1.record()
+    barrier()
+    dev_s = max_over_ranks(e0.elapsed_time(e1) / 1e3)
+    launches = (eng.launches - l0) + args.steps * (len(batches) + 1 + 6)
+    clocks = sampler.stop() if rank == 0 else None
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+
+    # per-kernel-family profile of one (eager) step with CUDA events on the launch stream
+    roofline, families = None, {}
+    if rank == 0:
+        eng.prof = []
+        step_device(graph=False)
+        torch.cuda.synchronize()
+        for label, flops, nbytes, a, b in eng.prof:
+            f = families.setdefault(label, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0))
+            f['ms'] += a.elapsed_time(b)
+            f['flops'] += flops
+            f['bytes'] += nbytes
+            f['launches'] += 1
+        eng.prof = None
+        pk = peaks()
+        top = max(families, key=lambda k_: families[k_]['ms'])
+        f = families[top]
+        t_hbm, t_tc = f['bytes'] / (pk['hbm'] * 1e9), f['flops'] / (pk['tf'] * 1e12)
+        sec = f['ms'] / 1e3
+        if t_hbm >= t_tc:
+            roofline = {'kernel': top, 'bound': 'hbm', 'achieved': f['bytes'] / sec / 1e9, 'peak': pk['hbm'], 'unit': 'GB/s'}
+        else:
+            roofline = {'kernel': top, 'bound': 'tensor', 'achieved': f['flops'] / sec / 1e12, 'peak': pk['tf'], 'unit': 'TFLOP/s'}
+        roofline['frac'] = roofline['achieved'] / roofline['peak']
+        roofline['traffic'] = None
+        roofline['peak_source'] = pk['src']
+        roofline['ms_per_launch'] = f['ms'] / f['launches']
+        roofline['share_of_step'] = f['ms'] / sum(v['ms'] for v in families.values())
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+        import tdeed_oracle as O
+        cores = os.cpu_count()
+        torch.set_num_threads(cores)
+        cfg = O.named_config(CONFIG['name'])
+        sd = {k_: v.detach().cpu() for k_, v in model.state_dict().items()}
+        x = video[:1].cpu()
+        O.predict(sd, cfg, x)
+        t0 = time.perf_counter()
+        reps = 3
+        for _ in range(reps):
+            O.predict(sd, cfg, x)
+        dt = (time.perf_counter() - t0) / reps
+        cpu_baseline = {'value': 1.0 / dt, 'unit': 'clips/s', 'cores': cores, 'kind': 'port',
+                        'sample': '%d x 1 clip (100x3x224x398 u8) through the CPU oracle fp32 forward, torch threads = %d' % (reps, cores)}
+
+    if rank == 0:
+        total_clips = n_clips * args.steps * world
+        value = total_clips / dev_s
+        out = {
+            'metric': 'clips_per_s', 'value': value, 'unit': 'clips/s', 'frames_per_s': value * 100, 'n_gpus': world,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dev_s / args.steps * 1e3, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
+            'config': {'workload': CONFIG['name'] + ' batched inference + NMS', 'clips_per_step': n_clips,
+                       'clips_per_batch': B, 'frame_shape': [100, 3, FRAME_H, FRAME_W], 'video_frames': VIDEO_FRAMES,
+                       'l2_policy': 'inputs (4.5 GB/video) larger than L2', 'parallelism': 'clip-sharded x%d' % world},
+            'e2e': {'value': total_clips / e2e_s, 'unit': 'clips/s', 'h2d_bytes_per_step': int(n_clips * 100 * 3 * FRAME_H * FRAME_W),
+                    'd2h_bytes_per_step': int(d2h[0])},
+            'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
+            'kernel_families_ms_per_step': {k_: round(v['ms'], 3) for k_, v in sorted(families.items(), key=lambda kv: -kv[1]['ms'])},
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,197 @@
+/* tdeed_b200.h — C-ABI of libtdeed_sm100.so: hand-written sm_100a kernels for T-DEED's per-clip
+ * inference/training hot path (BASELINE.json north_star).
+ *
+ * The reference (arturxe2/T-DEED) is pure Python/PyTorch and has NO operator/plugin/FFI layer
+ * (SURVEY.md §8b): its seam is the Python class API of model/model.py.  This header is therefore the
+ * boundary a maintainer would bind from the reference's own modules (ctypes stub in INTEGRATION.md);
+ * each entry point cites the reference lines whose arithmetic it replaces (paths under the
+ * reference repo root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all memory
+ *     (the library never allocates or frees device memory and keeps no mutable global state);
+ *   - calls are asynchronous on `stream` (a cudaStream_t), re-entrant, and never synchronise;
+ *   - activations are channels-last: images NHWC [frames, H, W, C], sequences [B, T, C];
+ *   - dtype arguments: TDEED_F32 or TDEED_BF16 (storage type; accumulation is always fp32);
+ *   - return 0 on success or a negative tdeed_status; tdeed_last_error() gives the text (thread-local);
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef TDEED_B200_H_
+#define TDEED_B200_H_
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  TDEED_OK = 0,
+  TDEED_ERR_SHAPE = -1,       /* bad shape / alignment / null pointer */
+  TDEED_ERR_UNSUPPORTED = -2, /* configuration outside what the kernels cover */
+  TDEED_ERR_CUDA = -3         /* launch or driver error (cudaGetLastError text preserved) */
+} tdeed_status;
+
+enum { TDEED_F32 = 0, TDEED_BF16 = 1, TDEED_U8 = 2 };
+enum { TDEED_ACT_NONE = 0, TDEED_ACT_RELU = 1, TDEED_ACT_GELU = 2 };
+enum { TDEED_SHIFT_GSM = 0, TDEED_SHIFT_GSF = 1 };
+enum { TDEED_GEMM_AUTO = 0, TDEED_GEMM_SIMT = 1, TDEED_GEMM_TCGEN05 = 2 };
+
+int tdeed_abi_version(void);
+const char* tdeed_last_error(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * (1) preprocessing fused into the stem.  Replaces model/model.py:107 (x/255), :121-129 (center /
+ * fixed crop, optional horizontal flip, per-clip ImageNet Normalize loop) and timm's
+ * stem ConvNormAct(3->32, k3, s2, pad1)+BN(eval)+ReLU.
+ * frames: planar [n_frames, 3, in_h, in_w] of u8 or f32 valued 0..255.  The crop window is
+ * [crop_y, crop_y+h) x [crop_x, crop_x+w); flip mirrors the cropped window.  w/b are the conv
+ * weights [32][3][3][3] and bias [32] with BatchNorm folded in (fp32).
+ * out: NHWC [n_frames, ceil(h/2), ceil(w/2), 32] of out_dtype. */
+int tdeed_stem_fwd(const void* frames, int frames_dtype, int n_frames, int in_h, int in_w,
+                   int crop_y, int crop_x, int h, int w, int flip,
+                   const float* weight, const float* bias,
+                   void* out, int out_dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (2) 1x1 convolution / linear layer as a GEMM with fused epilogue:
+ *        out[m, n] = act( sum_k A[m, k] * W[n, k] + bias[n] + residual[m, n] )
+ * Replaces timm Bottleneck conv1 / conv3 / downsample (+folded BN, ReLU, shortcut add), the SGP MLP
+ * and concat_fc 1x1 Conv1d layers (model/modules.py:134-138,186,244-251,307-309) and nn.Linear.
+ * A is given as up to TDEED_GEMM_MAX_SEGS column segments that are concatenated along K (the
+ * GatedShift "y[:, :fold] = gs(x[:, :fold]); y[:, fold:] = x[:, fold:]" of model/shift.py:89-93 is a
+ * virtual concat of the gate-shift output and the untouched channels).  Segment s covers columns
+ * [col0, col0+k) of the row-major matrix `a` with leading dimension `lda` (elements); segments
+ * consume W's columns in order.  When gather_stride > 1, segment rows are a strided spatial
+ * subsample of an NHWC tensor [frames, gather_h, gather_w, lda]: row m = (f, oy, ox) reads pixel
+ * (f, oy*stride, ox*stride) — the stride-2 1x1 "downsample" shortcut.
+ * W: [N, K] row-major (K = sum of segment k) of `dtype`.  bias: fp32 [N] or NULL.  residual: [M, ldr]
+ * of res_dtype or NULL.  out: [M, ldo] of out_dtype.  lda/ldr/ldo must be multiples of 8 elements
+ * and all base pointers 16-byte aligned.  backend: TDEED_GEMM_AUTO picks tcgen05 for bf16 and the
+ * exact fp32 CUDA-core kernel for f32. */
+#define TDEED_GEMM_MAX_SEGS 2
+typedef struct {
+  const void* a;
+  long long lda;
+  int col0;
+  int k;
+} tdeed_gemm_seg;
+
+int tdeed_gemm_fwd(int dtype, long long M, int N, int nseg, const tdeed_gemm_seg* segs_host,
+                   int gather_stride, int gather_h, int gather_w,
+                   const void* W, const float* bias,
+                   const void* residual, long long ldr, int res_dtype,
+                   int act, void* out, long long ldo, int out_dtype, int backend, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (3) grouped 3x3 convolution (+folded BN + ReLU): timm Bottleneck conv2, group width 8 / 16,
+ * stride 1 or 2, pad 1.  in: NHWC [n, h, w, c]; weight fp32 [c][group_width][3][3] (torch layout,
+ * BN folded), bias fp32 [c]; out: NHWC [n, ceil(h/stride), ceil(w/stride), c]. */
+int tdeed_conv3x3g_fwd(int dtype, const void* in, int n, int h, int w, int c, int group_width, int stride,
+                       const float* weight, const float* bias, void* out, void* stream);
+
+/* (4) squeeze-excite, in place: x *= sigmoid(fc2(relu(fc1(mean_hw(x))))).  timm SEModule.
+ * x: NHWC [n, hw, c]; w1 [rd][c], b1 [rd], w2 [c][rd], b2 [c] fp32. */
+int tdeed_se_fwd(int dtype, void* x, int n, int hw, int c, int rd,
+                 const float* w1, const float* b1, const float* w2, const float* b2, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (5) Gate-Shift module on the first `fold` channels of x (model/shift.py:64-93):
+ *   GSM  model/impl/gsm.py:89-116, GSF model/impl/gsf.py:38-93  (eval-mode BatchNorm3d folded into
+ *   bn_scale/bn_shift).  x: NHWC [clips*clip_len, h, w, c]; out: [clips*clip_len*h*w, ld_out] holding the
+ *   gate-shifted `fold` channels (channel-interleaved as the reference), ld_out >= fold, multiple of 8.
+ *   conv3d_w fp32 [2][fold/2][3][3][3], conv3d_b [2]; cc_w fp32 [2][2][3][3] = channel_conv1/2 weights,
+ *   cc_b [2] (ignored for GSM).  workspace: fp32, at least tdeed_gsf_workspace_floats(...) elements. */
+long long tdeed_gsf_workspace_floats(int clips, int clip_len, int h, int w, int fold);
+int tdeed_gsf_fwd(int dtype, int mode, const void* x, int clips, int clip_len, int h, int w, int c, int fold,
+                  const float* bn_scale, const float* bn_shift, const float* conv3d_w, const float* conv3d_b,
+                  const float* cc_w, const float* cc_b, float* workspace,
+                  void* out, int ld_out, void* stream);
+
+/* (6) global average pool + positional encoding: feat[f, :] = mean_hw(x[f]) + temp_enc[f % clip_len, :]
+ * (timm head global_pool, model/model.py:133-137).  x: NHWC [n, hw, c]; temp_enc fp32 [clip_len, c];
+ * out fp32 [n, c]. */
+int tdeed_pool_posenc_fwd(int dtype, const void* x, int n, int hw, int c, int clip_len,
+                          const float* temp_enc, float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (7) SGP token mixing (model/modules.py:159-186, everything of SGPBlock.forward before the MLP), on
+ * [B, T, C] fp32 sequences.  If t_in != t_out the input is first AdaptiveMaxPool1d'ed to t_out
+ * (model/modules.py:64,76).  With xp = (pooled) x and ln = LayerNorm_C(xp):
+ *    y = xp + fc(ln)*relu(global_fc(mean_T ln)) + (convw(ln)+convkw(ln))*psi(ln) + ln
+ *    g = GroupNorm16(y)
+ * Depthwise weights fp32: psi_w/convw_w [C][ks], convkw_w [C][up], fc_w/gfc_w [C]; biases [C].
+ * y: fp32 [B, t_out, C];  g: [B, t_out, C] of g_dtype (the MLP's GEMM operand). */
+typedef struct {
+  const float *ln_w, *ln_b, *gn_w, *gn_b;
+  const float *psi_w, *psi_b, *fc_w, *fc_b, *convw_w, *convw_b, *convkw_w, *convkw_b, *gfc_w, *gfc_b;
+} tdeed_sgp_weights;
+int tdeed_sgp_mix_fwd(const float* x, int B, int t_in, int t_out, int C, int ks, int up,
+                      const tdeed_sgp_weights* w_host, float* y, void* g, int g_dtype, void* stream);
+
+/* (8) SGPMixer token mixing (model/modules.py:283-307): z = LN1(skip) [B,T,C], xu =
+ * linear-upsample(align_corners) of LN2(x) [B,t_coarse,C] to T; writes the 6C-wide concat
+ * [out1,out2,out3,out4,z,xu] as [B*T, 6C] of cat_dtype for the concat_fc GEMM. */
+typedef struct {
+  const float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+  const float *psi1_w, *psi1_b, *psi2_w, *psi2_b, *convw1_w, *convw1_b, *convkw1_w, *convkw1_b;
+  const float *convw2_w, *convw2_b, *convkw2_w, *convkw2_b;
+  const float *fc1_w, *fc1_b, *gfc1_w, *gfc1_b, *fc2_w, *fc2_b, *gfc2_w, *gfc2_b;
+} tdeed_mixer_weights;
+int tdeed_sgp_mixer_mix_fwd(const float* x_coarse, const float* skip, int B, int t_coarse, int T, int C,
+                            int ks, int up, const tdeed_mixer_weights* w_host,
+                            void* cat, int cat_dtype, void* stream);
+
+/* (9) GroupNorm(16, C) over [B, T, C] fp32 -> out of out_dtype (model/modules.py:115,186,311). */
+int tdeed_groupnorm_fwd(const float* x, int B, int T, int C, int groups, const float* gamma, const float* beta,
+                        void* out, int out_dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (10) heads + softmax + displacement scatter-max.  Replaces FCLayers/FC2Layers (eval: dropout is
+ * identity; model/modules.py:366-387, model/model.py:141-146), torch.softmax and the B x T Python
+ * loop of process_prediction / process_double_head (model/modules.py:406-426).
+ * feat fp32 [B,T,C]; w_cls fp32 [k_out, C], b_cls [k_out]; w_displ fp32 [C] / b_displ [1] or NULL.
+ * logits fp32 [B,T,k_out]; displ fp32 [B,T] (if w_displ); probs fp32 [B,T,k_softmax]:
+ *   p = softmax(logits[..., :k_softmax]);  probs[b, clamp(t - rint(displ[b,t]), 0, T-1)] = max(., p[b,t])
+ *   (plain softmax when w_displ is NULL). */
+int tdeed_heads_fwd(const float* feat, int B, int T, int C, const float* w_cls, const float* b_cls, int k_out,
+                    const float* w_displ, const float* b_displ, int k_softmax,
+                    float* logits, float* displ, float* probs, void* stream);
+
+/* (10b) process_prediction / process_double_head on precomputed logits (model/modules.py:406-426):
+ * probs[b, clamp(t - rint(displ[b,t]), 0, T-1)] = max(., softmax(logits[b,t,:k_softmax]));  displ may be
+ * NULL (plain softmax).  logits fp32 [B,T,ld_logits]; probs fp32 [B,T,k_softmax]. */
+int tdeed_softmax_scatter_fwd(const float* logits, int ld_logits, const float* displ, int B, int T,
+                              int k_softmax, float* probs, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * (11) per-video post-processing, bit-exact with util/eval.py.
+ * clip_accumulate (util/eval.py:303-349): for clips i = 0..n_clips-1 IN ORDER,
+ *   scores[start_i + t] += pred[i, t];  support += (rowsum != 0) [mode 0, batched path]  or += 1 [mode 1,
+ *   TTA path]; rows before frame 0 / past video_len are dropped.  pred fp32 [n_clips, T, K]; starts i32. */
+int tdeed_clip_accumulate(float* scores, int* support, int video_len, int K,
+                          const float* pred, const int* starts, int n_clips, int T, int mode, void* stream);
+
+/* extract (util/eval.py:87-193): support==0 -> 1; scores /= support; pred = argmax; events = frames with
+ * pred != 0; high-recall events = every (frame, class>=1) with score >= threshold (fp32 compare),
+ * frame-major then class order.  counts_out i32 [2] = {n_events, n_high_recall}.  Capacities:
+ * ev_* video_len entries, hr_* video_len*(K-1) entries. */
+int tdeed_extract_events(float* scores, int* support, int video_len, int K, float threshold,
+                         int* pred, int* ev_frame, int* ev_label, float* ev_score,
+                         int* hr_frame, int* hr_label, float* hr_score, int* counts_out, void* stream);
+
+/* (soft-)NMS of one video's event list (util/eval.py:195-261).  Input events must be in the
+ * reference's frame-major order with at most one event per (frame, label); labels in [1, K).
+ * n_events_dev points to the device-side event count (e.g. counts_out+1 of tdeed_extract_events), so
+ * no host round trip is needed; capacity bounds the arrays.  soft=0: hard NMS, out_score holds the
+ * fp32 scores widened to f64;  soft=1: quadratic-decay soft NMS in f64 exactly as the reference.
+ * threshold is compared in double (util/eval.py:213,247).  Output is sorted by frame, ties in the
+ * reference's label-bucket (first-appearance) order; out_count i32 [1].
+ * workspace: bytes >= tdeed_nms_workspace_bytes(capacity, K). */
+long long tdeed_nms_workspace_bytes(int capacity, int K);
+int tdeed_nms(const int* frame, const int* label, const float* score, const int* n_events_dev, int capacity,
+              int K, int window, double threshold, int soft, void* workspace,
+              int* out_frame, int* out_label, double* out_score, int* out_count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDEED_B200_H_ */

@@ -1,0 +1,54 @@
+// tdeed_gemm_fwd: backend selection between the exact CUDA-core kernel and the tcgen05 kernel.
+#include "common.cuh"
+
+namespace tdeed {
+struct SimtSegs {
+  const void* a[TDEED_GEMM_MAX_SEGS];
+  long long lda[TDEED_GEMM_MAX_SEGS];
+  int col0[TDEED_GEMM_MAX_SEGS];
+  int k[TDEED_GEMM_MAX_SEGS];
+  int nseg;
+};
+int gemm_simt_launch(int dtype, long long M, int N, int K, const SimtSegs& segs, int gstride, int gh, int gw,
+                     const void* W, const float* bias, const void* residual, long long ldr, int res_dtype,
+                     int act, void* out, long long ldo, int out_dtype, cudaStream_t st);
+int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* segs, const void* W, const float* bias,
+                   const void* residual, long long ldr, int res_dtype, int act, void* out, long long ldo,
+                   int out_dtype, cudaStream_t st);
+}  // namespace tdeed
+
+extern "C" int tdeed_gemm_fwd(int dtype, long long M, int N, int nseg, const tdeed_gemm_seg* segs,
+                              int gather_stride, int gather_h, int gather_w,
+                              const void* W, const float* bias,
+                              const void* residual, long long ldr, int res_dtype,
+                              int act, void* out, long long ldo, int out_dtype, int backend, void* stream) {
+  using namespace tdeed;
+  TDEED_REQUIRE(segs && W && out, TDEED_ERR_SHAPE, "tdeed_gemm_fwd: null pointer");
+  TDEED_REQUIRE(nseg >= 1 && nseg <= TDEED_GEMM_MAX_SEGS, TDEED_ERR_SHAPE, "tdeed_gemm_fwd: nseg=%d", nseg);
+  TDEED_REQUIRE(dtype == TDEED_F32 || dtype == TDEED_BF16, TDEED_ERR_UNSUPPORTED, "tdeed_gemm_fwd: dtype %d", dtype);
+  TDEED_REQUIRE(M > 0 && N > 0 && N % 8 == 0 && ldo % 8 == 0 && ldo >= N, TDEED_ERR_SHAPE,
+                "tdeed_gemm_fwd: M=%lld N=%d ldo=%lld (N, ldo must be multiples of 8)", M, N, ldo);
+  TDEED_REQUIRE(!residual || (ldr % 8 == 0 && ldr >= N), TDEED_ERR_SHAPE, "tdeed_gemm_fwd: ldr=%lld", ldr);
+  int K = 0;
+  SimtSegs ss{};
+  ss.nseg = nseg;
+  for (int s = 0; s < nseg; ++s) {
+    TDEED_REQUIRE(segs[s].a && segs[s].k > 0 && segs[s].k % 4 == 0 && segs[s].col0 % 4 == 0 &&
+                  segs[s].lda >= segs[s].col0 + segs[s].k, TDEED_ERR_SHAPE,
+                  "tdeed_gemm_fwd: segment %d (col0=%d k=%d lda=%lld) must be 4-aligned and in range", s,
+                  segs[s].col0, segs[s].k, segs[s].lda);
+    ss.a[s] = segs[s].a; ss.lda[s] = segs[s].lda; ss.col0[s] = segs[s].col0; ss.k[s] = segs[s].k;
+    K += segs[s].k;
+  }
+  TDEED_REQUIRE(gather_stride <= 1 || (gather_h > 0 && gather_w > 0 && nseg == 1), TDEED_ERR_SHAPE,
+                "tdeed_gemm_fwd: gather needs one segment and a geometry");
+  cudaStream_t st = (cudaStream_t)stream;
+  bool use_tc = (backend == TDEED_GEMM_TCGEN05) || (backend == TDEED_GEMM_AUTO && dtype == TDEED_BF16 && gather_stride <= 1 && K % 8 == 0);
+  if (use_tc) {
+    TDEED_REQUIRE(dtype == TDEED_BF16 && gather_stride <= 1, TDEED_ERR_UNSUPPORTED,
+                  "tdeed_gemm_fwd: the tcgen05 backend needs bf16 operands and no gather");
+    return gemm_tc_launch(M, N, K, nseg, segs, W, bias, residual, ldr, res_dtype, act, out, ldo, out_dtype, st);
+  }
+  return gemm_simt_launch(dtype, M, N, K, ss, gather_stride, gather_h, gather_w, W, bias, residual, ldr, res_dtype,
+                          act, out, ldo, out_dtype, st);
+}

@@ -1,0 +1,276 @@
+"""Drop-in for the reference's model/model.py: same entry points (TDEEDModel, TDEEDModel.Impl,
+update_labels_2heads), same constructor arguments, same state_dict layout — so the reference's
+train_tdeed.py / evaluate_tdeed_challenge.py / util/eval.py run unchanged with this package first
+on sys.path — while Impl.forward runs as hand-written sm_100a kernels (libtdeed_sm100.so through
+tdeed_b200.InferenceEngine).  There is no PyTorch / CPU fallback: without the built library or a
+CUDA device, forward raises.
+"""
+import random
+from contextlib import nullcontext
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+from torch import nn
+from tqdm import tqdm
+
+from model import regnet
+from model.modules import (BaseRGBModel, EDSGPMIXERLayers, FCLayers, FC2Layers, step, process_prediction,
+                           process_double_head, process_labels)
+from model.shift import make_temporal_shift
+from tdeed_b200.engine import EngineConfig, InferenceEngine
+
+
+class TDEEDModel(BaseRGBModel):
+
+    class Impl(nn.Module):
+
+        def __init__(self, args=None):
+            super().__init__()
+            self._modality = args.modality
+            assert self._modality == 'rgb', 'Only RGB supported for now'
+            self._temp_arch = args.temporal_arch
+            assert self._temp_arch in ['ed_sgp_mixer'], 'Only ed_sgp_mixer supported for now'
+            self._radi_displacement = args.radi_displacement
+            self._feature_arch = args.feature_arch
+            assert 'rny' in self._feature_arch, 'Only rny supported for now'
+            self._double_head = False
+            self._args = args
+
+            if self._feature_arch.startswith(('rny002', 'rny008')):
+                features = regnet.create_model({
+                    'rny002': 'regnety_002',
+                    'rny008': 'regnety_008',
+                }[self._feature_arch.rsplit('_', 1)[0]], pretrained=True)
+                feat_dim = features.head.fc.in_features
+                features.head.fc = nn.Identity()
+                self._d = feat_dim
+            else:
+                raise NotImplementedError(args._feature_arch)
+
+            self._require_clip_len = -1
+            if self._feature_arch.endswith('_gsm'):
+                make_temporal_shift(features, args.clip_len, mode='gsm')
+                self._require_clip_len = args.clip_len
+            elif self._feature_arch.endswith('_gsf'):
+                make_temporal_shift(features, args.clip_len, mode='gsf')
+                self._require_clip_len = args.clip_len
+
+            self._features = features
+            self._feat_dim = self._d
+            self.temp_enc = nn.Parameter(torch.normal(mean=0, std=1 / args.clip_len, size=(args.clip_len, self._d)))
+            if self._temp_arch == 'ed_sgp_mixer':
+                self._temp_fine = EDSGPMIXERLayers(self._d, args.clip_len, num_layers=args.n_layers, ks=args.sgp_ks,
+                                                   k=args.sgp_r, concat=True)
+                self._pred_fine = FCLayers(self._feat_dim, args.num_classes + 1)
+            else:
+                raise NotImplementedError(self._temp_arch)
+            if self._radi_displacement > 0:
+                self._pred_displ = FCLayers(self._feat_dim, 1)
+
+            self.croping = args.crop_dim
+            self._engines = {}
+            self._engine_versions = {}
+
+        # ---- engine management -------------------------------------------------------------
+        def engine_config(self):
+            a = self._args
+            dh = None
+            if self._double_head:
+                dh = [self._pred_fine._fc1._fc_out.out_features, self._pred_fine._fc2._fc_out.out_features]
+            return EngineConfig(self._feature_arch, a.clip_len, a.n_layers, a.sgp_ks, a.sgp_r, a.num_classes,
+                                self._radi_displacement, self.croping, double_head=dh)
+
+        def _weights_version(self):
+            """Cheap change detector: in-place updates (optimizer.step, load_state_dict) bump Tensor._version."""
+            tr = self.__dict__.get('_tracked')
+            if tr is None:
+                tr = list(self.parameters()) + list(self.buffers())
+                self.__dict__['_tracked'] = tr
+            return sum(t._version for t in tr) + (1 << 40) * int(self._double_head)
+
+        def engine(self, precision):
+            """InferenceEngine for the current weights ('bf16' | 'fp32'); re-prepared when parameters changed."""
+            dev = self.temp_enc.device
+            if dev.type != 'cuda':
+                raise RuntimeError('tdeed_b200 has no CPU path: move the model to a CUDA device (got %s)' % dev)
+            ver = self._weights_version()
+            eng = self._engines.get(precision)
+            if eng is None:
+                eng = InferenceEngine(self.engine_config(), self.state_dict(), device=dev, precision=precision)
+                self._engines[precision] = eng
+            elif self._engine_versions.get(precision) != ver:
+                eng.cfg = self.engine_config()
+                eng.load_state(self.state_dict())
+            self._engine_versions[precision] = ver
+            return eng
+
+        # ---- forward -------------------------------------------------------------------------
+        def forward(self, x, y=None, inference=False, augment_inference=False, use_graph=False):
+            """x: (B, T, 3, H, W) valued 0..255 (uint8 or float).  Returns what the reference returns:
+            ({'im_feat': logits, 'displ_feat': displ}, y) when radi_displacement > 0 else (logits, y)."""
+            if not inference:
+                raise NotImplementedError(
+                    'tdeed_b200: the training forward/backward path (sm_100a backward kernels) is not built yet; '
+                    'inference (inference=True / predict / epoch(optimizer=None)) is')
+            precision = 'bf16' if torch.is_autocast_enabled() else 'fp32'
+            eng = self.engine(precision)
+            if x.dtype not in (torch.uint8, torch.float32):
+                x = x.float()
+            x = x.contiguous()
+            fwd = eng.forward_graphed if use_graph else eng.forward
+            logits, displ, probs = fwd(x, flip=augment_inference)
+            self._last_probs = probs
+            if self._radi_displacement > 0:
+                return {'im_feat': logits, 'displ_feat': displ}, y
+            return logits, y
+
+        def update_pred_head(self, num_classes=[1, 1]):
+            self._pred_fine = FC2Layers(self._feat_dim, num_classes).to(self.temp_enc.device)
+            self._double_head = True
+            self._engines.clear()
+            self.__dict__.pop('_tracked', None)
+
+        def print_stats(self):
+            print('Model params:', sum(p.numel() for p in self.parameters()))
+            print('  CNN features:', sum(p.numel() for p in self._features.parameters()))
+            print('  Temporal:', sum(p.numel() for p in self._temp_fine.parameters()))
+            print('  Head:', sum(p.numel() for p in self._pred_fine.parameters()))
+
+    def __init__(self, device='cuda', args=None):
+        self.device = device
+        self._model = TDEEDModel.Impl(args=args)
+        self._model.print_stats()
+        self._args = args
+        self._model.to(device)
+        self._num_classes = args.num_classes + 1
+
+    def epoch(self, loader, optimizer=None, scaler=None, lr_scheduler=None, acc_grad_iter=1, fg_weight=5,
+              valMAP=False):
+        """Same contract as the reference (model/model.py:193-332).  Evaluation (optimizer=None) runs on the
+        sm_100a inference engine; the loss glue (cross-entropy / MSE on (B*T, K) logits) is host-side torch."""
+        if optimizer is None:
+            inference = True
+            self._model.eval()
+        else:
+            inference = False
+            optimizer.zero_grad()
+            self._model.train()
+
+        if valMAP:
+            map_labels = []
+            map_preds = []
+
+        ce_kwargs = {}
+        if fg_weight != 1:
+            ce_kwargs['weight'] = torch.FloatTensor([1] + [fg_weight] * (self._num_classes - 1)).to(self.device)
+
+        epoch_loss = 0.
+        with torch.no_grad() if optimizer is None else nullcontext():
+            for batch_idx, batch in enumerate(tqdm(loader)):
+                frame = batch['frame'].to(self.device)          # kept uint8: the stem kernel normalises
+                label = batch['label'].to(self.device)
+
+                if self._model._double_head:
+                    batch_dataset = batch['dataset']
+                    label = update_labels_2heads(label, batch_dataset, self._args.num_classes)
+
+                if 'labelD' in batch.keys():
+                    labelD = batch['labelD'].to(self.device).float()
+
+                if 'frame2' in batch.keys():
+                    frame = frame.float()
+                    frame2 = batch['frame2'].to(self.device).float()
+                    label2 = batch['label2'].to(self.device)
+                    if 'labelD2' in batch.keys():
+                        labelD2 = batch['labelD2'].to(self.device).float()
+                        labelD_dist = torch.zeros((labelD.shape[0], label.shape[1])).to(self.device)
+                    l = [random.betavariate(0.2, 0.2) for _ in range(frame2.shape[0])]
+                    label_dist = torch.zeros((label.shape[0], label.shape[1], self._num_classes)).to(self.device)
+                    for i in range(frame2.shape[0]):
+                        frame[i] = l[i] * frame[i] + (1 - l[i]) * frame2[i]
+                        label_dist[i, range(label.shape[1]), label[i]] += l[i]
+                        label_dist[i, range(label2.shape[1]), label2[i]] += 1 - l[i]
+                        if 'labelD2' in batch.keys():
+                            labelD_dist[i] = l[i] * labelD[i] + (1 - l[i]) * labelD2[i]
+                    label = label_dist
+                    if 'labelD2' in batch.keys():
+                        labelD = labelD_dist
+
+                if valMAP:
+                    labels_aux = process_labels(label, labelD if 'labelD' in batch.keys() else None,
+                                                num_classes=self._num_classes)
+                    map_labels.append(labels_aux.cpu())
+
+                label = label.flatten() if len(label.shape) == 2 else label.view(-1, label.shape[-1])
+
+                with torch.autocast('cuda', dtype=torch.bfloat16):
+                    pred, y = self._model(frame, y=label, inference=inference)
+
+                if 'labelD' in batch.keys():
+                    predD = pred['displ_feat']
+                    pred = pred['im_feat']
+
+                if valMAP:
+                    pred_aux = process_prediction(pred, predD)
+                    map_preds.append(pred_aux.cpu())
+
+                loss = 0.
+                if self._model._double_head:
+                    b, t, c = pred.shape
+                    if len(label.shape) == 2:
+                        label = label.view(b, t, c)
+                    if len(label.shape) == 1:
+                        label = label.view(b, t)
+                    n1 = self._args.num_classes + 1
+                    for i in range(pred.shape[0]):
+                        if batch_dataset[i] == 1:
+                            aux_label = label[i][:, :n1] if len(label.shape) == 3 else label[i]
+                            loss += F.cross_entropy(pred[i][:, :n1], aux_label, weight=ce_kwargs['weight'][:n1]) / pred.shape[0]
+                        elif batch_dataset[i] == 2:
+                            aux_label = label[i][:, n1:] if len(label.shape) == 3 else label[i] - n1
+                            loss += F.cross_entropy(pred[i][:, n1:], aux_label,
+                                                    weight=ce_kwargs['weight'][:self._args.pretrain['num_classes'] + 1]) / pred.shape[0]
+                else:
+                    loss += F.cross_entropy(pred.reshape(-1, self._num_classes), label, **ce_kwargs)
+
+                if 'labelD' in batch.keys():
+                    loss = loss + F.mse_loss(predD, labelD, reduction='none').mean()
+
+                if optimizer is not None:
+                    step(optimizer, scaler, loss / acc_grad_iter, lr_scheduler=lr_scheduler,
+                         backward_only=(batch_idx + 1) % acc_grad_iter != 0)
+
+                epoch_loss += loss.detach().item()
+
+        if valMAP:
+            return epoch_loss / len(loader), torch.cat(map_labels, 0), torch.cat(map_preds, 0)
+        return epoch_loss / len(loader)
+
+    def predict(self, seq, use_amp=True, augment_inference=False, use_graph=True):
+        """(L,C,H,W) or (B,L,C,H,W) frames valued 0..255 -> (argmax (B,T) int64, probs (B,T,K) float32) ndarrays.
+        use_amp=True runs the bf16 tensor-core engine (the reference: fp16 autocast), False the exact fp32 one.
+        uint8 input is uploaded as uint8 (4x less H2D than the reference's float path) and normalised in the stem kernel."""
+        if not isinstance(seq, torch.Tensor):
+            seq = torch.as_tensor(np.asarray(seq))
+        if len(seq.shape) == 4:
+            seq = seq.unsqueeze(0)
+        if seq.dtype not in (torch.uint8, torch.float32):
+            seq = seq.float()
+        if seq.device.type != 'cuda':
+            seq = seq.to(self.device, non_blocking=True)
+
+        self._model.eval()
+        with torch.no_grad():
+            with torch.autocast('cuda', dtype=torch.bfloat16) if use_amp else nullcontext():
+                self._model(seq, inference=True, augment_inference=augment_inference, use_graph=use_graph)
+            # softmax (+ displacement scatter-max over the first head) is fused into the heads kernel
+            pred = self._model._last_probs.cpu().numpy()
+        return np.argmax(pred, axis=2), pred
+
+
+def update_labels_2heads(labels, datasets, num_classes1=1):
+    for i in range(len(datasets)):
+        if datasets[i] == 2:
+            labels[i] = labels[i] + num_classes1 + 1
+    return labels

@@ -1,0 +1,351 @@
+"""Inference engine: T-DEED's Impl.forward(inference=True) (model/model.py:105-149 of the reference)
+as a fixed sequence of libtdeed_sm100 kernel launches.
+
+Host responsibilities (Python, as the north star prescribes): fold eval-mode BatchNorm into the
+conv weights, lay weights out for the kernels (1x1 convs as K-major [N, K] matrices, bf16 for the
+tcgen05 path), own device buffers, issue launches on the current stream, and optionally capture
+the whole forward in a CUDA graph (static shapes: B clips x T frames x H x W).
+
+precision: 'bf16' = bf16 activations/weights in the backbone and for every GEMM operand, fp32
+accumulation, fp32 SGP residual stream (the reference runs fp16 autocast); 'fp32' = exact fp32
+CUDA-core path used for 1e-3 parity against the reference's fp32 forward.
+"""
+import math
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+REGNET = {
+    'rny002': dict(widths=[24, 56, 152, 368], depths=[1, 1, 4, 7], group_width=8),
+    'rny008': dict(widths=[64, 128, 320, 768], depths=[1, 3, 8, 2], group_width=16),
+}
+
+
+def fold_dim(channels, n_div=4):
+    """model/shift.py:79 of the reference."""
+    return math.ceil(channels // n_div / 4) * 4
+
+
+def sgp_up_size(ks, k):
+    """model/modules.py:119-120 of the reference."""
+    up = round((ks + 1) * k)
+    return up + 1 if up % 2 == 0 else up
+
+
+def center_crop_offsets(h, w, crop):
+    """torchvision CenterCrop offsets (model/model.py:100,124)."""
+    return int(round((h - crop) / 2.0)), int(round((w - crop) / 2.0))
+
+
+def _round8(v):
+    return (v + 7) // 8 * 8
+
+
+class EngineConfig:
+    def __init__(self, feature_arch, clip_len, n_layers, sgp_ks, sgp_r, num_classes, radi_displacement, crop_dim,
+                 double_head=None):
+        self.backbone, self.shift_mode = feature_arch.rsplit('_', 1) if '_' in feature_arch else (feature_arch, None)
+        if self.backbone not in REGNET:
+            raise NotImplementedError(feature_arch)
+        self.clip_len = clip_len
+        self.n_layers = n_layers
+        self.sgp_ks = sgp_ks
+        self.sgp_up = sgp_up_size(sgp_ks, sgp_r)
+        self.num_classes = num_classes
+        self.radi_displacement = radi_displacement
+        self.crop_dim = crop_dim if (crop_dim is not None and crop_dim > 0) else None
+        self.double_head = list(double_head) if double_head else None
+        self.feat_dim = REGNET[self.backbone]['widths'][-1]
+
+    def blocks(self):
+        r = REGNET[self.backbone]
+        prev = 32
+        for si, (w, d) in enumerate(zip(r['widths'], r['depths'])):
+            for bi in range(d):
+                yield ('_features.s%d.b%d' % (si + 1, bi + 1), prev if bi == 0 else w, w, 2 if bi == 0 else 1,
+                       si >= 2 and self.shift_mode in ('gsm', 'gsf'))
+            prev = w
+
+
+def _bn_fold(sd, p, eps=1e-5):
+    scale = sd[p + '.weight'].float() / torch.sqrt(sd[p + '.running_var'].float() + eps)
+    shift = sd[p + '.bias'].float() - sd[p + '.running_mean'].float() * scale
+    return scale, shift
+
+
+class InferenceEngine:
+    """Prepared weights + launch sequence.  `state` is a state_dict with the reference's key names."""
+
+    def __init__(self, cfg, state, device='cuda', precision='bf16', gemm_backend=L.GEMM_AUTO):
+        if not torch.cuda.is_available():
+            raise RuntimeError('tdeed_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+        L.load()
+        assert precision in ('bf16', 'fp32')
+        self.cfg = cfg
+        self.device = torch.device(device)
+        self.precision = precision
+        self.act_dtype = torch.bfloat16 if precision == 'bf16' else torch.float32
+        self.gemm_backend = gemm_backend
+        self.launches = 0
+        self.prof = None
+        self._graphs = {}
+        self.load_state(state)
+
+    # ------------------------------------------------------------------ weights
+    def load_state(self, state):
+        cfg, dev, adt = self.cfg, self.device, self.act_dtype
+        sd = {k: v.detach().to(dev) for k, v in state.items()}
+        f32 = lambda t: t.float().contiguous()
+        W = {}
+        sc, sh = _bn_fold(sd, '_features.stem.bn')
+        W['stem_w'] = f32(sd['_features.stem.conv.weight'].float() * sc[:, None, None, None])
+        W['stem_b'] = f32(sh)
+        gw = REGNET[cfg.backbone]['group_width']
+        blocks = []
+        for p, cin, cout, stride, shifted in cfg.blocks():
+            b = dict(cin=cin, cout=cout, stride=stride, shifted=shifted, gw=gw)
+            c1 = p + ('.conv1.net' if shifted else '.conv1')
+            sc, sh = _bn_fold(sd, c1 + '.bn')
+            b['w1'] = (sd[c1 + '.conv.weight'].float().reshape(cout, cin) * sc[:, None]).to(adt).contiguous()
+            b['b1'] = f32(sh)
+            sc, sh = _bn_fold(sd, p + '.conv2.bn')
+            b['w2'] = f32(sd[p + '.conv2.conv.weight'].float() * sc[:, None, None, None])
+            b['b2'] = f32(sh)
+            rd = sd[p + '.se.fc1.weight'].shape[0]
+            b['se_w1'] = f32(sd[p + '.se.fc1.weight'].reshape(rd, cout))
+            b['se_b1'] = f32(sd[p + '.se.fc1.bias'])
+            b['se_w2'] = f32(sd[p + '.se.fc2.weight'].reshape(cout, rd))
+            b['se_b2'] = f32(sd[p + '.se.fc2.bias'])
+            sc, sh = _bn_fold(sd, p + '.conv3.bn')
+            b['w3'] = (sd[p + '.conv3.conv.weight'].float().reshape(cout, cout) * sc[:, None]).to(adt).contiguous()
+            b['b3'] = f32(sh)
+            if (p + '.downsample.conv.weight') in sd:
+                sc, sh = _bn_fold(sd, p + '.downsample.bn')
+                b['wd'] = (sd[p + '.downsample.conv.weight'].float().reshape(cout, cin) * sc[:, None]).to(adt).contiguous()
+                b['bd'] = f32(sh)
+            if shifted:
+                g = p + '.conv1.gs'
+                fd = fold_dim(cin)
+                sc, sh = _bn_fold(sd, g + '.bn')
+                gs = dict(fold=fd, bn_scale=f32(sc), bn_shift=f32(sh), w3d=f32(sd[g + '.conv3D.weight'].reshape(-1)),
+                          b3d=f32(sd[g + '.conv3D.bias']))
+                if cfg.shift_mode == 'gsf':
+                    gs['cc_w'] = f32(torch.cat([sd[g + '.channel_conv1.weight'].reshape(-1),
+                                                sd[g + '.channel_conv2.weight'].reshape(-1)]))
+                    gs['cc_b'] = f32(torch.cat([sd[g + '.channel_conv1.bias'], sd[g + '.channel_conv2.bias']]))
+                b['gs'] = gs
+            blocks.append(b)
+        W['blocks'] = blocks
+        W['temp_enc'] = f32(sd['temp_enc'])
+        d = cfg.feat_dim
+
+        def dw(name):
+            return f32(sd[name + '.weight'].reshape(d, -1)), f32(sd[name + '.bias'])
+
+        def mlp(p):
+            return dict(w1=sd[p + '.mlp.0.weight'].reshape(4 * d, d).to(adt).contiguous(), b1=f32(sd[p + '.mlp.0.bias']),
+                        w2=sd[p + '.mlp.2.weight'].reshape(d, 4 * d).to(adt).contiguous(), b2=f32(sd[p + '.mlp.2.bias']))
+
+        sgp = []
+        for i in range(2 * cfg.n_layers + 1):
+            p = '_temp_fine._sgp.%d' % i
+            w = dict(ln_w=f32(sd[p + '.ln.weight'].reshape(d)), ln_b=f32(sd[p + '.ln.bias'].reshape(d)),
+                     gn_w=f32(sd[p + '.gn.weight']), gn_b=f32(sd[p + '.gn.bias']))
+            for n, key in (('psi', 'psi'), ('fc', 'fc'), ('convw', 'convw'), ('convkw', 'convkw'), ('gfc', 'global_fc')):
+                w[n + '_w'], w[n + '_b'] = dw(p + '.' + key)
+            sgp.append(dict(mix=w, mlp=mlp(p)))
+        W['sgp'] = sgp
+        mixers = []
+        for i in range(cfg.n_layers):
+            p = '_temp_fine._sgpMixer.%d' % i
+            w = dict(ln1_w=f32(sd[p + '.ln1.weight'].reshape(d)), ln1_b=f32(sd[p + '.ln1.bias'].reshape(d)),
+                     ln2_w=f32(sd[p + '.ln2.weight'].reshape(d)), ln2_b=f32(sd[p + '.ln2.bias'].reshape(d)))
+            for n, key in (('psi1', 'psi1'), ('psi2', 'psi2'), ('convw1', 'convw1'), ('convkw1', 'convkw1'),
+                           ('convw2', 'convw2'), ('convkw2', 'convkw2'), ('fc1', 'fc1'), ('gfc1', 'global_fc1'),
+                           ('fc2', 'fc2'), ('gfc2', 'global_fc2')):
+                w[n + '_w'], w[n + '_b'] = dw(p + '.' + key)
+            mixers.append(dict(mix=w, mlp=mlp(p), gn_w=f32(sd[p + '.gn.weight']), gn_b=f32(sd[p + '.gn.bias']),
+                               wc=sd[p + '.concat_fc.weight'].reshape(d, 6 * d).to(adt).contiguous(),
+                               bc=f32(sd[p + '.concat_fc.bias'])))
+        W['mixers'] = mixers
+        if cfg.double_head:
+            W['cls_w'] = f32(torch.cat([sd['_pred_fine._fc1._fc_out.weight'], sd['_pred_fine._fc2._fc_out.weight']]))
+            W['cls_b'] = f32(torch.cat([sd['_pred_fine._fc1._fc_out.bias'], sd['_pred_fine._fc2._fc_out.bias']]))
+        else:
+            W['cls_w'] = f32(sd['_pred_fine._fc_out.weight'])
+            W['cls_b'] = f32(sd['_pred_fine._fc_out.bias'])
+        if cfg.radi_displacement > 0:
+            W['displ_w'] = f32(sd['_pred_displ._fc_out.weight'].reshape(-1))
+            W['displ_b'] = f32(sd['_pred_displ._fc_out.bias'])
+        else:
+            W['displ_w'] = W['displ_b'] = None
+        self.W = W
+        self._graphs.clear()
+
+    # ------------------------------------------------------------------ forward
+    def _op(self, label, flops, nbytes, fn, *a, **k):
+        """Launch one kernel family; when self.prof is a list, bracket it with CUDA events and record the
+        algorithmic FLOPs / bytes for bench.py."""
+        self.launches += k.pop('_n', 1)
+        if self.prof is None:
+            return fn(*a, **k)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        out = fn(*a, **k)
+        e1.record()
+        self.prof.append((label, flops, nbytes, e0, e1))
+        return out
+
+    def _gemm(self, segs, w, bias=None, label='gemm', **k):
+        rows = k['rows']
+        n, kk = w.shape
+        es = w.element_size()
+        out_es = 4 if k.get('out_dtype') == torch.float32 else es
+        nbytes = rows * kk * es + n * kk * es + rows * n * out_es + (rows * n * k['residual'].element_size() if k.get('residual') is not None else 0)
+        return self._op(label, 2.0 * rows * n * kk, nbytes, ops.gemm, segs, w, bias, backend=self.gemm_backend, **k)
+
+    def crop_window(self, in_h, in_w):
+        if self.cfg.crop_dim is None:
+            return 0, 0, in_h, in_w
+        cy, cx = center_crop_offsets(in_h, in_w, self.cfg.crop_dim)
+        return cy, cx, self.cfg.crop_dim, self.cfg.crop_dim
+
+    def backbone(self, frames, flip=False, crop=None, taps=None):
+        """frames (B,T,3,H,W) u8|f32 on device -> feat (B*T, d) fp32 (pooled + temp_enc)."""
+        cfg, W, adt = self.cfg, self.W, self.act_dtype
+        b, t = frames.shape[:2]
+        n = b * t
+        in_h, in_w = frames.shape[-2:]
+        crop = crop or self.crop_window(in_h, in_w)
+        es = 2 if adt == torch.bfloat16 else 4
+        oh0, ow0 = (crop[2] + 1) // 2, (crop[3] + 1) // 2
+        x = self._op('stem', 2.0 * n * oh0 * ow0 * 32 * 27, n * (3 * crop[2] * crop[3] * frames.element_size() + oh0 * ow0 * 32 * es),
+                     ops.stem, frames.reshape(n, 3, in_h, in_w), crop, flip, W['stem_w'], W['stem_b'], adt)
+        if taps is not None:
+            taps['stem'] = x
+        for bi, blk in enumerate(W['blocks']):
+            _, h, w, cin = x.shape
+            cout, stride = blk['cout'], blk['stride']
+            m = n * h * w
+            if blk['shifted']:
+                gs = blk['gs']
+                fd = gs['fold']
+                ws = torch.empty(ops.gsf_workspace_floats(b, t, h, w, fd), dtype=torch.float32, device=x.device)
+                gso = torch.empty((m, _round8(fd)), dtype=adt, device=x.device)
+                self._op('gsf', 2.0 * m * 27 * fd, m * fd * es * 2, ops.gsf, x, b, t, fd,
+                         L.SHIFT_GSF if cfg.shift_mode == 'gsf' else L.SHIFT_GSM, gs, ws, gso,
+                         _n=3 if cfg.shift_mode == 'gsf' else 2)
+                segs = [(gso, gso.shape[1], 0, fd), (x, cin, fd, cin - fd)]
+            else:
+                segs = [(x, cin, 0, cin)]
+            a1 = self._gemm(segs, blk['w1'], blk['b1'], label='conv1x1', act=L.ACT_RELU, rows=m).view(n, h, w, cout)
+            oh, ow = (h + stride - 1) // stride, (w + stride - 1) // stride
+            mo = n * oh * ow
+            a2 = self._op('conv3x3g', 2.0 * mo * cout * 9 * blk['gw'], (m + mo) * cout * es + cout * 9 * blk['gw'] * 4,
+                          ops.conv3x3g, a1, blk['w2'], blk['b2'], blk['gw'], stride)
+            self._op('se', 4.0 * n * cout * blk['se_w1'].shape[0], 2 * mo * cout * es,
+                     ops.se_, a2, blk['se_w1'], blk['se_b1'], blk['se_w2'], blk['se_b2'])
+            if 'wd' in blk:
+                res = self._gemm([(x, cin, 0, cin)], blk['wd'], blk['bd'], label='conv1x1_ds', rows=mo,
+                                 gather=(stride, h, w) if stride > 1 else None)
+            else:
+                res = x.view(mo, cout)
+            x = self._gemm([(a2.view(mo, cout), cout, 0, cout)], blk['w3'], blk['b3'], label='conv1x1', residual=res,
+                           act=L.ACT_RELU, rows=mo).view(n, oh, ow, cout)
+            if taps is not None:
+                taps['s%d.b%d' % (self._stage_of(bi))] = x
+        hw = x.shape[1] * x.shape[2]
+        return self._op('pool_posenc', float(n * hw * x.shape[3]), n * hw * x.shape[3] * es + n * x.shape[3] * 4,
+                        ops.pool_posenc, x, t, W['temp_enc'])
+
+    def _stage_of(self, bi):
+        depths = REGNET[self.cfg.backbone]['depths']
+        s = 0
+        while bi >= depths[s]:
+            bi -= depths[s]
+            s += 1
+        return s + 1, bi + 1
+
+    def _mlp(self, g, y, p, rows):
+        h = self._gemm([(g.view(rows, -1), g.shape[-1], 0, g.shape[-1])], p['w1'], p['b1'], label='sgp_gemm',
+                       act=L.ACT_GELU, rows=rows)
+        return self._gemm([(h, h.shape[1], 0, h.shape[1])], p['w2'], p['b2'], label='sgp_gemm', residual=y.view(rows, -1),
+                          rows=rows, out_dtype=torch.float32)
+
+    def _sgp_block(self, x, t_out, p):
+        cfg = self.cfg
+        b, _, d = x.shape
+        y, g = self._op('sgp_mix', 2.0 * b * t_out * d * (2 * cfg.sgp_ks + cfg.sgp_up + 2), b * d * (x.shape[1] * 4 + t_out * 6),
+                        ops.sgp_mix, x, t_out, cfg.sgp_ks, cfg.sgp_up, p['mix'], self.act_dtype)
+        return self._mlp(g, y, p['mlp'], b * t_out).view(b, t_out, d)
+
+    def temporal(self, feat):
+        """(B,T,d) fp32 -> (B,T,d) fp32: EDSGPMIXERLayers.forward (model/modules.py:69-87)."""
+        cfg, W = self.cfg, self.W
+        b, t, d = feat.shape
+        L_ = cfg.n_layers
+        lens = [math.ceil(t / 2 ** i) for i in range(L_ + 1)]
+        x = feat
+        skips = []
+        for i in range(L_):
+            x = self._sgp_block(x, lens[i], W['sgp'][i])     # pooling of the previous level is fused here
+            skips.append(x)
+        x = self._sgp_block(x, lens[L_], W['sgp'][L_])
+        for i in range(L_):
+            j = L_ - 1 - i
+            mp = W['mixers'][j]
+            rows = b * lens[j]
+            cat = self._op('sgp_mix', 4.0 * rows * d * (2 * cfg.sgp_ks + cfg.sgp_up + 2), rows * d * (6 + 12),
+                           ops.sgp_mixer_mix, x, skips[j], cfg.sgp_ks, cfg.sgp_up, mp['mix'], self.act_dtype)
+            o = self._gemm([(cat, 6 * d, 0, 6 * d)], mp['wc'], mp['bc'], label='sgp_gemm', act=L.ACT_GELU, rows=rows,
+                           out_dtype=torch.float32).view(b, lens[j], d)
+            g = self._op('sgp_mix', 8.0 * rows * d, rows * d * 6, ops.groupnorm, o, mp['gn_w'], mp['gn_b'], self.act_dtype)
+            x = self._mlp(g, o, mp['mlp'], rows).view(b, lens[j], d)
+            x = self._sgp_block(x, lens[j], W['sgp'][L_ + i + 1])
+        return x
+
+    def heads(self, x):
+        cfg, W = self.cfg, self.W
+        b, t, d = x.shape
+        return self._op('heads', 2.0 * b * t * d * (W['cls_w'].shape[0] + 1), b * t * d * 4,
+                        ops.heads, x, W['cls_w'], W['cls_b'], W['displ_w'], W['displ_b'], cfg.num_classes + 1)
+
+    def forward(self, frames, flip=False, crop=None, taps=None):
+        """frames (B,T,3,H,W) u8|f32 device tensor -> (logits (B,T,K'), displ (B,T)|None, probs (B,T,K))."""
+        b, t = frames.shape[:2]
+        feat = self.backbone(frames, flip=flip, crop=crop, taps=taps).view(b, t, self.cfg.feat_dim)
+        if taps is not None:
+            taps['feat_posenc'] = feat
+        x = self.temporal(feat)
+        if taps is not None:
+            taps['temporal'] = x
+        return self.heads(x)
+
+    # ------------------------------------------------------------------ CUDA graph replay
+    def forward_graphed(self, frames, flip=False):
+        """Same as forward() but replays a captured CUDA graph (static shapes).  Returns views of
+        static output buffers that are overwritten by the next call with the same key."""
+        key = (tuple(frames.shape), frames.dtype, bool(flip))
+        ent = self._graphs.get(key)
+        if ent is None:
+            static_in = torch.empty_like(frames)
+            static_in.copy_(frames)
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):               # warm-up: sets kernel attributes, primes the allocator
+                    self.forward(static_in, flip=flip)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = self.launches
+            with torch.cuda.graph(graph):
+                outs = self.forward(static_in, flip=flip)
+            ent = dict(graph=graph, static_in=static_in, outs=outs, launches=self.launches - n0)
+            self._graphs[key] = ent
+        ent['static_in'].copy_(frames, non_blocking=True)
+        ent['graph'].replay()
+        self.launches += ent['launches']
+        return ent['outs']

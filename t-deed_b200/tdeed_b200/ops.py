@@ -1,0 +1,183 @@
+"""Tensor-level wrappers over the C-ABI (one function per entry point of include/tdeed_b200.h).
+
+PyTorch supplies device memory and the current stream only; every computation happens inside
+libtdeed_sm100.so.  All wrappers are asynchronous on torch's current CUDA stream.
+"""
+import ctypes
+
+import torch
+
+from . import _lib as L
+
+
+def stem(frames, crop, flip, weight, bias, out_dtype):
+    """frames (N,3,H,W) u8|f32 (device) -> NHWC (N, ceil(h/2), ceil(w/2), 32)."""
+    n, _, in_h, in_w = frames.shape
+    cy, cx, h, w = crop
+    out = torch.empty((n, (h + 1) // 2, (w + 1) // 2, 32), dtype=out_dtype, device=frames.device)
+    L.check(L.load().tdeed_stem_fwd(L.ptr(frames), L.dtype_code(frames.dtype), n, in_h, in_w, cy, cx, h, w,
+                                    int(bool(flip)), L.ptr(weight), L.ptr(bias), L.ptr(out), L.dtype_code(out_dtype),
+                                    L.stream()), 'stem')
+    return out
+
+
+def gemm(segs, weight, bias=None, residual=None, act=L.ACT_NONE, out=None, out_dtype=None, gather=None,
+         backend=L.GEMM_AUTO, rows=None):
+    """out[M,N] = act(concat_k(segs) @ weight.T + bias + residual).
+
+    segs: list of (tensor2d_or_flat, lda, col0, k); tensors are activations whose rows are M.
+    gather: (stride, h, w) for the strided 1x1 shortcut conv (rows = frames*ceil(h/s)*ceil(w/s)).
+    """
+    dtype = weight.dtype
+    n_out = weight.shape[0]
+    m = rows
+    arr = (L.GemmSeg * len(segs))()
+    for i, (t, lda, col0, k) in enumerate(segs):
+        assert t.dtype == dtype, 'segment dtype %s != weight dtype %s' % (t.dtype, dtype)
+        arr[i].a, arr[i].lda, arr[i].col0, arr[i].k = L.ptr(t), lda, col0, k
+    if out is None:
+        out = torch.empty((m, n_out), dtype=out_dtype or dtype, device=weight.device)
+    ldo = out.stride(-2) if out.dim() >= 2 else n_out
+    gs, gh, gw = gather if gather else (1, 0, 0)
+    L.check(L.load().tdeed_gemm_fwd(L.dtype_code(dtype), m, n_out, len(segs), arr, gs, gh, gw, L.ptr(weight),
+                                    L.ptr(bias), L.ptr(residual),
+                                    residual.stride(-2) if residual is not None else 0,
+                                    L.dtype_code(residual.dtype) if residual is not None else 0,
+                                    act, L.ptr(out), ldo, L.dtype_code(out.dtype), backend, L.stream()), 'gemm')
+    return out
+
+
+def conv3x3g(x, weight, bias, group_width, stride, out=None):
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, (h + stride - 1) // stride, (w + stride - 1) // stride, c), dtype=x.dtype, device=x.device)
+    L.check(L.load().tdeed_conv3x3g_fwd(L.dtype_code(x.dtype), L.ptr(x), n, h, w, c, group_width, stride,
+                                        L.ptr(weight), L.ptr(bias), L.ptr(out), L.stream()), 'conv3x3g')
+    return out
+
+
+def se_(x, w1, b1, w2, b2):
+    n, h, w, c = x.shape
+    L.check(L.load().tdeed_se_fwd(L.dtype_code(x.dtype), L.ptr(x), n, h * w, c, w1.shape[0], L.ptr(w1), L.ptr(b1),
+                                  L.ptr(w2), L.ptr(b2), L.stream()), 'se')
+    return x
+
+
+def gsf_workspace_floats(clips, clip_len, h, w, fold):
+    return int(L.load().tdeed_gsf_workspace_floats(clips, clip_len, h, w, fold))
+
+
+def gsf(x, clips, clip_len, fold, mode, p, workspace, out):
+    """x NHWC (clips*clip_len, h, w, c) -> out (N*h*w, ld_out) holding the gate-shifted fold channels."""
+    n, h, w, c = x.shape
+    L.check(L.load().tdeed_gsf_fwd(L.dtype_code(x.dtype), mode, L.ptr(x), clips, clip_len, h, w, c, fold,
+                                   L.ptr(p['bn_scale']), L.ptr(p['bn_shift']), L.ptr(p['w3d']), L.ptr(p['b3d']),
+                                   L.ptr(p.get('cc_w')), L.ptr(p.get('cc_b')), L.ptr(workspace), L.ptr(out),
+                                   out.shape[-1], L.stream()), 'gsf')
+    return out
+
+
+def pool_posenc(x, clip_len, temp_enc, out=None):
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, c), dtype=torch.float32, device=x.device)
+    L.check(L.load().tdeed_pool_posenc_fwd(L.dtype_code(x.dtype), L.ptr(x), n, h * w, c, clip_len, L.ptr(temp_enc),
+                                           L.ptr(out), L.stream()), 'pool_posenc')
+    return out
+
+
+def _fill(struct, tensors):
+    for name in struct._names:
+        setattr(struct, name, L.ptr(tensors[name]))
+    return struct
+
+
+def sgp_mix(x, t_out, ks, up, w, g_dtype):
+    b, t_in, c = x.shape
+    y = torch.empty((b, t_out, c), dtype=torch.float32, device=x.device)
+    g = torch.empty((b, t_out, c), dtype=g_dtype, device=x.device)
+    ws = _fill(L.SgpWeights(), w)
+    L.check(L.load().tdeed_sgp_mix_fwd(L.ptr(x), b, t_in, t_out, c, ks, up, ctypes.byref(ws), L.ptr(y), L.ptr(g),
+                                       L.dtype_code(g_dtype), L.stream()), 'sgp_mix')
+    return y, g
+
+
+def sgp_mixer_mix(x_coarse, skip, ks, up, w, cat_dtype):
+    b, tc, c = x_coarse.shape
+    t = skip.shape[1]
+    cat = torch.empty((b * t, 6 * c), dtype=cat_dtype, device=skip.device)
+    ws = _fill(L.MixerWeights(), w)
+    L.check(L.load().tdeed_sgp_mixer_mix_fwd(L.ptr(x_coarse), L.ptr(skip), b, tc, t, c, ks, up, ctypes.byref(ws),
+                                             L.ptr(cat), L.dtype_code(cat_dtype), L.stream()), 'sgp_mixer_mix')
+    return cat
+
+
+def groupnorm(x, gamma, beta, out_dtype, groups=16):
+    b, t, c = x.shape
+    out = torch.empty((b, t, c), dtype=out_dtype, device=x.device)
+    L.check(L.load().tdeed_groupnorm_fwd(L.ptr(x), b, t, c, groups, L.ptr(gamma), L.ptr(beta), L.ptr(out),
+                                         L.dtype_code(out_dtype), L.stream()), 'groupnorm')
+    return out
+
+
+def heads(feat, w_cls, b_cls, w_displ, b_displ, k_softmax):
+    b, t, c = feat.shape
+    k_out = w_cls.shape[0]
+    logits = torch.empty((b, t, k_out), dtype=torch.float32, device=feat.device)
+    probs = torch.empty((b, t, k_softmax), dtype=torch.float32, device=feat.device)
+    displ = torch.empty((b, t), dtype=torch.float32, device=feat.device) if w_displ is not None else None
+    L.check(L.load().tdeed_heads_fwd(L.ptr(feat), b, t, c, L.ptr(w_cls), L.ptr(b_cls), k_out, L.ptr(w_displ),
+                                     L.ptr(b_displ), k_softmax, L.ptr(logits), L.ptr(displ), L.ptr(probs),
+                                     L.stream()), 'heads')
+    return logits, displ, probs
+
+
+def softmax_scatter(logits, displ, k_softmax):
+    """process_prediction / process_double_head: logits (B,T,K') fp32, displ (B,T) fp32 | None -> probs (B,T,k)."""
+    b, t, kk = logits.shape
+    probs = torch.empty((b, t, k_softmax), dtype=torch.float32, device=logits.device)
+    L.check(L.load().tdeed_softmax_scatter_fwd(L.ptr(logits), kk, L.ptr(displ), b, t, k_softmax, L.ptr(probs),
+                                               L.stream()), 'softmax_scatter')
+    return probs
+
+
+def clip_accumulate(scores, support, pred, starts, mode):
+    video_len, k = scores.shape
+    n_clips, t, _ = pred.shape
+    L.check(L.load().tdeed_clip_accumulate(L.ptr(scores), L.ptr(support), video_len, k, L.ptr(pred), L.ptr(starts),
+                                           n_clips, t, mode, L.stream()), 'clip_accumulate')
+
+
+def extract_events(scores, support, threshold):
+    """Normalises scores/support in place.  Returns dict of device tensors (capacity-sized) + counts."""
+    video_len, k = scores.shape
+    dev = scores.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    out = {
+        'pred': torch.empty(video_len, **i32),
+        'ev_frame': torch.empty(video_len, **i32), 'ev_label': torch.empty(video_len, **i32),
+        'ev_score': torch.empty(video_len, dtype=torch.float32, device=dev),
+        'hr_frame': torch.empty(video_len * (k - 1), **i32), 'hr_label': torch.empty(video_len * (k - 1), **i32),
+        'hr_score': torch.empty(video_len * (k - 1), dtype=torch.float32, device=dev),
+        'counts': torch.zeros(2, **i32),
+    }
+    L.check(L.load().tdeed_extract_events(L.ptr(scores), L.ptr(support), video_len, k, float(threshold),
+                                          L.ptr(out['pred']), L.ptr(out['ev_frame']), L.ptr(out['ev_label']),
+                                          L.ptr(out['ev_score']), L.ptr(out['hr_frame']), L.ptr(out['hr_label']),
+                                          L.ptr(out['hr_score']), L.ptr(out['counts']), L.stream()), 'extract_events')
+    return out
+
+
+def nms(frame, label, score, n_events_dev, k, window, threshold, soft):
+    """(soft-)NMS of one video's events.  Returns (out_frame i32, out_label i32, out_score f64, out_count i32[1])."""
+    cap = frame.numel()
+    dev = frame.device
+    ws = torch.empty(int(L.load().tdeed_nms_workspace_bytes(cap, k)), dtype=torch.uint8, device=dev)
+    of = torch.empty(cap, dtype=torch.int32, device=dev)
+    ol = torch.empty(cap, dtype=torch.int32, device=dev)
+    os_ = torch.empty(cap, dtype=torch.float64, device=dev)
+    oc = torch.zeros(1, dtype=torch.int32, device=dev)
+    L.check(L.load().tdeed_nms(L.ptr(frame), L.ptr(label), L.ptr(score), L.ptr(n_events_dev), cap, k, int(window),
+                               float(threshold), int(bool(soft)), L.ptr(ws), L.ptr(of), L.ptr(ol), L.ptr(os_),
+                               L.ptr(oc), L.stream()), 'nms')
+    return of, ol, os_, oc

@@ -1,0 +1,230 @@
+"""GPU parity of every C-ABI kernel against the CPU oracle (oracle/tdeed_oracle.py) or, for the plain
+GEMM, a torch fp32 matmul.  Tolerances: fp32 kernels 1e-4 relative-to-max (north star: 1e-3 end to end);
+bf16 kernels are compared on bf16-rounded inputs with a tolerance that covers one bf16 output rounding."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import tdeed_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip('no CUDA device')
+    return torch.device('cuda:0')
+
+
+def rel_err(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+def _gemm_case(dev, dtype, m, n, ks, act, with_res, backend, gather=None, seed=0):
+    from tdeed_b200 import _lib as L, ops
+    g = torch.Generator().manual_seed(seed)
+    k = sum(ks)
+    w = (torch.randn(n, k, generator=g) / math.sqrt(k)).to(dtype)
+    bias = torch.randn(n, generator=g)
+    segs_cpu, segs = [], []
+    if gather:
+        s, frames, h, wd = gather
+        src = torch.randn(frames, h, wd, ks[0] + 8, generator=g).to(dtype)        # lda > k: extra columns ignored
+        sub = src[:, ::s, ::s, :ks[0]].reshape(-1, ks[0])
+        m = sub.shape[0]
+        segs_cpu.append(sub)
+        segs.append((src.to(dev), ks[0] + 8, 0, ks[0]))
+    else:
+        for i, kk in enumerate(ks):
+            col0 = 8 * i                                                           # second segment starts mid-row
+            lda = (col0 + kk + 7) // 8 * 8
+            a = torch.randn(m, lda, generator=g).to(dtype)
+            segs_cpu.append(a[:, col0:col0 + kk])
+            segs.append((a.to(dev), lda, col0, kk))
+    res = torch.randn(m, n, generator=g).to(dtype) if with_res else None
+    ref = torch.cat([s_.float() for s_ in segs_cpu], 1) @ w.float().t() + bias
+    if with_res:
+        ref = ref + res.float()
+    if act == L.ACT_RELU:
+        ref = torch.relu(ref)
+    elif act == L.ACT_GELU:
+        ref = torch.nn.functional.gelu(ref)
+    out = ops.gemm(segs, w.to(dev), bias.to(dev), residual=res.to(dev) if with_res else None, act=act, rows=m,
+                   out_dtype=torch.float32, backend=backend,
+                   gather=(gather[0], gather[2], gather[3]) if gather else None)
+    torch.cuda.synchronize()
+    return rel_err(out, ref)
+
+
+@pytest.mark.parametrize('m,n,ks', [(300, 24, (32,)), (1000, 152, (16, 40)), (70, 368, (92, 276)), (513, 1472, (368,))])
+def test_gemm_simt_fp32(dev, m, n, ks):
+    from tdeed_b200 import _lib as L
+    for act, res in ((L.ACT_NONE, False), (L.ACT_RELU, True), (L.ACT_GELU, False)):
+        assert _gemm_case(dev, torch.float32, m, n, ks, act, res, L.GEMM_SIMT) < 1e-5
+
+
+def test_gemm_simt_gather(dev):
+    from tdeed_b200 import _lib as L
+    assert _gemm_case(dev, torch.float32, 0, 56, (24,), L.ACT_NONE, False, L.GEMM_SIMT, gather=(2, 3, 14, 10)) < 1e-5
+    assert _gemm_case(dev, torch.bfloat16, 0, 152, (56,), L.ACT_NONE, False, L.GEMM_SIMT, gather=(2, 2, 7, 9)) < 1e-5
+
+
+@pytest.mark.parametrize('m,n,ks', [
+    (128, 32, (64,)), (300, 24, (32,)), (1000, 56, (24,)), (777, 152, (16, 40)), (4900, 368, (92, 276)),
+    (400, 1472, (368,)), (400, 368, (1472,)), (1300, 768, (4608,)), (19600, 368, (368,)), (129, 3072, (768,))])
+def test_gemm_tcgen05_bf16(dev, m, n, ks):
+    """tcgen05/TMA kernel vs fp32 matmul of the same bf16 operands (fp32 accumulate -> only order differs)."""
+    from tdeed_b200 import _lib as L
+    for act, res in ((L.ACT_NONE, False), (L.ACT_RELU, True), (L.ACT_GELU, False)):
+        assert _gemm_case(dev, torch.bfloat16, m, n, ks, act, res, L.GEMM_TCGEN05) < 2e-5
+
+
+def _nhwc(x):
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def _nchw(x):
+    return x.permute(0, 3, 1, 2).contiguous()
+
+
+@pytest.mark.parametrize('in_dtype', [torch.uint8, torch.float32])
+@pytest.mark.parametrize('flip', [False, True])
+def test_stem(dev, in_dtype, flip):
+    from tdeed_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    frames = torch.randint(0, 256, (5, 3, 50, 70), generator=g, dtype=torch.uint8)
+    w = torch.randn(32, 3, 3, 3, generator=g) * 0.2
+    b = torch.randn(32, generator=g) * 0.1
+    cfg = O.Config(crop_dim=None)
+    crop = (3, 11, 44, 45)                                   # odd width -> ceil(w/2) outputs
+    x = frames[None, :, :, 3:47, 11:56]
+    xn = O.preprocess(x, cfg, flip=flip)
+    ref = torch.relu(torch.nn.functional.conv2d(xn, w, b, stride=2, padding=1))
+    out = ops.stem(frames.to(in_dtype).to(dev), crop, flip, w.to(dev), b.to(dev), torch.float32)
+    assert rel_err(_nchw(out), ref) < 1e-5
+    out16 = ops.stem(frames.to(in_dtype).to(dev), crop, flip, w.to(dev), b.to(dev), torch.bfloat16)
+    assert rel_err(_nchw(out16), ref) < 6e-3
+
+
+@pytest.mark.parametrize('c,gw,stride,h,w', [(24, 8, 2, 20, 22), (152, 8, 1, 7, 9), (368, 8, 2, 14, 14),
+                                              (64, 16, 2, 12, 10), (320, 16, 1, 5, 6)])
+def test_conv3x3g(dev, c, gw, stride, h, w):
+    from tdeed_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(3, c, h, w, generator=g)
+    wt = torch.randn(c, gw, 3, 3, generator=g) / math.sqrt(9 * gw)
+    b = torch.randn(c, generator=g) * 0.1
+    ref = torch.relu(torch.nn.functional.conv2d(x, wt, b, stride=stride, padding=1, groups=c // gw))
+    out = ops.conv3x3g(_nhwc(x).to(dev), wt.to(dev), b.to(dev), gw, stride)
+    assert rel_err(_nchw(out), ref) < 1e-5
+    xb = x.to(torch.bfloat16)
+    refb = torch.relu(torch.nn.functional.conv2d(xb.float(), wt, b, stride=stride, padding=1, groups=c // gw))
+    outb = ops.conv3x3g(_nhwc(xb).to(dev), wt.to(dev), b.to(dev), gw, stride)
+    assert rel_err(_nchw(outb), refb) < 6e-3
+
+
+@pytest.mark.parametrize('c,rd,hw', [(24, 8, (9, 7)), (368, 92, (7, 7)), (768, 192, (4, 5))])
+def test_se_and_pool(dev, c, rd, hw):
+    from tdeed_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(4, c, *hw, generator=g)
+    w1, b1 = torch.randn(rd, c, generator=g) / math.sqrt(c), torch.randn(rd, generator=g) * 0.1
+    w2, b2 = torch.randn(c, rd, generator=g) / math.sqrt(rd), torch.randn(c, generator=g) * 0.1
+    s = x.mean((2, 3))
+    s = torch.sigmoid(torch.relu(s @ w1.t() + b1) @ w2.t() + b2)
+    ref = x * s[:, :, None, None]
+    out = ops.se_(_nhwc(x).to(dev), w1.to(dev), b1.to(dev), w2.to(dev), b2.to(dev))
+    assert rel_err(_nchw(out), ref) < 1e-5
+    te = torch.randn(2, c, generator=g)
+    pooled = ops.pool_posenc(_nhwc(x).to(dev), 2, te.to(dev))
+    assert rel_err(pooled, x.mean((2, 3)) + te.repeat(2, 1)) < 1e-5
+
+
+@pytest.mark.parametrize('mode', ['gsf', 'gsm'])
+@pytest.mark.parametrize('fold,c,hw', [(16, 56, (6, 5)), (40, 152, (4, 4)), (92, 368, (3, 2)), (192, 768, (2, 3))])
+def test_gate_shift(dev, mode, fold, c, hw):
+    from tdeed_b200 import _lib as L, ops
+    g = torch.Generator().manual_seed(4)
+    clips, T = 2, 5
+    x = torch.randn(clips * T, c, *hw, generator=g)
+    sd = {'g.bn.weight': torch.rand(fold, generator=g) + 0.5, 'g.bn.bias': torch.randn(fold, generator=g) * 0.1,
+          'g.bn.running_mean': torch.randn(fold, generator=g) * 0.1, 'g.bn.running_var': torch.rand(fold, generator=g) + 0.5,
+          'g.conv3D.weight': torch.randn(2, fold // 2, 3, 3, 3, generator=g) / math.sqrt(27 * fold / 2),
+          'g.conv3D.bias': torch.randn(2, generator=g) * 0.1,
+          'g.channel_conv1.weight': torch.randn(1, 2, 3, 3, generator=g) * 0.3, 'g.channel_conv1.bias': torch.randn(1, generator=g) * 0.1,
+          'g.channel_conv2.weight': torch.randn(1, 2, 3, 3, generator=g) * 0.3, 'g.channel_conv2.bias': torch.randn(1, generator=g) * 0.1}
+    ref = O.gate_shift(x[:, :fold], sd, 'g', T, mode)
+    scale = sd['g.bn.weight'] / torch.sqrt(sd['g.bn.running_var'] + 1e-5)
+    p = dict(bn_scale=scale, bn_shift=sd['g.bn.bias'] - sd['g.bn.running_mean'] * scale,
+             w3d=sd['g.conv3D.weight'].reshape(-1), b3d=sd['g.conv3D.bias'],
+             cc_w=torch.cat([sd['g.channel_conv1.weight'].reshape(-1), sd['g.channel_conv2.weight'].reshape(-1)]),
+             cc_b=torch.cat([sd['g.channel_conv1.bias'], sd['g.channel_conv2.bias']]))
+    p = {k: v.float().contiguous().to(dev) for k, v in p.items()}
+    xh = _nhwc(x).to(dev)
+    ld = (fold + 7) // 8 * 8
+    ws = torch.empty(ops.gsf_workspace_floats(clips, T, hw[0], hw[1], fold), dtype=torch.float32, device=dev)
+    out = torch.zeros(clips * T * hw[0] * hw[1], ld, device=dev)
+    ops.gsf(xh, clips, T, fold, L.SHIFT_GSF if mode == 'gsf' else L.SHIFT_GSM, p, ws, out)
+    got = out[:, :fold].reshape(clips * T, hw[0], hw[1], fold).permute(0, 3, 1, 2)
+    assert rel_err(got, ref) < 2e-5
+
+
+@pytest.mark.parametrize('c,t_in,t_out,ks,r', [(368, 25, 25, 7, 4), (368, 25, 13, 5, 4), (768, 100, 50, 9, 4), (368, 13, 7, 11, 2)])
+def test_sgp_block_fp32(dev, c, t_in, t_out, ks, r):
+    from model.modules import SGPBlock
+    torch.manual_seed(5)
+    blk = SGPBlock(c, kernel_size=ks, k=r, init_conv_vars=0.1)
+    for p in blk.parameters():
+        p.data.add_(torch.randn_like(p) * 0.05)
+    x = torch.randn(2, c, t_in)
+    sd = {'b.' + k: v for k, v in blk.state_dict().items()}
+    xp = torch.nn.functional.adaptive_max_pool1d(x, t_out) if t_out != t_in else x
+    ref = O.sgp_block(xp, sd, 'b')
+    blk = blk.to(dev).eval()
+    got = blk.forward_btc(x.permute(0, 2, 1).contiguous().to(dev), t_out).permute(0, 2, 1)
+    assert rel_err(got, ref) < 2e-5
+
+
+@pytest.mark.parametrize('c,tc,t,ks,r', [(368, 13, 25, 7, 4), (768, 50, 100, 9, 4), (368, 7, 13, 5, 4)])
+def test_sgp_mixer_fp32(dev, c, tc, t, ks, r):
+    from model.modules import SGPMixer
+    torch.manual_seed(6)
+    mix = SGPMixer(c, kernel_size=ks, k=r, init_conv_vars=0.1, t_size=t)
+    for p in mix.parameters():
+        p.data.add_(torch.randn_like(p) * 0.03)
+    x, z = torch.randn(2, c, tc), torch.randn(2, c, t)
+    sd = {'m.' + k: v for k, v in mix.state_dict().items()}
+    ref = O.sgp_mixer(x, z, sd, 'm', t)
+    mix = mix.to(dev).eval()
+    got = mix(x.to(dev), z.to(dev))
+    assert rel_err(got, ref) < 2e-5
+
+
+def test_heads_softmax_scatter(dev):
+    from tdeed_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    for c, k_out, k_sm in ((368, 5, 5), (768, 31, 13), (768, 33, 33)):
+        feat = torch.randn(3, 40, c, generator=g)
+        w, b = torch.randn(k_out, c, generator=g) / math.sqrt(c) * 3, torch.randn(k_out, generator=g)
+        wd, bd = torch.randn(c, generator=g) / math.sqrt(c) * 4, torch.randn(1, generator=g)
+        logits_ref = feat @ w.t() + b
+        displ_ref = feat @ wd + bd
+        logits, displ, probs = ops.heads(feat.to(dev), w.to(dev), b.to(dev), wd.to(dev), bd.to(dev), k_sm)
+        assert rel_err(logits, logits_ref) < 1e-5 and rel_err(displ, displ_ref) < 1e-5
+        # scatter-max exactness: feed the kernel's own logits/displ to the oracle
+        ref = O.scatter_max_probs(logits.cpu(), displ.cpu(), num_softmax=k_sm)
+        assert float((probs.cpu() - ref).abs().max()) < 1e-6
+        assert torch.equal(probs.cpu() == 0, ref == 0)          # untouched rows stay exactly zero
+        again = ops.softmax_scatter(logits, displ, k_sm)
+        assert torch.equal(again, probs)
+        _, _, plain = ops.heads(feat.to(dev), w.to(dev), b.to(dev), None, None, k_sm)
+        assert float((plain.cpu() - torch.softmax(logits.cpu()[..., :k_sm], 2)).abs().max()) < 1e-6
+    # rounding: half-to-even and clamping
+    lg = torch.zeros(1, 8, 3)
+    lg[0, :, 1] = torch.arange(8.)
+    d = torch.tensor([[0.5, 1.5, 2.5, -0.5, -1.5, 60.0, -60.0, 0.49]])
+    assert torch.equal(ops.softmax_scatter(lg.to(dev), d.to(dev), 3).cpu(), O.scatter_max_probs(lg, d))

@@ -1,0 +1,63 @@
+"""CPU-only checks of the host side: the C-ABI library exports what include/tdeed_b200.h declares, the
+drop-in model package mirrors the reference's state_dict layout, and the product fails loudly without CUDA."""
+import ctypes
+import os
+import re
+from argparse import Namespace
+
+import pytest
+import torch
+
+import tdeed_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _args(cfg):
+    return Namespace(modality='rgb', temporal_arch='ed_sgp_mixer', radi_displacement=cfg.radi_displacement,
+                     feature_arch=cfg.feature_arch, clip_len=cfg.clip_len, n_layers=cfg.n_layers, sgp_ks=cfg.sgp_ks,
+                     sgp_r=cfg.sgp_r, num_classes=cfg.num_classes, crop_dim=cfg.crop_dim)
+
+
+def test_library_exports_every_declared_symbol():
+    from tdeed_b200 import _lib
+    header = open(os.path.join(ROOT, 'include', 'tdeed_b200.h')).read()
+    declared = set(re.findall(r'\b(tdeed_[a-z0-9_]+)\s*\(', header))
+    declared -= {'tdeed_gemm_seg', 'tdeed_status'}
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = ctypes.CDLL(_lib.LIB_PATH)           # loads without a GPU
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().tdeed_abi_version() == 1
+
+
+@pytest.mark.parametrize('name', ['FineDiving_small', 'FineGym_big', 'SoccerNetBall_challenge2'])
+def test_dropin_state_dict_matches_reference_layout(name):
+    from model.model import TDEEDModel
+    cfg = O.named_config(name)
+    m = TDEEDModel(device='cpu', args=_args(cfg))
+    if cfg.double_head:
+        m._model.update_pred_head(cfg.double_head)
+    sd = m.state_dict()
+    ref = O.state_shapes(cfg)
+    assert list(sd.keys()) == list(ref.keys())
+    for k, shape in ref.items():
+        assert tuple(sd[k].shape) == tuple(shape), k
+    m.load(O.random_state(cfg, 0))             # strict load of a reference-layout checkpoint
+
+
+def test_no_cpu_fallback():
+    from model.model import TDEEDModel
+    cfg = O.Config(clip_len=4, crop_dim=32)
+    m = TDEEDModel(device='cpu', args=_args(cfg))
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        m.predict(torch.zeros(1, 4, 3, 32, 32, dtype=torch.uint8), use_amp=False)
+
+
+def test_gemm_rejects_bad_arguments_without_gpu():
+    from tdeed_b200 import _lib as L
+    lib = L.load()
+    seg = (L.GemmSeg * 1)()
+    seg[0].a, seg[0].lda, seg[0].col0, seg[0].k = 16, 8, 0, 8
+    rc = lib.tdeed_gemm_fwd(L.F32, 4, 12, 1, seg, 1, 0, 0, 16, None, None, 0, 0, 0, 16, 16, 0, 0, None)
+    assert rc == -1 and b'multiples of 8' in lib.tdeed_last_error()
