@@ -31,6 +31,10 @@ class reference_modules:
         for k in self._saved:
             del sys.modules[k]
         self._path = list(sys.path)
+        # the reference's model/ and util/ have no __init__.py (namespace packages): any regular package of
+        # the same name further down sys.path (the product's drop-in t-deed_b200/model) would win -> hide it
+        sys.path[:] = [p for p in sys.path
+                       if not os.path.exists(os.path.join(p or '.', 'model', '__init__.py'))]
         sys.path[:0] = [REFERENCE_ROOT, os.path.join(_HERE, 'timm_shim'), os.path.join(_HERE, 'stubs')]
         mods = {}
         for name in ('model.modules', 'model.shift', 'model.model', 'model.impl.gsm',

@@ -61,7 +61,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if (clock64() - t0 > 4000000000LL) {
+      printf("tdeed gemm_tc: mbarrier wait timed out (block %d,%d thread %d parity %u)\n", blockIdx.x, blockIdx.y, threadIdx.x, parity);
+      __trap();
+    }
   }
 }
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
@@ -295,6 +298,10 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
   for (int s = 0; s < nseg; ++s) {
     TDEED_REQUIRE(segs[s].lda % 8 == 0 && (reinterpret_cast<uintptr_t>(segs[s].a) & 15) == 0, TDEED_ERR_SHAPE,
                   "gemm_tc: segment %d needs lda %% 8 == 0 and a 16-byte aligned base", s);
+    // TMA box origins must be 16-byte aligned in global memory: column offsets in A and in W are multiples of 8
+    TDEED_REQUIRE(segs[s].col0 % 8 == 0 && wcol % 8 == 0, TDEED_ERR_SHAPE,
+                  "gemm_tc: segment %d starts at A column %d / W column %d; both must be multiples of 8 (pad the segment)",
+                  s, segs[s].col0, wcol);
     // the tensor spans columns [0, col0 + k): loads past it are zero-filled, which implements the K tail
     int rc = make_map(&maps[s], segs[s].a, M, (long long)segs[s].col0 + segs[s].k, segs[s].lda, TC_BM);
     if (rc) return rc;

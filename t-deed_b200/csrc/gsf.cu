@@ -148,8 +148,12 @@ gsf_blend_kernel(const T* __restrict__ x, int clip_len, int hw, int c, int fold,
   const long long idx = (long long)blockIdx.x * GS_THREADS + threadIdx.x;
   if (idx >= total) return;
   const int half = fold / 2, quarter = fold / 4;
-  const int jo = (int)(idx % fold);                 // output (interleaved) channel
-  const long long fp = idx / fold;                  // frame*hw + pixel
+  const int jo = (int)(idx % ld_out);               // output (interleaved) channel, or a pad column
+  const long long fp = idx / ld_out;                // frame*hw + pixel
+  if (jo >= fold) {                                 // pad columns feed zero weights in the GEMM: keep them finite
+    Elem<T>::st(out + (size_t)fp * ld_out + jo, 0.f);
+    return;
+  }
   const int p = (int)(fp % hw);
   const long long f = fp / hw;
   const int t = (int)(f % clip_len);
@@ -193,7 +197,7 @@ static int launch_gsf(int mode, const void* x, int clips, int clip_len, int h, i
     rc = check_launch("tdeed_gsf_fwd(weights)");
     if (rc) return rc;
   }
-  const long long total = (long long)n * hw * fold;
+  const long long total = (long long)n * hw * ld_out;
   gsf_blend_kernel<T><<<(unsigned)ceil_div_ll(total, GS_THREADS), GS_THREADS, 0, st>>>(
       (const T*)x, clip_len, hw, c, fold, mode, gate, wgt, (T*)out, ld_out, total);
   return check_launch("tdeed_gsf_fwd(blend)");

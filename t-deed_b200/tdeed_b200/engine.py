@@ -108,7 +108,19 @@ class InferenceEngine:
             b = dict(cin=cin, cout=cout, stride=stride, shifted=shifted, gw=gw)
             c1 = p + ('.conv1.net' if shifted else '.conv1')
             sc, sh = _bn_fold(sd, c1 + '.bn')
-            b['w1'] = (sd[c1 + '.conv.weight'].float().reshape(cout, cin) * sc[:, None]).to(adt).contiguous()
+            w1 = sd[c1 + '.conv.weight'].float().reshape(cout, cin) * sc[:, None]
+            if shifted:
+                # K layout of the virtual concat [gate-shift out (fold, padded to 8) | x[:, xs:]]: TMA box origins
+                # must be 16-byte aligned, so the x segment starts at the multiple of 8 below `fold`; the few
+                # overlapped channels / pad columns get zero weights.
+                fd = fold_dim(cin)
+                fdp, xs = _round8(fd), fd // 8 * 8
+                wp = torch.zeros((cout, fdp + cin - xs), dtype=torch.float32, device=dev)
+                wp[:, :fd] = w1[:, :fd]
+                wp[:, fdp + (fd - xs):] = w1[:, fd:]
+                w1 = wp
+                b['x_start'] = xs
+            b['w1'] = w1.to(adt).contiguous()
             b['b1'] = f32(sh)
             sc, sh = _bn_fold(sd, p + '.conv2.bn')
             b['w2'] = f32(sd[p + '.conv2.conv.weight'].float() * sc[:, None, None, None])
@@ -237,7 +249,7 @@ class InferenceEngine:
                 self._op('gsf', 2.0 * m * 27 * fd, m * fd * es * 2, ops.gsf, x, b, t, fd,
                          L.SHIFT_GSF if cfg.shift_mode == 'gsf' else L.SHIFT_GSM, gs, ws, gso,
                          _n=3 if cfg.shift_mode == 'gsf' else 2)
-                segs = [(gso, gso.shape[1], 0, fd), (x, cin, fd, cin - fd)]
+                segs = [(gso, gso.shape[1], 0, gso.shape[1]), (x, cin, blk['x_start'], cin - blk['x_start'])]
             else:
                 segs = [(x, cin, 0, cin)]
             a1 = self._gemm(segs, blk['w1'], blk['b1'], label='conv1x1', act=L.ACT_RELU, rows=m).view(n, h, w, cout)

@@ -61,7 +61,9 @@ def test_golden_postproc(golden_dir, dev, batch):
         assert np.array_equal(s, g[c + '_nms_score'])
         f, l, s = nms_gpu(ev, k, w1, 0.01, soft=True)
         assert np.array_equal(f, g[c + '_snms_frame']) and np.array_equal(l, g[c + '_snms_label'])
-        assert np.array_equal(s, g[c + '_snms_score'])          # float64 bit-exact
+        ref_s = g[c + '_snms_score']
+        bad = np.nonzero(s != ref_s)[0]
+        assert len(bad) == 0, [(int(f[i]), int(l[i]), float(s[i]).hex(), float(ref_s[i]).hex()) for i in bad[:8]]   # float64 bit-exact
 
 
 def test_nms_random_vs_oracle(dev):
@@ -117,9 +119,16 @@ def test_tta_accumulate_and_full_size_properties(dev):
     for lab in range(1, k):
         fl = f[l == lab]
         assert np.all(np.diff(fl) > 6)
-    # idempotence: NMS of an NMS output returns it unchanged
+    # idempotence: NMS of an NMS output keeps every event (same-frame tie order follows the NEW list's label
+    # first-appearance order, exactly like the reference, so compare as sets)
     of = torch.as_tensor(f).to(dev); ol = torch.as_tensor(l).to(dev); osc = torch.as_tensor(s.astype(np.float32)).to(dev)
     cnt = torch.tensor([len(f)], dtype=torch.int32, device=dev)
     f2, l2, s2, c2 = ops.nms(of, ol, osc, cnt, k, 6, 0.01, False)
     n2 = int(c2.item())
-    assert n2 == len(f) and np.array_equal(f2[:n2].cpu().numpy(), f) and np.array_equal(l2[:n2].cpu().numpy(), l)
+    assert n2 == len(f) and np.array_equal(f2[:n2].cpu().numpy(), f)
+    assert set(zip(f2[:n2].cpu().tolist(), l2[:n2].cpu().tolist())) == set(zip(f.tolist(), l.tolist()))
+    # and the full-size result equals the CPU oracle on the same event list (bit-exact)
+    nh = int(ev['counts'][1].item())
+    hr = (ev['hr_frame'][:nh].cpu().numpy(), ev['hr_label'][:nh].cpu().numpy(), ev['hr_score'][:nh].cpu().numpy())
+    rf, rl, rs = P.nms(*hr, window=6, threshold=0.01)
+    assert np.array_equal(f, rf) and np.array_equal(l, rl) and np.array_equal(s, rs.astype(np.float64))
