@@ -269,7 +269,10 @@ def main():
     # per-kernel-family profile of one (eager) step with CUDA events on the launch stream
     roofline, families = None, {}
     if rank == 0:
+        step_device(graph=False)            # untimed: lets the caching allocator settle for the eager pass
+        torch.cuda.synchronize()
         eng.prof = []
+        torch.cuda._sleep(40_000_000)       # keep the GPU busy while the host enqueues, so event deltas are pure GPU time
         step_device(graph=False)
         torch.cuda.synchronize()
         for label, flops, nbytes, a, b in eng.prof:

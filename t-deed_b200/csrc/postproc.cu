@@ -222,8 +222,13 @@ nms_segment_kernel(const int* __restrict__ frame, const int* __restrict__ label,
   }
   __syncthreads();
 
-  // rounds: every alive candidate >= thr that outranks all alive neighbours within +-window is selected
-  // simultaneously (they are > window apart), then its neighbourhood is suppressed (hard) or decayed (soft).
+  // rounds: every alive candidate >= thr that outranks all alive neighbours within +-sel_window is selected
+  // simultaneously, then its +-window neighbourhood is suppressed (hard) or decayed (soft).
+  // hard: sel_window = window (selected events are > window apart; suppression is order independent).
+  // soft: sel_window = 2*window, so two events selected in one round never share a decayed neighbour and
+  //       an event selected in a later round was outranked by every earlier one within 2*window -> the
+  //       fp64 decays hit each score in exactly the reference's sequential (descending-score) order.
+  const int sel_window = soft ? 2 * window : window;
   while (true) {
     int any = 0;
     for (int i = threadIdx.x; i < m; i += NMS_THREADS) {
@@ -233,9 +238,9 @@ nms_segment_kernel(const int* __restrict__ frame, const int* __restrict__ label,
       any = 1;
       const int fi = sf[i];
       bool top = true;
-      for (int j = i - 1; j >= 0 && fi - sf[j] <= window && top; --j)
+      for (int j = i - 1; j >= 0 && fi - sf[j] <= sel_window && top; --j)
         if ((fl[j] & F_ALIVE) && outranks(ss[j], j, si, i)) top = false;
-      for (int j = i + 1; j < m && sf[j] - fi <= window && top; ++j)
+      for (int j = i + 1; j < m && sf[j] - fi <= sel_window && top; ++j)
         if ((fl[j] & F_ALIVE) && outranks(ss[j], j, si, i)) top = false;
       if (top) fl[i] |= F_SEL;
     }
