@@ -51,6 +51,19 @@ int tdeed_stem_fwd(const void* frames, int frames_dtype, int n_frames, int in_h,
                    const float* weight, const float* bias,
                    void* out, int out_dtype, void* stream);
 
+/* (1b) bf16 tensor-core variant of (1), optionally fused with the first 1x1 conv of stage 1 (timm
+ * s1.b1.conv1: 32 -> n1 channels, BN folded, ReLU): the stem is an implicit GEMM (K = 27 padded to 32) whose A
+ * operand is built by the threads in shared memory and multiplied by tcgen05.mma; with w1 != NULL the ReLU'd
+ * stem rows feed a second MMA and the full-resolution stem activation is never written to HBM.
+ * w0: bf16 [32][32] (k = ci*9 + ky*3 + kx, zero padded), b0 fp32 [32]; w1: bf16 [ceil16(n1)][32] zero padded
+ * rows, b1 fp32 [n1] (n1 % 8 == 0, n1 <= 64).  out_stem (may be NULL): bf16 NHWC
+ * [n, ceil(oh/stem_sub), ceil(ow/stem_sub), 32] holding every stem_sub-th pixel (stem_sub = 2 is what the
+ * stride-2 shortcut conv of s1.b1 reads); out_c1: bf16 NHWC [n, oh, ow, n1] (required iff w1). */
+int tdeed_stem_tc_fwd(const void* frames, int frames_dtype, int n_frames, int in_h, int in_w,
+                      int crop_y, int crop_x, int h, int w, int flip,
+                      const void* w0_bf16, const float* b0, const void* w1_bf16, const float* b1, int n1,
+                      void* out_stem, int stem_sub, void* out_c1, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (2) 1x1 convolution / linear layer as a GEMM with fused epilogue:
  *        out[m, n] = act( sum_k A[m, k] * W[n, k] + bias[n] + residual[m, n] )

@@ -12,9 +12,9 @@ struct SimtSegs {
 int gemm_simt_launch(int dtype, long long M, int N, int K, const SimtSegs& segs, int gstride, int gh, int gw,
                      const void* W, const float* bias, const void* residual, long long ldr, int res_dtype,
                      int act, void* out, long long ldo, int out_dtype, cudaStream_t st);
-int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* segs, const void* W, const float* bias,
-                   const void* residual, long long ldr, int res_dtype, int act, void* out, long long ldo,
-                   int out_dtype, cudaStream_t st);
+int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* segs, int gstride, int gh, int gw,
+                   const void* W, const float* bias, const void* residual, long long ldr, int res_dtype, int act,
+                   void* out, long long ldo, int out_dtype, cudaStream_t st);
 }  // namespace tdeed
 
 extern "C" int tdeed_gemm_fwd(int dtype, long long M, int N, int nseg, const tdeed_gemm_seg* segs,
@@ -43,11 +43,13 @@ extern "C" int tdeed_gemm_fwd(int dtype, long long M, int N, int nseg, const tde
   TDEED_REQUIRE(gather_stride <= 1 || (gather_h > 0 && gather_w > 0 && nseg == 1), TDEED_ERR_SHAPE,
                 "tdeed_gemm_fwd: gather needs one segment and a geometry");
   cudaStream_t st = (cudaStream_t)stream;
-  bool use_tc = (backend == TDEED_GEMM_TCGEN05) || (backend == TDEED_GEMM_AUTO && dtype == TDEED_BF16 && gather_stride <= 1 && K % 8 == 0);
+  bool aligned8 = K % 8 == 0;
+  for (int s = 0; s < nseg; ++s) aligned8 = aligned8 && segs[s].col0 % 8 == 0 && (s == nseg - 1 || segs[s].k % 8 == 0);
+  bool use_tc = (backend == TDEED_GEMM_TCGEN05) || (backend == TDEED_GEMM_AUTO && dtype == TDEED_BF16 && aligned8);
   if (use_tc) {
-    TDEED_REQUIRE(dtype == TDEED_BF16 && gather_stride <= 1, TDEED_ERR_UNSUPPORTED,
-                  "tdeed_gemm_fwd: the tcgen05 backend needs bf16 operands and no gather");
-    return gemm_tc_launch(M, N, K, nseg, segs, W, bias, residual, ldr, res_dtype, act, out, ldo, out_dtype, st);
+    TDEED_REQUIRE(dtype == TDEED_BF16, TDEED_ERR_UNSUPPORTED, "tdeed_gemm_fwd: the tcgen05 backend needs bf16 operands");
+    return gemm_tc_launch(M, N, K, nseg, segs, gather_stride, gather_h, gather_w, W, bias, residual, ldr, res_dtype, act,
+                          out, ldo, out_dtype, st);
   }
   return gemm_simt_launch(dtype, M, N, K, ss, gather_stride, gather_h, gather_w, W, bias, residual, ldr, res_dtype,
                           act, out, ldo, out_dtype, st);

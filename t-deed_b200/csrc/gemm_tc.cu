@@ -1,25 +1,26 @@
 // (2b) tcgen05 GEMM with fused epilogue — the bf16 backend of tdeed_gemm_fwd.
 //   out[m, n] = act( sum_k A[m, k] * W[n, k] + bias[n] + residual[m, n] ),  A/W bf16, fp32 accumulate
 //
-// sm_100a structure (one output tile of 128 x BLOCK_N per CTA, 6 warps, warp-specialised):
-//   warp 0   TMA producer : cp.async.bulk.tensor 2D loads of the A (128 x 64) and W (BLOCK_N x 64)
-//                           k-blocks into a ring of 128B-swizzled shared-memory stages (mbarrier
-//                           expect_tx / complete_tx)
-//   warp 1   MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128,
-//                           N=BLOCK_N, K=16) four times per k-block, accumulator in TMEM;
-//                           tcgen05.commit releases the smem stage / signals the epilogue.
-//                           This warp also owns tcgen05.alloc / dealloc.
-//   warps 2-5 epilogue    : tcgen05.ld 32x32b (lane = output row) -> bias / residual / activation in
-//                           registers -> 16-byte global stores.
-// A may be a virtual concat of up to two column segments (two tensor maps): the GatedShift concat.
+// sm_100a structure: PERSISTENT CTAs (one per SM) loop over 128 x BLOCK_N output tiles; 6 warps, warp-specialised:
+//   warp 0   TMA producer : cp.async.bulk.tensor loads of the A (128 x 64) and W (BLOCK_N x 64) k-blocks into a
+//                           ring of up to 10 128B-swizzled shared-memory stages (mbarrier expect_tx /
+//                           complete_tx).  The ring runs ahead across tile boundaries, which is what keeps
+//                           enough bytes in flight for the thin-K (K = 24..56) layers that are pure HBM streams.
+//   warp 1   MMA issuer   : one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BLOCK_N, K=16)
+//                           four times per k-block into one of TWO TMEM accumulators; tcgen05.commit releases
+//                           the smem stage / hands the accumulator to the epilogue.  Owns tcgen05.alloc/dealloc.
+//   warps 2-5 epilogue    : tcgen05.ld 32x32b (lane = output row) -> bias / residual / activation in registers
+//                           -> 16-byte global stores, overlapped with the next tile's loads and MMAs.
+// A may be a virtual concat of up to two column segments (two tensor maps): the GatedShift concat; or a 4D
+// strided view of an NHWC tensor (every `stride`-th pixel): the stride-2 1x1 shortcut conv as implicit GEMM.
 // K tails and M / N tails rely on TMA out-of-bounds zero fill and masked stores.
 #include "common.cuh"
 #include <cuda.h>
 
 namespace tdeed {
 
-constexpr int TC_BM = 128, TC_BK = 64, TC_MAX_STAGES = 6;
-constexpr int TC_THREADS = 192;
+constexpr int TC_BM = 128, TC_BK = 64, TC_MAX_STAGES = 10;
+constexpr int TC_THREADS = 320;   // producer warp, MMA warp, 8 epilogue warps
 
 struct TcParams {
   long long M;
@@ -36,6 +37,9 @@ struct TcParams {
   long long ldo;
   int out_dtype;
   uint32_t tmem_cols;
+  int m_tiles, n_tiles;
+  // 4D gather geometry (strided 1x1 conv): an M tile is a bw x bh patch of output pixels of one frame
+  int gather, Ho, Wo, bw, bh, tiles_x, tiles_y;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -72,6 +76,14 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint64_t* ba
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 
@@ -102,28 +114,42 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr) : "memory");
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---------------------------------------------------------------- kernel
-__global__ void __launch_bounds__(TC_THREADS)
+struct TileCoord { int mt, nt; };
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle pattern
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t a_stage_bytes = TC_BM * TC_BK * 2;                 // 16 KB
-  const uint32_t w_stage_bytes = (uint32_t)p.block_n * TC_BK * 2;   // block_n * 128 B (block_n % 16 == 0 -> 1024-aligned for %8)
+  const uint32_t w_stage_bytes = (uint32_t)p.block_n * TC_BK * 2;   // block_n * 128 B
   const uint32_t stage_bytes = a_stage_bytes + ((w_stage_bytes + 1023u) & ~1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.num_stages * stage_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + TC_MAX_STAGES;
-  uint64_t* tmem_full_bar = bars + 2 * TC_MAX_STAGES;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 1);
+  uint64_t* tmem_full_bar = bars + 2 * TC_MAX_STAGES;        // [2]
+  uint64_t* tmem_empty_bar = bars + 2 * TC_MAX_STAGES + 2;   // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 4);
+  float* s_bias = reinterpret_cast<float*>(bars + 2 * TC_MAX_STAGES + 6);   // [n_tiles * block_n], zero padded
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * TC_BM;
-  const int n0 = blockIdx.y * p.block_n;
   const int total_kb = p.nkb[0] + (p.nseg > 1 ? p.nkb[1] : 0);
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const uint32_t a_tx_bytes = p.gather ? (uint32_t)(p.bw * p.bh) * 128u : a_stage_bytes;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a0)) : "memory");
@@ -133,9 +159,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 256);     // every epilogue thread arrives
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < p.n_tiles * p.block_n; i += TC_THREADS) s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -146,20 +176,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   const uint32_t tmem_base = *tmem_base_slot;
 
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer (one lane) =====
     if (lane == 0) {
-      int kb = 0;
-      for (int s = 0; s < p.nseg; ++s) {
-        const CUtensorMap* map_a = (s == 0) ? &map_a0 : &map_a1;
-        for (int i = 0; i < p.nkb[s]; ++i, ++kb) {
-          const int stage = kb % p.num_stages;
-          const uint32_t round = (uint32_t)(kb / p.num_stages);
-          mbar_wait(&empty_bar[stage], (round & 1u) ^ 1u);
-          uint8_t* sa = smem + (size_t)stage * stage_bytes;
-          uint8_t* sw = sa + a_stage_bytes;
-          mbar_expect_tx(&full_bar[stage], a_stage_bytes + w_stage_bytes);
-          tma_load_2d(map_a, &full_bar[stage], sa, p.a_col0[s] + i * TC_BK, m0);
-          tma_load_2d(&map_w, &full_bar[stage], sw, p.w_col0[s] + i * TC_BK, n0);
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+        const int n0 = nt * p.block_n;
+        int c1 = mt * TC_BM, c2 = 0, c3 = 0;
+        if (p.gather) {
+          const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y;
+          c3 = mt / (p.tiles_x * p.tiles_y);
+          c1 = tx * p.bw;
+          c2 = ty * p.bh;
+        }
+        for (int s = 0; s < p.nseg; ++s) {
+          const CUtensorMap* map_a = (s == 0) ? &map_a0 : &map_a1;
+          for (int i = 0; i < p.nkb[s]; ++i, ++it) {
+            const int stage = it % p.num_stages;
+            const uint32_t round = it / p.num_stages;
+            mbar_wait(&empty_bar[stage], (round & 1u) ^ 1u);
+            uint8_t* sa = smem + (size_t)stage * stage_bytes;
+            uint8_t* sw = sa + a_stage_bytes;
+            mbar_expect_tx(&full_bar[stage], a_tx_bytes + w_stage_bytes);
+            if (p.gather) tma_load_4d(map_a, &full_bar[stage], sa, p.a_col0[s] + i * TC_BK, c1, c2, c3);
+            else tma_load_2d(map_a, &full_bar[stage], sa, p.a_col0[s] + i * TC_BK, c1);
+            tma_load_2d(&map_w, &full_bar[stage], sw, p.w_col0[s] + i * TC_BK, n0);
+          }
         }
       }
     }
@@ -167,62 +209,123 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // ===== MMA issuer =====
     // instruction descriptor: D=f32, A=B=bf16, both K-major, N = block_n, M = 128
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-    for (int kb = 0; kb < total_kb; ++kb) {
-      const int stage = kb % p.num_stages;
-      const uint32_t round = (uint32_t)(kb / p.num_stages);
-      mbar_wait(&full_bar[stage], round & 1u);
+    uint32_t it = 0, j = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+      const uint32_t acc = j & 1u;
+      mbar_wait(&tmem_empty_bar[acc], ((j >> 1) & 1u) ^ 1u);     // epilogue has drained this accumulator
       tcgen05_fence_after();
-      if (lane == 0) {
-        const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-        const uint32_t sw = sa + a_stage_bytes;
+      const uint32_t tmem_d = tmem_base + acc * (uint32_t)p.block_n;
+      for (int kb = 0; kb < total_kb; ++kb, ++it) {
+        const int stage = it % p.num_stages;
+        const uint32_t round = it / p.num_stages;
+        mbar_wait(&full_bar[stage], round & 1u);
+        tcgen05_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sw = sa + a_stage_bytes;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k) {
-          const uint64_t adesc = umma_desc_sw128(sa + k * 32);
-          const uint64_t bdesc = umma_desc_sw128(sw + k * 32);
-          umma_bf16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < TC_BK / 16; ++k) {
+            const uint64_t adesc = umma_desc_sw128(sa + k * 32);
+            const uint64_t bdesc = umma_desc_sw128(sw + k * 32);
+            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);                   // frees the smem stage once the MMAs retire
+          if (kb == total_kb - 1) umma_commit(&tmem_full_bar[acc]);
         }
-        umma_commit(&empty_bar[stage]);                   // frees the smem stage once the MMAs retire
-        if (kb == total_kb - 1) umma_commit(tmem_full_bar);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
-    // ===== epilogue: warp w may only touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
+    // ===== epilogue: 8 warps.  Warp w may only touch TMEM lanes [32*(w%4), +32); the two warps of a lane
+    // group split the accumulator's 32-column chunks (even / odd).  Bias comes from shared memory and the
+    // residual chunk is requested before the TMEM load so both latencies overlap. =====
     const int lg = warp & 3;
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
-    const long long m = (long long)m0 + lg * 32 + lane;
-    const bool row_ok = m < p.M;
-    for (int c0 = 0; c0 < p.block_n; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c0, r);
-      tmem_ld_wait();
-      if (!row_ok) continue;
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int n = n0 + c0 + 8 * h;
-        if (n >= p.N) continue;          // N is a multiple of 8
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * h + j]);
-        if (p.bias) {
-          const float4 b0 = *reinterpret_cast<const float4*>(p.bias + n);
-          const float4 b1 = *reinterpret_cast<const float4*>(p.bias + n + 4);
-          v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-          v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-        }
-        if (p.residual) {
-          float rv[8];
-          if (p.res_dtype == TDEED_F32) load8(reinterpret_cast<const float*>(p.residual) + m * p.ldr + n, rv);
-          else load8(reinterpret_cast<const __nv_bfloat16*>(p.residual) + m * p.ldr + n, rv);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] += rv[j];
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = apply_act_rt(v[j], p.act);
-        if (p.out_dtype == TDEED_F32) store8(reinterpret_cast<float*>(p.out) + m * p.ldo + n, v);
-        else store8(reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo + n, v);
+    const int half = (warp - 2) >> 2;
+    const int r = lg * 32 + lane;                           // row inside the tile
+    uint32_t j = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
+      const uint32_t acc = j & 1u;
+      const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
+      const int n0 = nt * p.block_n;
+      long long m;
+      bool row_ok;
+      if (p.gather) {
+        const int tx = mt % p.tiles_x, ty = (mt / p.tiles_x) % p.tiles_y, f = mt / (p.tiles_x * p.tiles_y);
+        const int by = r / p.bw, bx = r - by * p.bw;
+        const int oy = ty * p.bh + by, ox = tx * p.bw + bx;
+        row_ok = (by < p.bh) && (oy < p.Ho) && (ox < p.Wo);
+        m = ((long long)f * p.Ho + oy) * p.Wo + ox;
+      } else {
+        m = (long long)mt * TC_BM + r;
+        row_ok = m < p.M;
       }
+      const uint32_t tmem_row = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * (uint32_t)p.block_n;
+      bool waited = false;
+      for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
+        const int nbase = n0 + c0;
+        if (nbase >= p.N) break;                            // warp-uniform
+        // residual chunk (up to 32 columns) requested first: its latency overlaps the barrier wait / TMEM load
+        uint4 rraw[8];
+        const bool has_res = p.residual != nullptr && row_ok;
+        if (has_res) {
+          if (p.res_dtype == TDEED_F32) {
+            const float* rp = reinterpret_cast<const float*>(p.residual) + m * p.ldr + nbase;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (nbase + 4 * q < p.N) rraw[q] = *reinterpret_cast<const uint4*>(rp + 4 * q);
+          } else {
+            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + m * p.ldr + nbase;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (nbase + 8 * q < p.N) rraw[q] = *reinterpret_cast<const uint4*>(rp + 8 * q);
+          }
+        }
+        if (!waited) {
+          mbar_wait(&tmem_full_bar[acc], (j >> 1) & 1u);
+          tcgen05_fence_after();
+          waited = true;
+        }
+        uint32_t v32[32];
+        tmem_ld32(tmem_row + (uint32_t)c0, v32);
+        tmem_ld_wait();
+        if (!row_ok) continue;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int n = nbase + 8 * h;
+          if (n >= p.N || c0 + 8 * h >= p.block_n) continue;   // N tail / columns of the next n-tile (block_n % 32 == 16)
+          float v[8];
+          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + n);
+          const float4 b1 = *reinterpret_cast<const float4*>(s_bias + n + 4);
+          v[0] = __uint_as_float(v32[8 * h + 0]) + b0.x; v[1] = __uint_as_float(v32[8 * h + 1]) + b0.y;
+          v[2] = __uint_as_float(v32[8 * h + 2]) + b0.z; v[3] = __uint_as_float(v32[8 * h + 3]) + b0.w;
+          v[4] = __uint_as_float(v32[8 * h + 4]) + b1.x; v[5] = __uint_as_float(v32[8 * h + 5]) + b1.y;
+          v[6] = __uint_as_float(v32[8 * h + 6]) + b1.z; v[7] = __uint_as_float(v32[8 * h + 7]) + b1.w;
+          if (has_res) {
+            if (p.res_dtype == TDEED_F32) {
+              const uint4 ra = rraw[2 * h], rb = rraw[2 * h + 1];
+              v[0] += __uint_as_float(ra.x); v[1] += __uint_as_float(ra.y); v[2] += __uint_as_float(ra.z); v[3] += __uint_as_float(ra.w);
+              v[4] += __uint_as_float(rb.x); v[5] += __uint_as_float(rb.y); v[6] += __uint_as_float(rb.z); v[7] += __uint_as_float(rb.w);
+            } else {
+              const uint4 ra = rraw[h];
+              const uint32_t w4[4] = {ra.x, ra.y, ra.z, ra.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                v[2 * q] += __uint_as_float(w4[q] << 16);
+                v[2 * q + 1] += __uint_as_float(w4[q] & 0xffff0000u);
+              }
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = apply_act_rt(v[q], p.act);
+          if (p.out_dtype == TDEED_F32) store8(reinterpret_cast<float*>(p.out) + m * p.ldo + n, v);
+          else store8(reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo + n, v);
+        }
+      }
+      if (!waited) {                                        // this warp had no chunk in this tile: still consume the phase
+        mbar_wait(&tmem_full_bar[acc], (j >> 1) & 1u);
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&tmem_empty_bar[acc]);                    // accumulator may be overwritten
     }
   }
 
@@ -253,24 +356,30 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2D bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, 64 cols], 128B swizzle.
-static int make_map(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+// bf16 tensor of rank `rank` (dims[0] innermost, contiguous); strides in bytes for dims 1..rank-1; 128B swizzle.
+static int make_map(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                    const cuuint32_t* box) {
   EncodeTiledFn enc = get_encode_fn();
   TDEED_REQUIRE(enc != nullptr, TDEED_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
-  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  TDEED_REQUIRE(r == CUDA_SUCCESS, TDEED_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r, rows, cols, ld);
+  TDEED_REQUIRE(r == CUDA_SUCCESS, TDEED_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rank=%d dims=%llu,%llu", (int)r, rank,
+                (unsigned long long)dims[0], (unsigned long long)dims[1]);
   return TDEED_OK;
 }
 
-int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* segs, const void* W, const float* bias,
-                   const void* residual, long long ldr, int res_dtype, int act, void* out, long long ldo,
-                   int out_dtype, cudaStream_t st) {
+static int make_map_2d(CUtensorMap* map, const void* base, long long rows, long long cols, long long ld, int box_rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  return make_map(map, base, 2, dims, strides, box);
+}
+
+int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* segs, int gstride, int gh, int gw,
+                   const void* W, const float* bias, const void* residual, long long ldr, int res_dtype, int act,
+                   void* out, long long ldo, int out_dtype, cudaStream_t st) {
   TDEED_REQUIRE(M > 0 && M < (1LL << 31) - TC_BM, TDEED_ERR_SHAPE, "gemm_tc: M=%lld out of range", M);
   TDEED_REQUIRE(N % 8 == 0 && K % 8 == 0, TDEED_ERR_SHAPE, "gemm_tc: N=%d, K=%d must be multiples of 8", N, K);
   TcParams p{};
@@ -278,19 +387,37 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
   p.bias = bias; p.residual = residual; p.ldr = ldr; p.res_dtype = res_dtype; p.act = act;
   p.out = out; p.ldo = ldo; p.out_dtype = out_dtype;
 
+  // M tiling
+  long long frames = 0;
+  if (gstride > 1) {
+    p.gather = 1;
+    p.Ho = (gh + gstride - 1) / gstride;
+    p.Wo = (gw + gstride - 1) / gstride;
+    TDEED_REQUIRE(M % ((long long)p.Ho * p.Wo) == 0, TDEED_ERR_SHAPE, "gemm_tc: M=%lld is not frames*%d*%d", M, p.Ho, p.Wo);
+    frames = M / ((long long)p.Ho * p.Wo);
+    p.bw = p.Wo < TC_BM ? p.Wo : TC_BM;
+    p.bh = TC_BM / p.bw < p.Ho ? TC_BM / p.bw : p.Ho;
+    p.tiles_x = ceil_div(p.Wo, p.bw);
+    p.tiles_y = ceil_div(p.Ho, p.bh);
+    p.m_tiles = (int)(frames * p.tiles_x * p.tiles_y);
+  } else {
+    p.m_tiles = (int)ceil_div_ll(M, TC_BM);
+  }
+
   // tile width: one tile when N <= 256, else an even split; shrink for skinny-M problems to get more CTAs
-  const int m_tiles = (int)ceil_div_ll(M, TC_BM);
   int n_tiles = ceil_div(N, 256);
   int block_n = ceil_div(ceil_div(N, n_tiles), 16) * 16;
-  while (block_n > 32 && (long long)m_tiles * ceil_div(N, block_n) < kNumSMs) {
+  if (block_n < 32) block_n = 32;
+  while (block_n > 32 && (long long)p.m_tiles * ceil_div(N, block_n) < kNumSMs) {
     const int nb = ceil_div(block_n / 2, 16) * 16;
     if (nb == block_n) break;
     block_n = nb;
   }
-  n_tiles = ceil_div(N, block_n);
+  p.n_tiles = ceil_div(N, block_n);
   p.block_n = block_n;
   uint32_t cols = 32;
-  while ((int)cols < block_n) cols <<= 1;
+  while ((int)cols < 2 * block_n + 16) cols <<= 1;     // two accumulators (+ slack: the epilogue reads 32-column chunks)
+  if (cols > 512) cols = 512;
   p.tmem_cols = cols;
 
   CUtensorMap maps[3];
@@ -303,7 +430,17 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
                   "gemm_tc: segment %d starts at A column %d / W column %d; both must be multiples of 8 (pad the segment)",
                   s, segs[s].col0, wcol);
     // the tensor spans columns [0, col0 + k): loads past it are zero-filled, which implements the K tail
-    int rc = make_map(&maps[s], segs[s].a, M, (long long)segs[s].col0 + segs[s].k, segs[s].lda, TC_BM);
+    const long long cols_a = (long long)segs[s].col0 + segs[s].k;
+    int rc;
+    if (p.gather) {
+      const long long C = segs[s].lda;
+      cuuint64_t dims[4] = {(cuuint64_t)cols_a, (cuuint64_t)p.Wo, (cuuint64_t)p.Ho, (cuuint64_t)frames};
+      cuuint64_t strides[3] = {(cuuint64_t)gstride * C * 2, (cuuint64_t)gstride * gw * C * 2, (cuuint64_t)gh * gw * C * 2};
+      cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)p.bw, (cuuint32_t)p.bh, 1};
+      rc = make_map(&maps[s], segs[s].a, 4, dims, strides, box);
+    } else {
+      rc = make_map_2d(&maps[s], segs[s].a, M, cols_a, segs[s].lda, TC_BM);
+    }
     if (rc) return rc;
     p.nkb[s] = ceil_div(segs[s].k, TC_BK);
     p.a_col0[s] = segs[s].col0;
@@ -313,21 +450,28 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
   }
   if (nseg == 1) maps[1] = maps[0];
   TDEED_REQUIRE((reinterpret_cast<uintptr_t>(W) & 15) == 0, TDEED_ERR_SHAPE, "gemm_tc: W must be 16-byte aligned");
-  int rc = make_map(&maps[2], W, N, K, K, block_n);
+  int rc = make_map_2d(&maps[2], W, N, K, K, block_n);
   if (rc) return rc;
 
   const size_t stage_bytes = (size_t)TC_BM * TC_BK * 2 + (((size_t)block_n * TC_BK * 2 + 1023) & ~(size_t)1023);
-  int stages = total_kb < 4 ? total_kb : 4;
-  if (stages < 1) stages = 1;
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
+  if (stages < 2) stages = 2;
   p.num_stages = stages;
-  const size_t smem = 1024 + stages * stage_bytes + (2 * TC_MAX_STAGES + 2) * sizeof(uint64_t);
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
+  const size_t bias_bytes = (size_t)p.n_tiles * block_n * sizeof(float);
+  const size_t fixed = 1024 + (2 * TC_MAX_STAGES + 6) * sizeof(uint64_t) + bias_bytes;
+  TDEED_REQUIRE(fixed + 2 * stage_bytes <= 227 * 1024, TDEED_ERR_UNSUPPORTED, "gemm_tc: N=%d too wide for the bias staging area", N);
+  while (stages > 2 && fixed + stages * stage_bytes > 227 * 1024) --stages;
+  p.num_stages = stages;
+  const size_t smem = fixed + stages * stage_bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     TDEED_REQUIRE(e == cudaSuccess, TDEED_ERR_CUDA, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-    smem_set = 227 * 1024;
+    attr_set = true;
   }
-  dim3 grid((unsigned)m_tiles, (unsigned)n_tiles);
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
   gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], p);
   return check_launch("tdeed_gemm_fwd(tcgen05)");
 }

@@ -43,6 +43,8 @@ SIGNATURES = {
     'tdeed_last_error': (ctypes.c_char_p, []),
     'tdeed_stem_fwd': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp,
                                c_vp, c_int, c_vp]),
+    'tdeed_stem_tc_fwd': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
+                                  c_vp, c_int, c_vp, c_int, c_vp, c_vp]),
     'tdeed_gemm_fwd': (c_int, [c_int, c_ll, c_int, c_int, ctypes.POINTER(GemmSeg), c_int, c_int, c_int, c_vp, c_vp,
                                c_vp, c_ll, c_int, c_int, c_vp, c_ll, c_int, c_int, c_vp]),
     'tdeed_conv3x3g_fwd': (c_int, [c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),

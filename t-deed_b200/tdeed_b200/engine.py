@@ -90,6 +90,7 @@ class InferenceEngine:
         self.gemm_backend = gemm_backend
         self.launches = 0
         self.prof = None
+        self.fuse_stem = True            # bf16: tcgen05 stem fused with s1.b1.conv1
         self._graphs = {}
         self.load_state(state)
 
@@ -102,6 +103,9 @@ class InferenceEngine:
         sc, sh = _bn_fold(sd, '_features.stem.bn')
         W['stem_w'] = f32(sd['_features.stem.conv.weight'].float() * sc[:, None, None, None])
         W['stem_b'] = f32(sh)
+        w0 = torch.zeros((32, 32), dtype=torch.float32, device=dev)
+        w0[:, :27] = W['stem_w'].reshape(32, 27)
+        W['stem_w_tc'] = w0.to(torch.bfloat16).contiguous()        # tcgen05 stem: K = 27 padded to 32
         gw = REGNET[cfg.backbone]['group_width']
         blocks = []
         for p, cin, cout, stride, shifted in cfg.blocks():
@@ -148,6 +152,11 @@ class InferenceEngine:
                                                 sd[g + '.channel_conv2.weight'].reshape(-1)]))
                     gs['cc_b'] = f32(torch.cat([sd[g + '.channel_conv1.bias'], sd[g + '.channel_conv2.bias']]))
                 b['gs'] = gs
+            if not blocks and not shifted and cin == 32 and cout <= 64:
+                # s1.b1.conv1 fused into the tensor-core stem: rows padded to a multiple of 16
+                wf = torch.zeros(((cout + 15) // 16 * 16, 32), dtype=torch.float32, device=dev)
+                wf[:cout] = w1
+                b['w1_fused'] = wf.to(torch.bfloat16).contiguous()
             blocks.append(b)
         W['blocks'] = blocks
         W['temp_enc'] = f32(sd['temp_enc'])
@@ -233,15 +242,35 @@ class InferenceEngine:
         crop = crop or self.crop_window(in_h, in_w)
         es = 2 if adt == torch.bfloat16 else 4
         oh0, ow0 = (crop[2] + 1) // 2, (crop[3] + 1) // 2
-        x = self._op('stem', 2.0 * n * oh0 * ow0 * 32 * 27, n * (3 * crop[2] * crop[3] * frames.element_size() + oh0 * ow0 * 32 * es),
-                     ops.stem, frames.reshape(n, 3, in_h, in_w), crop, flip, W['stem_w'], W['stem_b'], adt)
+        fuse = adt == torch.bfloat16 and self.fuse_stem and 'w1_fused' in W['blocks'][0] and taps is None
+        a1_fused = None
+        if fuse:
+            # tcgen05 stem + s1.b1.conv1 in one kernel; only the stride-2 subsample of the stem output (the
+            # shortcut conv's input) and conv1's output reach HBM
+            c1 = W['blocks'][0]['cout']
+            x_sub, a1_fused = self._op('stem', 2.0 * n * oh0 * ow0 * 32 * (27 + c1),
+                                       n * (3 * crop[2] * crop[3] * frames.element_size() + oh0 * ow0 * (c1 + 8) * es),
+                                       ops.stem_tc, frames.reshape(n, 3, in_h, in_w), crop, flip, W['stem_w_tc'], W['stem_b'],
+                                       W['blocks'][0]['w1_fused'], W['blocks'][0]['b1'], c1, True, 2)
+            x = None
+        elif adt == torch.bfloat16 and self.fuse_stem:
+            x, _ = self._op('stem', 2.0 * n * oh0 * ow0 * 32 * 27, n * (3 * crop[2] * crop[3] * frames.element_size() + oh0 * ow0 * 32 * es),
+                            ops.stem_tc, frames.reshape(n, 3, in_h, in_w), crop, flip, W['stem_w_tc'], W['stem_b'])
+        else:
+            x = self._op('stem', 2.0 * n * oh0 * ow0 * 32 * 27, n * (3 * crop[2] * crop[3] * frames.element_size() + oh0 * ow0 * 32 * es),
+                         ops.stem, frames.reshape(n, 3, in_h, in_w), crop, flip, W['stem_w'], W['stem_b'], adt)
         if taps is not None:
             taps['stem'] = x
         for bi, blk in enumerate(W['blocks']):
-            _, h, w, cin = x.shape
+            if bi == 0 and a1_fused is not None:
+                h, w, cin = oh0, ow0, 32
+            else:
+                _, h, w, cin = x.shape
             cout, stride = blk['cout'], blk['stride']
             m = n * h * w
-            if blk['shifted']:
+            if bi == 0 and a1_fused is not None:
+                pass
+            elif blk['shifted']:
                 gs = blk['gs']
                 fd = gs['fold']
                 ws = torch.empty(ops.gsf_workspace_floats(b, t, h, w, fd), dtype=torch.float32, device=x.device)
@@ -252,14 +281,20 @@ class InferenceEngine:
                 segs = [(gso, gso.shape[1], 0, gso.shape[1]), (x, cin, blk['x_start'], cin - blk['x_start'])]
             else:
                 segs = [(x, cin, 0, cin)]
-            a1 = self._gemm(segs, blk['w1'], blk['b1'], label='conv1x1', act=L.ACT_RELU, rows=m).view(n, h, w, cout)
+            if bi == 0 and a1_fused is not None:
+                a1 = a1_fused
+            else:
+                a1 = self._gemm(segs, blk['w1'], blk['b1'], label='conv1x1', act=L.ACT_RELU, rows=m).view(n, h, w, cout)
             oh, ow = (h + stride - 1) // stride, (w + stride - 1) // stride
             mo = n * oh * ow
             a2 = self._op('conv3x3g', 2.0 * mo * cout * 9 * blk['gw'], (m + mo) * cout * es + cout * 9 * blk['gw'] * 4,
                           ops.conv3x3g, a1, blk['w2'], blk['b2'], blk['gw'], stride)
             self._op('se', 4.0 * n * cout * blk['se_w1'].shape[0], 2 * mo * cout * es,
                      ops.se_, a2, blk['se_w1'], blk['se_b1'], blk['se_w2'], blk['se_b2'])
-            if 'wd' in blk:
+            if bi == 0 and a1_fused is not None:
+                # the stem kernel already wrote the stride-2 subsample: plain GEMM, no gather
+                res = self._gemm([(x_sub, 32, 0, 32)], blk['wd'], blk['bd'], label='conv1x1_ds', rows=mo)
+            elif 'wd' in blk:
                 res = self._gemm([(x, cin, 0, cin)], blk['wd'], blk['bd'], label='conv1x1_ds', rows=mo,
                                  gather=(stride, h, w) if stride > 1 else None)
             else:

@@ -21,6 +21,21 @@ def stem(frames, crop, flip, weight, bias, out_dtype):
     return out
 
 
+def stem_tc(frames, crop, flip, w0, b0, w1=None, b1=None, n1=0, want_stem=True, stem_sub=1):
+    """bf16 tcgen05 stem (+ fused s1.b1.conv1).  Returns (stem_out | None, conv1_out | None), both NHWC bf16."""
+    n, _, in_h, in_w = frames.shape
+    cy, cx, h, w = crop
+    oh, ow = (h + 1) // 2, (w + 1) // 2
+    dev = frames.device
+    out_stem = torch.empty((n, (oh + stem_sub - 1) // stem_sub, (ow + stem_sub - 1) // stem_sub, 32),
+                           dtype=torch.bfloat16, device=dev) if want_stem else None
+    out_c1 = torch.empty((n, oh, ow, n1), dtype=torch.bfloat16, device=dev) if w1 is not None else None
+    L.check(L.load().tdeed_stem_tc_fwd(L.ptr(frames), L.dtype_code(frames.dtype), n, in_h, in_w, cy, cx, h, w,
+                                       int(bool(flip)), L.ptr(w0), L.ptr(b0), L.ptr(w1), L.ptr(b1), n1,
+                                       L.ptr(out_stem), stem_sub, L.ptr(out_c1), L.stream()), 'stem_tc')
+    return out_stem, out_c1
+
+
 def gemm(segs, weight, bias=None, residual=None, act=L.ACT_NONE, out=None, out_dtype=None, gather=None,
          backend=L.GEMM_AUTO, rows=None):
     """out[M,N] = act(concat_k(segs) @ weight.T + bias + residual).

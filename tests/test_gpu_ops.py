@@ -83,6 +83,15 @@ def test_gemm_tcgen05_bf16(dev, m, n, ks):
         assert _gemm_case(dev, torch.bfloat16, m, n, ks, act, res, L.GEMM_TCGEN05) < 2e-5
 
 
+@pytest.mark.parametrize('n,k,gather', [(152, 56, (2, 3, 14, 10)), (56, 24, (2, 2, 7, 9)), (24, 32, (2, 1, 6, 300)),
+                                         (368, 152, (2, 5, 14, 14)), (128, 64, (2, 3, 56, 100))])
+def test_gemm_tcgen05_strided_gather(dev, n, k, gather):
+    """Stride-2 1x1 shortcut conv as implicit GEMM: A is a 4D strided TMA view of the NHWC input."""
+    from tdeed_b200 import _lib as L
+    for act, res in ((L.ACT_NONE, False), (L.ACT_RELU, True)):
+        assert _gemm_case(dev, torch.bfloat16, 0, n, (k,), act, res, L.GEMM_TCGEN05, gather=gather) < 2e-5
+
+
 def _nhwc(x):
     return x.permute(0, 2, 3, 1).contiguous()
 
@@ -108,6 +117,36 @@ def test_stem(dev, in_dtype, flip):
     assert rel_err(_nchw(out), ref) < 1e-5
     out16 = ops.stem(frames.to(in_dtype).to(dev), crop, flip, w.to(dev), b.to(dev), torch.bfloat16)
     assert rel_err(_nchw(out16), ref) < 6e-3
+
+
+@pytest.mark.parametrize('in_dtype', [torch.uint8, torch.float32])
+@pytest.mark.parametrize('flip,n1', [(False, 24), (True, 64), (False, 0)])
+def test_stem_tcgen05_fused_conv1(dev, in_dtype, flip, n1):
+    """tcgen05 stem (+ fused s1.b1.conv1) vs the fp32 oracle computed on the same bf16-rounded operands."""
+    from tdeed_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    frames = torch.randint(0, 256, (3, 3, 70, 90), generator=g, dtype=torch.uint8)
+    w = (torch.randn(32, 3, 3, 3, generator=g) * 0.2).to(torch.bfloat16).float()
+    b = torch.randn(32, generator=g) * 0.1
+    crop = (2, 5, 67, 83)                                   # odd sizes: partial tiles in both directions
+    x = frames[None, :, :, 2:69, 5:88]
+    xn = O.preprocess(x, O.Config(crop_dim=None), flip=flip).to(torch.bfloat16).float()
+    stem_ref = torch.relu(torch.nn.functional.conv2d(xn, w, b, stride=2, padding=1))
+    w0 = torch.zeros(32, 32)
+    w0[:, :27] = w.reshape(32, 27)
+    args = (frames.to(in_dtype).to(dev), crop, flip, w0.to(torch.bfloat16).to(dev), b.to(dev))
+    if n1 == 0:
+        out, _ = ops.stem_tc(*args)
+        assert rel_err(_nchw(out), stem_ref) < 6e-3
+        return
+    w1 = (torch.randn(n1, 32, generator=g) / math.sqrt(32)).to(torch.bfloat16).float()
+    b1 = torch.randn(n1, generator=g) * 0.1
+    c1_ref = torch.relu(torch.nn.functional.conv2d(stem_ref.to(torch.bfloat16).float(), w1[:, :, None, None], b1))
+    w1p = torch.zeros((n1 + 15) // 16 * 16, 32)
+    w1p[:n1] = w1
+    sub, c1 = ops.stem_tc(*args, w1p.to(torch.bfloat16).to(dev), b1.to(dev), n1, True, 2)
+    assert rel_err(_nchw(sub), stem_ref[:, :, ::2, ::2]) < 6e-3
+    assert rel_err(_nchw(c1), c1_ref) < 8e-3
 
 
 @pytest.mark.parametrize('c,gw,stride,h,w', [(24, 8, 2, 20, 22), (152, 8, 1, 7, 9), (368, 8, 2, 14, 14),
