@@ -1,0 +1,254 @@
+// (3b) grouped 3x3 convolution (+folded BN + ReLU) on tcgen05 — the bf16 backend of timm Bottleneck.conv2
+// (group width 8 or 16, stride 1 or 2, pad 1).
+//
+// Implicit GEMM without im2col.  Output pixels are enumerated in a zero-padded "position space": every frame is
+// a (Ho+pad) x (Wo+pad) grid, so a 3x3 tap is a CONSTANT offset in linear position for every pixel of every frame.
+// A CTA tile is 128 consecutive positions (= the 128 TMEM lanes / GEMM rows).  The input window of the tile is
+// staged once in shared memory as planes [8-channel chunk][position][16 B] — which is exactly the canonical
+// K-major no-swizzle UMMA operand layout with SBO = 128 B and LBO = plane pitch — so the A operand of tap
+// (dy, dx) is the SAME shared-memory data addressed through a descriptor whose start address is shifted by the
+// tap offset: 9 tcgen05.mma (M=128, N=16, K=16) per 16-channel pair accumulate the whole 3x3 kernel in TMEM.
+// A pair is two width-8 groups (block-diagonal 16x16 weight tile) or one width-16 group (dense tile).
+// Stride 2 uses four parity planes (even/odd row x even/odd column) so taps stay unit-stride.
+// Weights of the CTA's channel block stay resident in shared memory; CTAs are persistent over position tiles,
+// several per SM so that staging, MMA and epilogue of different tiles overlap.
+#include "common.cuh"
+
+namespace tdeed {
+
+constexpr int C3T_THREADS = 128;
+constexpr int C3T_MAX_PAIRS = 8;     // 128 channels per CTA
+
+struct C3TParams {
+  const __nv_bfloat16* in;
+  __nv_bfloat16* out;
+  const float* bias;
+  const uint8_t* wimg;       // [pairs_total][9][512 B] canonical UMMA B tiles
+  int n, H, W, C, Ho, Wo, stride;
+  int GH, GW, G;             // padded position grid per frame
+  long long total_pos;
+  int ntiles;
+  int nplanes;
+  int tap_plane[9], tap_off[9];
+  int min_off, npos, npos_pad;
+  int nchunks_real, pairs_total, pairs_blk;
+  uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ uint32_t c3_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint64_t c3_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;          // Blackwell descriptor version; layout type 0 = no swizzle
+  return d;
+}
+__device__ __forceinline__ void c3_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void c3_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ bool c3_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(c3_smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void c3_wait(uint64_t* bar, uint32_t parity) {
+  if (c3_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!c3_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("tdeed conv3x3g_tc: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+__global__ void __launch_bounds__(C3T_THREADS)
+conv3x3g_tc_kernel(const C3TParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int pair0 = blockIdx.y * p.pairs_blk;
+  const int np = min(p.pairs_blk, p.pairs_total - pair0);
+  const int nch = 2 * np;                        // staged chunk planes (a trailing zero plane pads odd chunk counts)
+  const int chunk0 = 2 * pair0;
+  uint8_t* sW = smem;                                              // [pairs_blk][9][512]
+  uint8_t* sIn = sW + (size_t)p.pairs_blk * 9 * 512;               // [nplanes][nch][npos_pad][16]
+  float* s_bias = reinterpret_cast<float*>(sIn + (size_t)p.nplanes * 2 * p.pairs_blk * p.npos_pad * 16);
+  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + p.pairs_blk * 16);
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
+
+  for (int i = tid; i < np * 9 * 32; i += C3T_THREADS)
+    reinterpret_cast<uint4*>(sW)[i] = reinterpret_cast<const uint4*>(p.wimg + (size_t)pair0 * 9 * 512)[i];
+  for (int i = tid; i < np * 16; i += C3T_THREADS) {
+    const int ch = pair0 * 16 + i;
+    s_bias[i] = ch < p.C ? p.bias[ch] : 0.f;
+  }
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(c3_smem_u32(s_bar)), "r"(1));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(c3_smem_u32(s_tmem)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *s_tmem;
+  const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t plane_bytes = (uint32_t)p.npos_pad * 16u;
+  uint32_t phase = 0;
+
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+    const long long q0 = (long long)tile * 128;
+    const long long q_lo = q0 + p.min_off;
+
+    // ---- stage the input window: [plane][chunk][position] of 16-byte (8-channel) vectors ----
+    const int per_pos = p.nplanes * nch;
+    for (int i = tid; i < p.npos * per_pos; i += C3T_THREADS) {
+      const int c = i % nch, pl = (i / nch) % p.nplanes, s = i / per_pos;
+      const long long L = q_lo + s;
+      uint4 v = make_uint4(0u, 0u, 0u, 0u);
+      if (L >= 0 && L < p.total_pos && chunk0 + c < p.nchunks_real) {
+        const int f = (int)(L / p.G);
+        const int rem = (int)(L - (long long)f * p.G);
+        const int U = rem / p.GW, V = rem - U * p.GW;
+        const int iy = p.stride * (U - 1) + (pl >> 1), ix = p.stride * (V - 1) + (pl & 1);
+        if (U >= 1 && V >= 1 && iy < p.H && ix < p.W)
+          v = *reinterpret_cast<const uint4*>(p.in + (((size_t)f * p.H + iy) * p.W + ix) * p.C + (size_t)(chunk0 + c) * 8);
+      }
+      *reinterpret_cast<uint4*>(sIn + ((size_t)(pl * nch + c) * p.npos_pad + s) * 16) = v;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // previous tile's tcgen05.ld are complete
+    __syncthreads();
+
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t a0 = c3_smem_u32(sIn), b0 = c3_smem_u32(sW);
+      for (int pp = 0; pp < np; ++pp) {
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+          const uint32_t a = a0 + ((uint32_t)(p.tap_plane[t] * nch + 2 * pp) * (uint32_t)p.npos_pad + (uint32_t)(p.tap_off[t] - p.min_off)) * 16u;
+          const uint32_t b = b0 + (uint32_t)(pp * 9 + t) * 512u;
+          c3_umma(tmem_base + (uint32_t)pp * 16u, c3_desc(a, plane_bytes, 128u), c3_desc(b, 128u, 256u), idesc, t != 0 ? 1u : 0u);
+        }
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(c3_smem_u32(s_bar)) : "memory");
+    }
+    c3_wait(s_bar, phase);
+    phase ^= 1u;
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+
+    // ---- epilogue: row = position; bias + ReLU -> bf16 NHWC ----
+    const long long L = q0 + tid;
+    bool ok = L < p.total_pos;
+    size_t obase = 0;
+    if (ok) {
+      const int f = (int)(L / p.G);
+      const int rem = (int)(L - (long long)f * p.G);
+      const int U = rem / p.GW, V = rem - U * p.GW;
+      ok = U >= 1 && U <= p.Ho && V >= 1 && V <= p.Wo;
+      obase = (((size_t)f * p.Ho + (U - 1)) * p.Wo + (V - 1)) * p.C + (size_t)pair0 * 16;
+    }
+    for (int pp = 0; pp < np; ++pp) {
+      uint32_t v32[16];
+      c3_ld16(tmem_lane + (uint32_t)pp * 16u, v32);
+      if (!ok) continue;
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        if (pair0 * 16 + pp * 16 + 8 * hh >= p.C) continue;
+        float v[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] = fmaxf(__uint_as_float(v32[8 * hh + q]) + s_bias[pp * 16 + 8 * hh + q], 0.f);
+        store8(p.out + obase + pp * 16 + 8 * hh, v);
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+}  // namespace tdeed
+
+extern "C" int tdeed_conv3x3g_tc_fwd(const void* in, int n, int h, int w, int c, int stride, const void* wimg,
+                                     const float* bias, void* out, void* stream) {
+  using namespace tdeed;
+  TDEED_REQUIRE(in && wimg && bias && out, TDEED_ERR_SHAPE, "tdeed_conv3x3g_tc_fwd: null pointer");
+  TDEED_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && (stride == 1 || stride == 2), TDEED_ERR_SHAPE,
+                "tdeed_conv3x3g_tc_fwd: bad shape n=%d %dx%dx%d stride=%d", n, h, w, c, stride);
+  C3TParams p{};
+  p.in = (const __nv_bfloat16*)in; p.out = (__nv_bfloat16*)out; p.bias = bias; p.wimg = (const uint8_t*)wimg;
+  p.n = n; p.H = h; p.W = w; p.C = c; p.stride = stride;
+  p.Ho = (h + stride - 1) / stride; p.Wo = (w + stride - 1) / stride;
+  if (stride == 1) {
+    p.GH = h + 2; p.GW = w + 2; p.nplanes = 1;
+    for (int t = 0; t < 9; ++t) { p.tap_plane[t] = 0; p.tap_off[t] = (t / 3 - 1) * p.GW + (t % 3 - 1); }
+    p.min_off = -p.GW - 1;
+    p.npos = 128 + 2 * p.GW + 2;
+  } else {
+    p.GH = p.Ho + 1; p.GW = p.Wo + 1; p.nplanes = 4;
+    for (int t = 0; t < 9; ++t) {
+      const int dy = t / 3, dx = t % 3;
+      p.tap_plane[t] = ((dy != 1) ? 2 : 0) + ((dx != 1) ? 1 : 0);
+      p.tap_off[t] = -(dy == 0 ? p.GW : 0) - (dx == 0 ? 1 : 0);
+    }
+    p.min_off = -p.GW - 1;
+    p.npos = 128 + p.GW + 1;
+  }
+  p.npos_pad = p.npos | 1;                      // odd plane pitch: conflict-free 16-byte staging stores
+  p.G = p.GH * p.GW;
+  p.total_pos = (long long)n * p.G;
+  const long long nt = ceil_div_ll(p.total_pos, 128);
+  TDEED_REQUIRE(nt < (1LL << 31), TDEED_ERR_SHAPE, "tdeed_conv3x3g_tc_fwd: too many tiles");
+  p.ntiles = (int)nt;
+  p.nchunks_real = c / 8;
+  p.pairs_total = (c + 15) / 16;
+  const int nblk = ceil_div(p.pairs_total, C3T_MAX_PAIRS);
+  p.pairs_blk = ceil_div(p.pairs_total, nblk);
+  uint32_t cols = 32;
+  while ((int)cols < p.pairs_blk * 16) cols <<= 1;
+  p.tmem_cols = cols;
+  const size_t smem = (size_t)p.pairs_blk * 9 * 512 + (size_t)p.nplanes * 2 * p.pairs_blk * p.npos_pad * 16 +
+                      (size_t)p.pairs_blk * 16 * sizeof(float) + 16;
+  TDEED_REQUIRE(smem <= 227 * 1024, TDEED_ERR_UNSUPPORTED, "tdeed_conv3x3g_tc_fwd: width %d needs %zu B of shared memory", w, smem);
+  static size_t smem_set = 48 * 1024;
+  if (smem > smem_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3g_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    TDEED_REQUIRE(e == cudaSuccess, TDEED_ERR_CUDA, "tdeed_conv3x3g_tc_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    smem_set = 227 * 1024;
+  }
+  int per_sm = (int)((220 * 1024) / smem);
+  if (per_sm > 512 / (int)cols) per_sm = 512 / (int)cols;
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  int gx = (kNumSMs * per_sm) / nblk;
+  if (gx < 1) gx = 1;
+  if (gx > p.ntiles) gx = p.ntiles;
+  conv3x3g_tc_kernel<<<dim3(gx, nblk), C3T_THREADS, smem, (cudaStream_t)stream>>>(p);
+  return check_launch("tdeed_conv3x3g_tc_fwd");
+}
