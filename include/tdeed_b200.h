@@ -101,6 +101,12 @@ int tdeed_gemm_fwd(int dtype, long long M, int N, int nseg, const tdeed_gemm_seg
 int tdeed_conv3x3g_fwd(int dtype, const void* in, int n, int h, int w, int c, int group_width, int stride,
                        const float* weight, const float* bias, void* out, void* stream);
 
+/* (3b) tcgen05 variant of (3) for bf16 activations.  wimg: the weights as UMMA B tiles, bf16
+ * [ceil(c/16)][9 taps][16 out][16 in] per 16-channel pair (block-diagonal for group width 8), each tile stored in
+ * the canonical K-major no-swizzle layout [n/8][k/8][n%8][k%8] (512 B) — see tdeed_b200/engine.py:conv3_weight_image. */
+int tdeed_conv3x3g_tc_fwd(const void* in, int n, int h, int w, int c, int stride, const void* wimg,
+                          const float* bias, void* out, void* stream);
+
 /* (4) squeeze-excite, in place: x *= sigmoid(fc2(relu(fc1(mean_hw(x))))).  timm SEModule.
  * x: NHWC [n, hw, c]; w1 [rd][c], b1 [rd], w2 [c][rd], b2 [c] fp32. */
 int tdeed_se_fwd(int dtype, void* x, int n, int hw, int c, int rd,

@@ -88,11 +88,15 @@ conv3x3g_tc_kernel(const C3TParams p) {
   const int np = min(p.pairs_blk, p.pairs_total - pair0);
   const int nch = 2 * np;                        // staged chunk planes (a trailing zero plane pads odd chunk counts)
   const int chunk0 = 2 * pair0;
+  // ceil(2^24 / d): (i * m) >> 24 is the exact quotient for i < 2^16
+  const uint32_t div_nch = ((1u << 24) + (uint32_t)nch - 1u) / (uint32_t)nch;
+  const uint32_t div_perpos = ((1u << 24) + (uint32_t)(p.nplanes * nch) - 1u) / (uint32_t)(p.nplanes * nch);
   uint8_t* sW = smem;                                              // [pairs_blk][9][512]
   uint8_t* sIn = sW + (size_t)p.pairs_blk * 9 * 512;               // [nplanes][nch][npos_pad][16]
   float* s_bias = reinterpret_cast<float*>(sIn + (size_t)p.nplanes * 2 * p.pairs_blk * p.npos_pad * 16);
   uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + p.pairs_blk * 16);
   uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
+  int* s_tbl = reinterpret_cast<int*>(s_bar + 2);                  // [npos][nplanes]
 
   for (int i = tid; i < np * 9 * 32; i += C3T_THREADS)
     reinterpret_cast<uint4*>(sW)[i] = reinterpret_cast<const uint4*>(p.wimg + (size_t)pair0 * 9 * 512)[i];
@@ -122,22 +126,38 @@ conv3x3g_tc_kernel(const C3TParams p) {
     const long long q0 = (long long)tile * 128;
     const long long q_lo = q0 + p.min_off;
 
-    // ---- stage the input window: [plane][chunk][position] of 16-byte (8-channel) vectors ----
-    const int per_pos = p.nplanes * nch;
-    for (int i = tid; i < p.npos * per_pos; i += C3T_THREADS) {
-      const int c = i % nch, pl = (i / nch) % p.nplanes, s = i / per_pos;
+    // ---- per-tile position table: pixel index of every staged (position, parity plane), or -1 for padding ----
+    for (int e = tid; e < p.npos * p.nplanes; e += C3T_THREADS) {
+      const int s = e / p.nplanes, pl = e - s * p.nplanes;
       const long long L = q_lo + s;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (L >= 0 && L < p.total_pos && chunk0 + c < p.nchunks_real) {
-        const int f = (int)(L / p.G);
-        const int rem = (int)(L - (long long)f * p.G);
+      int pix = -1;
+      if (L >= 0 && L < p.total_pos) {
+        const int Li = (int)L;
+        const int f = Li / p.G;
+        const int rem = Li - f * p.G;
         const int U = rem / p.GW, V = rem - U * p.GW;
         const int iy = p.stride * (U - 1) + (pl >> 1), ix = p.stride * (V - 1) + (pl & 1);
-        if (U >= 1 && V >= 1 && iy < p.H && ix < p.W)
-          v = *reinterpret_cast<const uint4*>(p.in + (((size_t)f * p.H + iy) * p.W + ix) * p.C + (size_t)(chunk0 + c) * 8);
+        if (U >= 1 && V >= 1 && iy < p.H && ix < p.W) pix = (f * p.H + iy) * p.W + ix;
       }
-      *reinterpret_cast<uint4*>(sIn + ((size_t)(pl * nch + c) * p.npos_pad + s) * 16) = v;
+      s_tbl[e] = pix;
     }
+    __syncthreads();
+    // ---- stage the input window with cp.async (zero-fill for padding): [plane][chunk][position] x 16 B ----
+    const int per_pos = p.nplanes * nch;
+    const uint32_t sIn_u32 = c3_smem_u32(sIn);
+    for (int i = tid; i < p.npos * per_pos; i += C3T_THREADS) {
+      const int s = (int)(((unsigned long long)i * div_perpos) >> 24);
+      const int j = i - s * per_pos;
+      const int pl = (int)(((unsigned long long)j * div_nch) >> 24);
+      const int c = j - pl * nch;
+      const int pix = s_tbl[s * p.nplanes + pl];
+      const bool valid = pix >= 0 && chunk0 + c < p.nchunks_real;
+      const __nv_bfloat16* src = valid ? p.in + (size_t)pix * p.C + (size_t)(chunk0 + c) * 8 : p.in;
+      const uint32_t dst = sIn_u32 + (uint32_t)((pl * nch + c) * p.npos_pad + s) * 16u;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // previous tile's tcgen05.ld are complete
     __syncthreads();
@@ -234,7 +254,8 @@ extern "C" int tdeed_conv3x3g_tc_fwd(const void* in, int n, int h, int w, int c,
   while ((int)cols < p.pairs_blk * 16) cols <<= 1;
   p.tmem_cols = cols;
   const size_t smem = (size_t)p.pairs_blk * 9 * 512 + (size_t)p.nplanes * 2 * p.pairs_blk * p.npos_pad * 16 +
-                      (size_t)p.pairs_blk * 16 * sizeof(float) + 16;
+                      (size_t)p.pairs_blk * 16 * sizeof(float) + 16 + (size_t)p.npos * p.nplanes * sizeof(int);
+  TDEED_REQUIRE((long long)p.npos * p.nplanes * 2 * p.pairs_blk < 65536, TDEED_ERR_UNSUPPORTED, "tdeed_conv3x3g_tc_fwd: tile too large");
   TDEED_REQUIRE(smem <= 227 * 1024, TDEED_ERR_UNSUPPORTED, "tdeed_conv3x3g_tc_fwd: width %d needs %zu B of shared memory", w, smem);
   static size_t smem_set = 48 * 1024;
   if (smem > smem_set) {

@@ -91,6 +91,7 @@ class InferenceEngine:
         self.launches = 0
         self.prof = None
         self.fuse_stem = True            # bf16: tcgen05 stem fused with s1.b1.conv1
+        self.conv3_tc = True             # bf16: grouped 3x3 conv on tcgen05
         self._graphs = {}
         self.load_state(state)
 
@@ -129,6 +130,8 @@ class InferenceEngine:
             sc, sh = _bn_fold(sd, p + '.conv2.bn')
             b['w2'] = f32(sd[p + '.conv2.conv.weight'].float() * sc[:, None, None, None])
             b['b2'] = f32(sh)
+            if adt == torch.bfloat16:
+                b['w2_img'] = ops.conv3_weight_image(b['w2'], gw)      # tcgen05 B tiles
             rd = sd[p + '.se.fc1.weight'].shape[0]
             b['se_w1'] = f32(sd[p + '.se.fc1.weight'].reshape(rd, cout))
             b['se_b1'] = f32(sd[p + '.se.fc1.bias'])
@@ -287,8 +290,12 @@ class InferenceEngine:
                 a1 = self._gemm(segs, blk['w1'], blk['b1'], label='conv1x1', act=L.ACT_RELU, rows=m).view(n, h, w, cout)
             oh, ow = (h + stride - 1) // stride, (w + stride - 1) // stride
             mo = n * oh * ow
-            a2 = self._op('conv3x3g', 2.0 * mo * cout * 9 * blk['gw'], (m + mo) * cout * es + cout * 9 * blk['gw'] * 4,
-                          ops.conv3x3g, a1, blk['w2'], blk['b2'], blk['gw'], stride)
+            if 'w2_img' in blk and self.conv3_tc:
+                a2 = self._op('conv3x3g', 2.0 * mo * cout * 9 * blk['gw'], (m + mo) * cout * es + cout * 9 * blk['gw'] * 4,
+                              ops.conv3x3g_tc, a1, blk['w2_img'], blk['b2'], stride)
+            else:
+                a2 = self._op('conv3x3g', 2.0 * mo * cout * 9 * blk['gw'], (m + mo) * cout * es + cout * 9 * blk['gw'] * 4,
+                              ops.conv3x3g, a1, blk['w2'], blk['b2'], blk['gw'], stride)
             self._op('se', 4.0 * n * cout * blk['se_w1'].shape[0], 2 * mo * cout * es,
                      ops.se_, a2, blk['se_w1'], blk['se_b1'], blk['se_w2'], blk['se_b2'])
             if bi == 0 and a1_fused is not None:

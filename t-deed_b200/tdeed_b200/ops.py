@@ -71,6 +71,29 @@ def conv3x3g(x, weight, bias, group_width, stride, out=None):
     return out
 
 
+def conv3_weight_image(w, group_width):
+    """Folded conv2 weights fp32 [C][gw][3][3] -> bf16 UMMA B tiles [ceil(C/16)][9][16 out][16 in] in the canonical
+    K-major no-swizzle layout ([n/8][k/8][n%8][k%8], 512 B per tile) consumed by tdeed_conv3x3g_tc_fwd."""
+    c = w.shape[0]
+    pairs = (c + 15) // 16
+    co = torch.arange(c, device=w.device)
+    tiles = torch.zeros((pairs, 9, 16, 16), dtype=torch.float32, device=w.device)
+    for ci in range(group_width):
+        k = (co // group_width) * group_width + ci - 16 * (co // 16)
+        tiles[co // 16, :, co % 16, k] = w[:, ci].reshape(c, 9).float()
+    img = tiles.reshape(pairs, 9, 2, 8, 2, 8).permute(0, 1, 2, 4, 3, 5).contiguous()
+    return img.to(torch.bfloat16).reshape(-1)
+
+
+def conv3x3g_tc(x, wimg, bias, stride, out=None):
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty((n, (h + stride - 1) // stride, (w + stride - 1) // stride, c), dtype=x.dtype, device=x.device)
+    L.check(L.load().tdeed_conv3x3g_tc_fwd(L.ptr(x), n, h, w, c, stride, L.ptr(wimg), L.ptr(bias), L.ptr(out), L.stream()),
+            'conv3x3g_tc')
+    return out
+
+
 def se_(x, w1, b1, w2, b2):
     n, h, w, c = x.shape
     L.check(L.load().tdeed_se_fwd(L.dtype_code(x.dtype), L.ptr(x), n, h * w, c, w1.shape[0], L.ptr(w1), L.ptr(b1),

@@ -166,6 +166,22 @@ def test_conv3x3g(dev, c, gw, stride, h, w):
     assert rel_err(_nchw(outb), refb) < 6e-3
 
 
+@pytest.mark.parametrize('c,gw,stride,h,w,n', [(24, 8, 2, 20, 22, 3), (24, 8, 2, 21, 19, 2), (56, 8, 2, 12, 12, 5),
+                                                (152, 8, 1, 7, 9, 4), (368, 8, 2, 14, 14, 3), (368, 8, 1, 7, 7, 9),
+                                                (64, 16, 2, 12, 10, 3), (320, 16, 1, 5, 6, 4), (768, 16, 1, 7, 7, 3)])
+def test_conv3x3g_tcgen05(dev, c, gw, stride, h, w, n):
+    """tcgen05 shifted-descriptor implicit GEMM vs F.conv2d on the same bf16-rounded operands."""
+    from tdeed_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(n, c, h, w, generator=g).to(torch.bfloat16)
+    wt = (torch.randn(c, gw, 3, 3, generator=g) / math.sqrt(9 * gw)).to(torch.bfloat16).float()
+    b = torch.randn(c, generator=g) * 0.1
+    ref = torch.relu(torch.nn.functional.conv2d(x.float(), wt, b, stride=stride, padding=1, groups=c // gw))
+    out = ops.conv3x3g_tc(_nhwc(x).to(dev), ops.conv3_weight_image(wt.to(dev), gw), b.to(dev), stride)
+    assert tuple(out.shape) == (n, ref.shape[2], ref.shape[3], c)
+    assert rel_err(_nchw(out), ref) < 6e-3
+
+
 @pytest.mark.parametrize('c,rd,hw', [(24, 8, (9, 7)), (368, 92, (7, 7)), (768, 192, (4, 5))])
 def test_se_and_pool(dev, c, rd, hw):
     from tdeed_b200 import ops
