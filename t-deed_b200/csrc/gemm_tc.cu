@@ -363,7 +363,11 @@ static int make_map(CUtensorMap* map, const void* base, int rank, const cuuint64
   TDEED_REQUIRE(enc != nullptr, TDEED_ERR_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   // rows narrower than the 128-byte box (K = 24..56 layers) are contiguous in memory: promoting every
+                   // row request to 256 B made TMA pull 2.5x the tensor over the crossbar (ncu r1c) -> no promotion there
+                   dims[0] * 2 >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                      : (dims[0] * 2 >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_NONE),
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   TDEED_REQUIRE(r == CUDA_SUCCESS, TDEED_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rank=%d dims=%llu,%llu", (int)r, rank,
                 (unsigned long long)dims[0], (unsigned long long)dims[1]);

@@ -36,7 +36,7 @@ __device__ inline void frame_channel_sums(const T* __restrict__ x, int hw, int c
 template <typename T>
 __global__ void __launch_bounds__(SE_THREADS)
 se_kernel(T* __restrict__ x, int hw, int c, int rd, const float* __restrict__ w1, const float* __restrict__ b1,
-          const float* __restrict__ w2, const float* __restrict__ b2) {
+          const float* __restrict__ w2t, const float* __restrict__ b2) {
   extern __shared__ float smem[];
   const int c8n = c / 8;
   const int S = SE_THREADS / c8n > 0 ? SE_THREADS / c8n : 1;
@@ -61,7 +61,7 @@ se_kernel(T* __restrict__ x, int hw, int c, int rd, const float* __restrict__ w1
   __syncthreads();
   for (int ch = threadIdx.x; ch < c; ch += SE_THREADS) {
     float s = b2[ch];
-    for (int r = 0; r < rd; ++r) s = fmaf(w2[(size_t)ch * rd + r], s_hid[r], s);
+    for (int r = 0; r < rd; ++r) s = fmaf(w2t[(size_t)r * c + ch], s_hid[r], s);   // coalesced over ch
     s_scale[ch] = sigmoidf_(s);
   }
   __syncthreads();

@@ -155,17 +155,36 @@ stem_tc_kernel(const StemTcParams p) {
     const TIn* fbase = frames + (size_t)f * 3 * p.in_h * p.in_w;
 
     // ---- normalised input patch (zero padding applies in normalised space) ----
-    for (int i = tid; i < 3 * ST_PH * ST_PW; i += ST_THREADS) {
-      const int px = i % ST_PW, py = (i / ST_PW) % ST_PH, ci = i / (ST_PW * ST_PH);
-      const int y = iy0 + py, x = ix0 + px;
-      __nv_bfloat16 v = __float2bfloat16_rn(0.f);
-      if (y >= 0 && y < p.h && x >= 0 && x < p.w) {
-        const int sx = p.flip ? (p.w - 1 - x) : x;
-        const TIn raw = fbase[((size_t)ci * p.in_h + (p.crop_y + y)) * p.in_w + (p.crop_x + sx)];
-        if (sizeof(TIn) == 1) v = s_lut[ci][(int)raw];
-        else v = __float2bfloat16_rn(((float)raw / 255.f - mean[ci]) / stdv[ci]);
+    {
+      // two phases so that all of a thread's global loads are in flight together (the loop is latency bound otherwise)
+      constexpr int kElems = 3 * ST_PH * ST_PW;
+      constexpr int kIters = (kElems + ST_THREADS - 1) / ST_THREADS;
+      TIn raw[kIters];
+      bool inside[kIters];
+#pragma unroll
+      for (int k = 0; k < kIters; ++k) {
+        const int i = tid + k * ST_THREADS;
+        const int px = i % ST_PW, py = (i / ST_PW) % ST_PH, ci = i / (ST_PW * ST_PH);
+        const int y = iy0 + py, x = ix0 + px;
+        inside[k] = i < kElems && y >= 0 && y < p.h && x >= 0 && x < p.w;
+        raw[k] = TIn(0);
+        if (inside[k]) {
+          const int sx = p.flip ? (p.w - 1 - x) : x;
+          raw[k] = fbase[((size_t)ci * p.in_h + (p.crop_y + y)) * p.in_w + (p.crop_x + sx)];
+        }
       }
-      s_patch[ci][py][px] = v;
+#pragma unroll
+      for (int k = 0; k < kIters; ++k) {
+        const int i = tid + k * ST_THREADS;
+        if (i >= kElems) continue;
+        const int px = i % ST_PW, py = (i / ST_PW) % ST_PH, ci = i / (ST_PW * ST_PH);
+        __nv_bfloat16 v = __float2bfloat16_rn(0.f);
+        if (inside[k]) {
+          if (sizeof(TIn) == 1) v = s_lut[ci][(int)raw[k]];
+          else v = __float2bfloat16_rn(((float)raw[k] / 255.f - mean[ci]) / stdv[ci]);
+        }
+        s_patch[ci][py][px] = v;
+      }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // previous tile's tcgen05.ld are done
     __syncthreads();

@@ -135,7 +135,7 @@ class InferenceEngine:
             rd = sd[p + '.se.fc1.weight'].shape[0]
             b['se_w1'] = f32(sd[p + '.se.fc1.weight'].reshape(rd, cout))
             b['se_b1'] = f32(sd[p + '.se.fc1.bias'])
-            b['se_w2'] = f32(sd[p + '.se.fc2.weight'].reshape(cout, rd))
+            b['se_w2'] = f32(sd[p + '.se.fc2.weight'].reshape(cout, rd).t())     # transposed: [rd][c]
             b['se_b2'] = f32(sd[p + '.se.fc2.bias'])
             sc, sh = _bn_fold(sd, p + '.conv3.bn')
             b['w3'] = (sd[p + '.conv3.conv.weight'].float().reshape(cout, cout) * sc[:, None]).to(adt).contiguous()

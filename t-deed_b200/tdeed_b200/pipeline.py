@@ -32,6 +32,43 @@ class VideoScores:
         return ops.extract_events(self.scores, self.support, threshold)
 
 
+class ClipUploader:
+    """Double-buffered host->device staging of clip batches on a side stream, so the PCIe copy of batch i+1
+    overlaps the kernels of batch i (the reference blocks on `.to(device)` inside predict, model/model.py:340-342).
+
+        up = ClipUploader(batch_shape, device)
+        for host_clips in batches:                 # pinned uint8 (B,T,3,H,W) tensors
+            x = up.upload(host_clips)              # device view, valid until the next-but-one upload()
+            ... launch work that reads x on the current stream ...
+            up.release()                           # call after enqueuing the readers of x
+    """
+
+    def __init__(self, batch_shape, device, dtype=torch.uint8):
+        self.stream = torch.cuda.Stream(device=device)
+        self.bufs = [torch.empty(batch_shape, dtype=dtype, device=device) for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.free = [torch.cuda.Event() for _ in range(2)]
+        self.i = 0
+        self._used = [False, False]
+
+    def upload(self, host_clips):
+        k = self.i & 1
+        n = host_clips.shape[0]
+        with torch.cuda.stream(self.stream):
+            if self._used[k]:
+                self.stream.wait_event(self.free[k])         # readers of this buffer (two uploads ago) are done
+            self.bufs[k][:n].copy_(host_clips, non_blocking=True)
+            self.ready[k].record(self.stream)
+        torch.cuda.current_stream().wait_event(self.ready[k])
+        self._k = k
+        return self.bufs[k][:n]
+
+    def release(self):
+        self.free[self._k].record(torch.cuda.current_stream())
+        self._used[self._k] = True
+        self.i += 1
+
+
 def nms_events(ev, k, window, threshold, soft):
     """(soft-)NMS of the high-recall events of one video; returns numpy (frame i32, label i32, score f64)."""
     of, ol, os_, oc = ops.nms(ev['hr_frame'], ev['hr_label'], ev['hr_score'], ev['counts'][1:2], k, window, threshold, soft)

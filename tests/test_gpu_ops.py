@@ -192,7 +192,7 @@ def test_se_and_pool(dev, c, rd, hw):
     s = x.mean((2, 3))
     s = torch.sigmoid(torch.relu(s @ w1.t() + b1) @ w2.t() + b2)
     ref = x * s[:, :, None, None]
-    out = ops.se_(_nhwc(x).to(dev), w1.to(dev), b1.to(dev), w2.to(dev), b2.to(dev))
+    out = ops.se_(_nhwc(x).to(dev), w1.to(dev), b1.to(dev), w2.t().contiguous().to(dev), b2.to(dev))
     assert rel_err(_nchw(out), ref) < 1e-5
     te = torch.randn(2, c, generator=g)
     pooled = ops.pool_posenc(_nhwc(x).to(dev), 2, te.to(dev))
