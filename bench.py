@@ -158,7 +158,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours')
-    ap.add_argument('--clips-per-batch', type=int, default=13)
+    ap.add_argument('--clips-per-batch', type=int, default=39)
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
@@ -177,7 +177,7 @@ def main():
 
     from model.model import TDEEDModel
     from tdeed_b200 import ops
-    from tdeed_b200.pipeline import ClipUploader, VideoScores, nms_events
+    from tdeed_b200.pipeline import ClipUploader, PendingEvents, VideoScores, nms_events
     import contextlib
     import io
     with contextlib.redirect_stdout(io.StringIO()):
@@ -221,15 +221,28 @@ def main():
 
     uploader = ClipUploader(tuple(host_batch.shape), dev)
 
+    pending = []
+
     def step_e2e():
+        """One video through the host-facing path.  Nothing here blocks the host: clip uploads run on a side
+        stream, the event lists come back through async D2H copies that are collected one video later."""
         vs = VideoScores(VIDEO_FRAMES, K, dev)
         for lo, hi in batches:
             x = uploader.upload(host_batch[:hi - lo])                     # H2D of this batch's clips (side stream)
             _, _, probs = eng.forward_graphed(x)
             uploader.release()
             vs.add(probs, starts[lo:hi])
-        _, nbytes = postproc(vs, True)                                    # D2H of the event lists
-        d2h[0] = nbytes
+        ev = vs.events(0.01)
+        pending.append((PendingEvents(ev, K, NMS_WINDOW, 0.01, False), PendingEvents(ev, K, SNMS_WINDOW, 0.01, True)))
+        while len(pending) > 1:                                           # D2H of the previous video's event lists
+            a, b = pending.pop(0)
+            d2h[0] = a.nbytes + b.nbytes
+            a.get(), b.get()
+
+    def drain_e2e():
+        while pending:
+            a, b = pending.pop(0)
+            a.get(), b.get()
 
     def barrier():
         if world > 1:
@@ -262,10 +275,12 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     step_e2e()
+    drain_e2e()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_e2e()
+    drain_e2e()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
 

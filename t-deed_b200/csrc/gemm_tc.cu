@@ -16,6 +16,7 @@
 // K tails and M / N tails rely on TMA out-of-bounds zero fill and masked stores.
 #include "common.cuh"
 #include <cuda.h>
+#include <cstdlib>
 
 namespace tdeed {
 
@@ -40,6 +41,9 @@ struct TcParams {
   int m_tiles, n_tiles;
   // 4D gather geometry (strided 1x1 conv): an M tile is a bw x bh patch of output pixels of one frame
   int gather, Ho, Wo, bw, bh, tiles_x, tiles_y;
+  int out_bufs;   // 1 or 2 output staging tiles
+  int staged;     // 1: outputs go through the smem staging tile (coalesced stores); 0: row pieces straight from registers
+  int debug;   // TDEED_GEMM_DEBUG (dev only): 1 = skip global stores, 2 = skip TMEM loads, 4 = skip the MMAs
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -84,6 +88,7 @@ __device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* ba
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 8 epilogue warps
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 
@@ -145,6 +150,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   uint64_t* tmem_empty_bar = bars + 2 * TC_MAX_STAGES + 2;   // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 4);
   float* s_bias = reinterpret_cast<float*>(bars + 2 * TC_MAX_STAGES + 6);   // [n_tiles * block_n], zero padded
+  long long* s_rowm_base = reinterpret_cast<long long*>(s_bias + p.n_tiles * p.block_n);       // [2][128] global row of a tile row
+  uint8_t* s_out_base = reinterpret_cast<uint8_t*>(s_rowm_base + 2 * TC_BM);                     // [out_bufs][128][block_n*esz + 16]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_kb = p.nkb[0] + (p.nseg > 1 ? p.nkb[1] : 0);
@@ -225,6 +232,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           const uint32_t sw = sa + a_stage_bytes;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
+            if (p.debug & 4) break;
             const uint64_t adesc = umma_desc_sw128(sa + k * 32);
             const uint64_t bdesc = umma_desc_sw128(sw + k * 32);
             umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
@@ -236,17 +244,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
     }
   } else {
-    // ===== epilogue: 8 warps.  Warp w may only touch TMEM lanes [32*(w%4), +32); the two warps of a lane
-    // group split the accumulator's 32-column chunks (even / odd).  Bias comes from shared memory and the
-    // residual chunk is requested before the TMEM load so both latencies overlap. =====
+    // ===== epilogue: 8 warps (256 threads).  Warp w may only touch TMEM lanes [32*(w%4), +32); the two warps of a
+    // lane group split the accumulator's 32-column chunks (even / odd).  A thread owns a ROW of the accumulator:
+    //   phase 1  residual piece of the row (global, requested before the accumulator is ready) ; TMEM -> registers ;
+    //            + bias (smem) + residual, activation -> shared-memory staging tile (row-private, conflict-free)
+    //   phase 2  staging tile -> global with fully coalesced 16-byte stores.  (Writing row pieces straight to global
+    //            costs one 32-byte sector per lane per instruction: measured at 25-40 % of the kernel time in r1c.)
     const int lg = warp & 3;
     const int half = (warp - 2) >> 2;
     const int r = lg * 32 + lane;                           // row inside the tile
+    const int et = threadIdx.x - 64;                        // 0..255
+    const int esz = (p.out_dtype == TDEED_F32) ? 4 : 2;
+    const int pitch = p.block_n * esz + 16;                 // (pitch/16) odd -> conflict-free 16-byte row accesses
     uint32_t j = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
       const uint32_t acc = j & 1u;
       const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
       const int n0 = nt * p.block_n;
+      long long* s_rowm = s_rowm_base + acc * TC_BM;        // double buffered: the previous tile's phase 2 may still read its table
+      uint8_t* s_out = s_out_base + (p.out_bufs > 1 ? (size_t)acc * TC_BM * pitch : 0);
       long long m;
       bool row_ok;
       if (p.gather) {
@@ -259,25 +275,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         m = (long long)mt * TC_BM + r;
         row_ok = m < p.M;
       }
+      if (half == 0) s_rowm[r] = row_ok ? m : -1;           // global row of every tile row (or -1), for phase 2
+      const int ncols = min(p.block_n, p.N - n0);           // multiple of 8
       const uint32_t tmem_row = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * (uint32_t)p.block_n;
+      uint8_t* srow = s_out + r * pitch;
       bool waited = false;
-      for (int c0 = half * 32; c0 < p.block_n; c0 += 64) {
-        const int nbase = n0 + c0;
-        if (nbase >= p.N) break;                            // warp-uniform
-        // residual chunk (up to 32 columns) requested first: its latency overlaps the barrier wait / TMEM load
+      if (p.staged && p.out_bufs == 1 && j > 0) epi_bar_sync();   // single staging tile: previous phase 2 must have drained
+      for (int c0 = half * 32; c0 < ncols; c0 += 64) {
+        // residual piece (up to 32 columns) requested first: its latency overlaps the barrier wait / TMEM load
         uint4 rraw[8];
         const bool has_res = p.residual != nullptr && row_ok;
         if (has_res) {
-          if (p.res_dtype == TDEED_F32) {
-            const float* rp = reinterpret_cast<const float*>(p.residual) + m * p.ldr + nbase;
+          if (esz == 4) {
+            const float* rp = reinterpret_cast<const float*>(p.residual) + m * p.ldr + n0 + c0;
 #pragma unroll
             for (int q = 0; q < 8; ++q)
-              if (nbase + 4 * q < p.N) rraw[q] = *reinterpret_cast<const uint4*>(rp + 4 * q);
+              if (c0 + 4 * q < ncols) rraw[q] = *reinterpret_cast<const uint4*>(rp + 4 * q);
           } else {
-            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + m * p.ldr + nbase;
+            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + m * p.ldr + n0 + c0;
 #pragma unroll
             for (int q = 0; q < 4; ++q)
-              if (nbase + 8 * q < p.N) rraw[q] = *reinterpret_cast<const uint4*>(rp + 8 * q);
+              if (c0 + 8 * q < ncols) rraw[q] = *reinterpret_cast<const uint4*>(rp + 8 * q);
           }
         }
         if (!waited) {
@@ -286,22 +304,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           waited = true;
         }
         uint32_t v32[32];
-        tmem_ld32(tmem_row + (uint32_t)c0, v32);
-        tmem_ld_wait();
-        if (!row_ok) continue;
+        if (!(p.debug & 2)) {
+          tmem_ld32(tmem_row + (uint32_t)c0, v32);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v32[q] = 0u;
+        }
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
-          const int n = nbase + 8 * h;
-          if (n >= p.N || c0 + 8 * h >= p.block_n) continue;   // N tail / columns of the next n-tile (block_n % 32 == 16)
+          const int cl = c0 + 8 * h;                         // column inside the tile
+          if (cl >= ncols) continue;
           float v[8];
-          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + n);
-          const float4 b1 = *reinterpret_cast<const float4*>(s_bias + n + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + n0 + cl);
+          const float4 b1 = *reinterpret_cast<const float4*>(s_bias + n0 + cl + 4);
           v[0] = __uint_as_float(v32[8 * h + 0]) + b0.x; v[1] = __uint_as_float(v32[8 * h + 1]) + b0.y;
           v[2] = __uint_as_float(v32[8 * h + 2]) + b0.z; v[3] = __uint_as_float(v32[8 * h + 3]) + b0.w;
           v[4] = __uint_as_float(v32[8 * h + 4]) + b1.x; v[5] = __uint_as_float(v32[8 * h + 5]) + b1.y;
           v[6] = __uint_as_float(v32[8 * h + 6]) + b1.z; v[7] = __uint_as_float(v32[8 * h + 7]) + b1.w;
           if (has_res) {
-            if (p.res_dtype == TDEED_F32) {
+            if (esz == 4) {
               const uint4 ra = rraw[2 * h], rb = rraw[2 * h + 1];
               v[0] += __uint_as_float(ra.x); v[1] += __uint_as_float(ra.y); v[2] += __uint_as_float(ra.z); v[3] += __uint_as_float(ra.w);
               v[4] += __uint_as_float(rb.x); v[5] += __uint_as_float(rb.y); v[6] += __uint_as_float(rb.z); v[7] += __uint_as_float(rb.w);
@@ -317,15 +339,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           }
 #pragma unroll
           for (int q = 0; q < 8; ++q) v[q] = apply_act_rt(v[q], p.act);
-          if (p.out_dtype == TDEED_F32) store8(reinterpret_cast<float*>(p.out) + m * p.ldo + n, v);
-          else store8(reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo + n, v);
+          if (p.staged) {
+            if (esz == 4) store8(reinterpret_cast<float*>(srow) + cl, v);
+            else store8(reinterpret_cast<__nv_bfloat16*>(srow) + cl, v);
+          } else if (row_ok && !(p.debug & 1)) {
+            if (esz == 4) store8(reinterpret_cast<float*>(p.out) + m * p.ldo + n0 + cl, v);
+            else store8(reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo + n0 + cl, v);
+          }
         }
       }
-      if (!waited) {                                        // this warp had no chunk in this tile: still consume the phase
-        mbar_wait(&tmem_full_bar[acc], (j >> 1) & 1u);
-      }
+      if (!waited) mbar_wait(&tmem_full_bar[acc], (j >> 1) & 1u);   // this warp had no chunk: still consume the phase
       tcgen05_fence_before();
-      mbar_arrive(&tmem_empty_bar[acc]);                    // accumulator may be overwritten
+      mbar_arrive(&tmem_empty_bar[acc]);                    // accumulator may be overwritten by the MMA warp
+      if (!p.staged) continue;                              // direct-store mode: rows were written from registers
+      epi_bar_sync();                                       // staging tile + row table complete
+      if (!(p.debug & 1)) {
+        const int cpr = ncols * esz / 16;                   // 16-byte chunks per row
+        const uint32_t cpr_magic = ((1u << 24) + (uint32_t)cpr - 1u) / (uint32_t)cpr;
+        for (int idx = et; idx < TC_BM * cpr; idx += 256) {
+          const int row = (int)(((unsigned long long)idx * cpr_magic) >> 24);
+          const int ch = idx - row * cpr;
+          const long long mm = s_rowm[row];
+          if (mm >= 0)
+            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + ((size_t)mm * p.ldo + n0) * esz + (size_t)ch * 16) =
+                *reinterpret_cast<const uint4*>(s_out + row * pitch + ch * 16);
+        }
+      }
     }
   }
 
@@ -386,6 +425,8 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
                    void* out, long long ldo, int out_dtype, cudaStream_t st) {
   TDEED_REQUIRE(M > 0 && M < (1LL << 31) - TC_BM, TDEED_ERR_SHAPE, "gemm_tc: M=%lld out of range", M);
   TDEED_REQUIRE(N % 8 == 0 && K % 8 == 0, TDEED_ERR_SHAPE, "gemm_tc: N=%d, K=%d must be multiples of 8", N, K);
+  TDEED_REQUIRE(!residual || res_dtype == out_dtype, TDEED_ERR_UNSUPPORTED,
+                "gemm_tc: the residual must have the output's dtype (it shares the output staging tile)");
   TcParams p{};
   p.M = M; p.N = N; p.nseg = nseg;
   p.bias = bias; p.residual = residual; p.ldr = ldr; p.res_dtype = res_dtype; p.act = act;
@@ -409,7 +450,8 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
   }
 
   // tile width: one tile when N <= 256, else an even split; shrink for skinny-M problems to get more CTAs
-  int n_tiles = ceil_div(N, 256);
+  const int max_bn = (out_dtype == TDEED_F32) ? 128 : 256;   // fp32 staging tile: 128 x 128 x 4 B
+  int n_tiles = ceil_div(N, max_bn);
   int block_n = ceil_div(ceil_div(N, n_tiles), 16) * 16;
   if (block_n < 32) block_n = 32;
   while (block_n > 32 && (long long)p.m_tiles * ceil_div(N, block_n) < kNumSMs) {
@@ -463,17 +505,29 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
   if (stages < 2) stages = 2;
   p.num_stages = stages;
   const size_t bias_bytes = (size_t)p.n_tiles * block_n * sizeof(float);
-  const size_t fixed = 1024 + (2 * TC_MAX_STAGES + 6) * sizeof(uint64_t) + bias_bytes;
+  // Staging pays one CTA-wide barrier per tile: measured (tools/gemm_micro.py) to win for wide rows without a
+  // residual (s3/s4 conv1: -10..-25 %) and to lose for thin rows or when the residual read already pulled the
+  // row's lines into L1.
+  const char* force_staged = getenv("TDEED_GEMM_STAGED");
+  p.staged = force_staged ? atoi(force_staged) : (residual == nullptr && N >= 96 ? 1 : 0);
+  const size_t stage_out_bytes = p.staged ? (size_t)TC_BM * ((size_t)block_n * (out_dtype == TDEED_F32 ? 4 : 2) + 16) : 0;
+  const size_t fixed = 1024 + (2 * TC_MAX_STAGES + 6) * sizeof(uint64_t) + bias_bytes + 2 * TC_BM * sizeof(long long) + stage_out_bytes;
   TDEED_REQUIRE(fixed + 2 * stage_bytes <= 227 * 1024, TDEED_ERR_UNSUPPORTED, "gemm_tc: N=%d too wide for the bias staging area", N);
-  while (stages > 2 && fixed + stages * stage_bytes > 227 * 1024) --stages;
+  // a second output staging tile saves one CTA-wide barrier per tile; take it when >= 3 ring stages still fit
+  p.out_bufs = (fixed + stage_out_bytes + 3 * stage_bytes <= 227 * 1024) ? 2 : 1;
+  const size_t fixed2 = fixed + (p.out_bufs > 1 ? stage_out_bytes : 0);
+  while (stages > 2 && fixed2 + stages * stage_bytes > 227 * 1024) --stages;
   p.num_stages = stages;
-  const size_t smem = fixed + stages * stage_bytes;
+  const size_t smem = fixed2 + stages * stage_bytes;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     TDEED_REQUIRE(e == cudaSuccess, TDEED_ERR_CUDA, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("TDEED_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+  p.debug = dbg;
   const int num_tiles = p.m_tiles * p.n_tiles;
   const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
   gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], p);

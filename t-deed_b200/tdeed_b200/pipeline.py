@@ -76,6 +76,27 @@ def nms_events(ev, k, window, threshold, soft):
     return of[:n].cpu().numpy(), ol[:n].cpu().numpy(), os_[:n].cpu().numpy()
 
 
+class PendingEvents:
+    """(soft-)NMS result whose device->host copy is still in flight: lets the caller keep launching the next
+    video instead of synchronising per video like util/eval.py does.  `.get()` blocks and returns numpy arrays."""
+
+    def __init__(self, ev, k, window, threshold, soft):
+        of, ol, os_, oc = ops.nms(ev['hr_frame'], ev['hr_label'], ev['hr_score'], ev['counts'][1:2], k, window, threshold, soft)
+        self._host = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in (of, ol, os_, oc)]
+        for h, d in zip(self._host, (of, ol, os_, oc)):
+            h.copy_(d, non_blocking=True)
+        self._dev = (of, ol, os_, oc)          # keep alive until the copies have run
+        self._done = torch.cuda.Event()
+        self._done.record()
+        self.nbytes = sum(h.numel() * h.element_size() for h in self._host)
+
+    def get(self):
+        self._done.synchronize()
+        self._dev = None
+        n = int(self._host[3][0])
+        return self._host[0][:n].numpy(), self._host[1][:n].numpy(), self._host[2][:n].numpy()
+
+
 def events_to_dicts(video, fps, frames, labels, scores, classes_inv):
     """The reference's wire format: {'video', 'events': [{'label','frame','score'}], 'fps'}."""
     return {'video': video, 'fps': fps,
