@@ -132,3 +132,35 @@ def test_tta_accumulate_and_full_size_properties(dev):
     hr = (ev['hr_frame'][:nh].cpu().numpy(), ev['hr_label'][:nh].cpu().numpy(), ev['hr_score'][:nh].cpu().numpy())
     rf, rl, rs = P.nms(*hr, window=6, threshold=0.01)
     assert np.array_equal(f, rf) and np.array_equal(l, rl) and np.array_equal(s, rs.astype(np.float64))
+
+
+class _FakeDataset:
+    def __init__(self, videos):
+        self.videos = videos
+
+
+def test_util_eval_dropin_matches_reference_golden(golden_dir, dev):
+    """The drop-in util.eval functions (reference signatures, list-of-dict wire format) against the golden vectors
+    produced by the reference's own process_frame_predictions_challenge / (soft_)non_maximum_supression."""
+    import importlib
+    ue = importlib.import_module('util.eval')
+    assert 't-deed_b200' in ue.__file__
+    g = np.load(os.path.join(golden_dir, 'postproc.npz'))
+    for c in _cases(g):
+        length, k, w0, w1 = [int(v) for v in g[c + '_meta']]
+        thr = float(g[c + '_nms_thr'])
+        classes = {'c%d' % j: j for j in range(1, k)}
+        scores, support = g[c + '_scores_sum'].copy(), g[c + '_support'].copy()
+        ds = _FakeDataset([('vid', length, 25.0)])
+        pe, pehr, ps = ue.process_frame_predictions_challenge(ds, classes, {'vid': (scores, support)}, 0.01)
+        assert np.array_equal(scores, g[c + '_scores_norm'])                 # normalised in place like the reference
+        for tag, vp in (('ev', pe), ('hr', pehr)):
+            f, l, s = P.from_dicts(vp[0], classes)
+            assert np.array_equal(f, g[c + '_%s_frame' % tag]) and np.array_equal(l, g[c + '_%s_label' % tag])
+            assert np.array_equal(s, g[c + '_%s_score' % tag])
+        for tag, out in (('nms', ue.non_maximum_supression(pehr, window=w0, threshold=thr)),
+                         ('snms', ue.soft_non_maximum_supression(pehr, window=w1, threshold=0.01))):
+            f, l, s = P.from_dicts(out[0], classes)
+            assert out[0]['num_events'] == len(f) and out[0]['video'] == 'vid'
+            assert np.array_equal(f, g[c + '_%s_frame' % tag]) and np.array_equal(l, g[c + '_%s_label' % tag])
+            assert np.array_equal(s, g[c + '_%s_score' % tag])
