@@ -33,7 +33,7 @@ typedef enum {
 enum { TDEED_F32 = 0, TDEED_BF16 = 1, TDEED_U8 = 2 };
 enum { TDEED_ACT_NONE = 0, TDEED_ACT_RELU = 1, TDEED_ACT_GELU = 2 };
 enum { TDEED_SHIFT_GSM = 0, TDEED_SHIFT_GSF = 1 };
-enum { TDEED_GEMM_AUTO = 0, TDEED_GEMM_SIMT = 1, TDEED_GEMM_TCGEN05 = 2 };
+enum { TDEED_GEMM_AUTO = 0, TDEED_GEMM_SIMT = 1, TDEED_GEMM_TCGEN05 = 2, TDEED_GEMM_TCGEN05_THIN = 3 };
 
 int tdeed_abi_version(void);
 const char* tdeed_last_error(void);
@@ -78,8 +78,9 @@ int tdeed_stem_tc_fwd(const void* frames, int frames_dtype, int n_frames, int in
  * (f, oy*stride, ox*stride) — the stride-2 1x1 "downsample" shortcut.
  * W: [N, K] row-major (K = sum of segment k) of `dtype`.  bias: fp32 [N] or NULL.  residual: [M, ldr]
  * of res_dtype or NULL.  out: [M, ldo] of out_dtype.  lda/ldr/ldo must be multiples of 8 elements
- * and all base pointers 16-byte aligned.  backend: TDEED_GEMM_AUTO picks tcgen05 for bf16 and the
- * exact fp32 CUDA-core kernel for f32. */
+ * and all base pointers 16-byte aligned.  backend: TDEED_GEMM_AUTO picks, for bf16, the thin-K tcgen05 kernel
+ * (cp.async producers, resident weights) when K <= 64 and N <= 256 and the TMA-fed persistent tcgen05 kernel otherwise;
+ * for f32 the exact CUDA-core kernel. */
 #define TDEED_GEMM_MAX_SEGS 2
 typedef struct {
   const void* a;

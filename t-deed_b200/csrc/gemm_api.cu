@@ -15,6 +15,10 @@ int gemm_simt_launch(int dtype, long long M, int N, int K, const SimtSegs& segs,
 int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* segs, int gstride, int gh, int gw,
                    const void* W, const float* bias, const void* residual, long long ldr, int res_dtype, int act,
                    void* out, long long ldo, int out_dtype, cudaStream_t st);
+bool gemm_thin_applicable(int N, int K, int nseg, const tdeed_gemm_seg* segs, int gstride);
+int gemm_thin_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* segs, const void* W, const float* bias,
+                     const void* residual, long long ldr, int res_dtype, int act, void* out, long long ldo, int out_dtype,
+                     cudaStream_t st);
 }  // namespace tdeed
 
 extern "C" int tdeed_gemm_fwd(int dtype, long long M, int N, int nseg, const tdeed_gemm_seg* segs,
@@ -45,6 +49,12 @@ extern "C" int tdeed_gemm_fwd(int dtype, long long M, int N, int nseg, const tde
   cudaStream_t st = (cudaStream_t)stream;
   bool aligned8 = K % 8 == 0;
   for (int s = 0; s < nseg; ++s) aligned8 = aligned8 && segs[s].col0 % 8 == 0 && (s == nseg - 1 || segs[s].k % 8 == 0);
+  const bool thin_ok = dtype == TDEED_BF16 && gemm_thin_applicable(N, K, nseg, segs, gather_stride);
+  if (backend == TDEED_GEMM_TCGEN05_THIN || (backend == TDEED_GEMM_AUTO && thin_ok)) {
+    TDEED_REQUIRE(thin_ok, TDEED_ERR_UNSUPPORTED,
+                  "tdeed_gemm_fwd: the thin-K backend needs bf16, K <= 64, N <= 256, 8-aligned segments and no gather");
+    return gemm_thin_launch(M, N, K, nseg, segs, W, bias, residual, ldr, res_dtype, act, out, ldo, out_dtype, st);
+  }
   bool use_tc = (backend == TDEED_GEMM_TCGEN05) || (backend == TDEED_GEMM_AUTO && dtype == TDEED_BF16 && aligned8);
   if (use_tc) {
     TDEED_REQUIRE(dtype == TDEED_BF16, TDEED_ERR_UNSUPPORTED, "tdeed_gemm_fwd: the tcgen05 backend needs bf16 operands");

@@ -1,0 +1,339 @@
+// (2c) thin-K tcgen05 GEMM: the bf16 backend of tdeed_gemm_fwd for K <= 64 and N <= 256 (the stage-1/2 1x1 convs
+// and s3.b1.conv1 of RegNetY-200MF: K = 24 / 32 / 56 with M up to 1.6e7 rows — pure HBM streams).
+//
+// Why not the TMA kernel (gemm_tc.cu): rows of 48..112 bytes make one TMA request each; measured with all math and
+// stores disabled the TMA ring alone needed 2.0 us per 128 x 24 tile (tools/gemm_micro.py, TDEED_GEMM_DEBUG=7).  Here
+//   * 4 producer warps stream the A tile with 16-byte cp.async (LDGSTS) — a warp reads 512 contiguous bytes — straight
+//     into the canonical K-major NO-swizzle UMMA layout [8-column chunk][row][16 B] (SBO = 128 B, LBO = plane pitch),
+//     and signal the stage with cp.async.mbarrier.arrive.noinc (mbarrier count 128);
+//   * the weights (<= 256 x 64 bf16) are staged once per persistent CTA and stay resident;
+//   * one MMA lane issues ceil(K/16) tcgen05.mma (M=128, N=block_n, K=16) per tile into one of two TMEM accumulators;
+//   * 8 epilogue warps drain TMEM (tcgen05.ld.x32) -> bias / residual / activation -> 16-byte stores.
+// A 16-stage ring of 8..16 KB stages keeps > 64 KB of loads in flight per SM.
+#include "common.cuh"
+
+namespace tdeed {
+
+constexpr int TH_BM = 128;
+constexpr int TH_PROD_WARPS = 4;
+constexpr int TH_THREADS = 32 * (TH_PROD_WARPS + 1 + 8);     // producers, MMA, epilogue
+constexpr int TH_MAX_STAGES = 16;
+
+struct ThinParams {
+  long long M;
+  int N, K, block_n;
+  int nseg;
+  const __nv_bfloat16* a[TDEED_GEMM_MAX_SEGS];
+  long long lda[TDEED_GEMM_MAX_SEGS];
+  int col0[TDEED_GEMM_MAX_SEGS];
+  int kc[TDEED_GEMM_MAX_SEGS];     // 16-byte chunks per segment
+  int kc_total;                    // real chunks (K / 8)
+  int planes;                      // chunk planes per stage = 2 * ceil(K / 16)
+  int num_stages, m_tiles;
+  uint32_t a_plane_bytes, w_plane_bytes, stage_bytes;
+  const __nv_bfloat16* W;
+  const float* bias;
+  const void* residual;
+  long long ldr;
+  int act;
+  void* out;
+  long long ldo;
+  int out_dtype;
+  uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ uint32_t th_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void th_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(th_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ bool th_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(th_smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void th_wait(uint64_t* bar, uint32_t parity) {
+  if (th_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!th_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("tdeed gemm_thin: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void th_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(th_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint64_t th_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;          // Blackwell descriptor version; layout type 0 = no swizzle
+  return d;
+}
+__device__ __forceinline__ void th_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void th_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(th_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void th_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(TH_THREADS, 1)
+gemm_thin_kernel(const ThinParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* sW = smem;                                                     // [planes][block_n rows][16 B] (+16 B pitch pad)
+  uint8_t* sA = sW + (size_t)p.planes * p.w_plane_bytes;                  // [stages][planes][128 rows][16 B] (+16 B pad)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)p.num_stages * p.stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + TH_MAX_STAGES;
+  uint64_t* tmem_full_bar = bars + 2 * TH_MAX_STAGES;
+  uint64_t* tmem_empty_bar = bars + 2 * TH_MAX_STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TH_MAX_STAGES + 4);
+  float* s_bias = reinterpret_cast<float*>(bars + 2 * TH_MAX_STAGES + 6);  // [block_n]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- one-time setup: resident weights, zero padding planes, bias, barriers, TMEM ----
+  for (int i = threadIdx.x; i < p.planes * p.block_n; i += TH_THREADS) {
+    const int c = i / p.block_n, n = i - c * p.block_n;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (n < p.N && c < p.kc_total) v = *reinterpret_cast<const uint4*>(p.W + (size_t)n * p.K + c * 8);
+    *reinterpret_cast<uint4*>(sW + (size_t)c * p.w_plane_bytes + n * 16) = v;
+  }
+  {  // chunk planes beyond K/8 (K % 16 == 8) are never written by the producers: zero them once in every stage
+    const int npad = p.planes - p.kc_total;
+    for (int i = threadIdx.x; i < p.num_stages * npad * TH_BM; i += TH_THREADS) {
+      const int row = i % TH_BM, c = (i / TH_BM) % npad, st = i / (TH_BM * npad);
+      *reinterpret_cast<uint4*>(sA + (size_t)st * p.stage_bytes + (size_t)(p.kc_total + c) * p.a_plane_bytes + row * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  for (int i = threadIdx.x; i < p.block_n; i += TH_THREADS) s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.num_stages; ++s) {
+      th_mbar_init(&full_bar[s], 32 * TH_PROD_WARPS);       // one async arrival per producer thread
+      th_mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      th_mbar_init(&tmem_full_bar[a], 1);
+      th_mbar_init(&tmem_empty_bar[a], 256);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == TH_PROD_WARPS) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(th_smem_u32(tmem_slot)), "r"(p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // weights / zero planes were written by the generic proxy
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < TH_PROD_WARPS) {
+    // ===== cp.async producers: 128 threads, chunk q = t + 128*i of the tile's 128 x kc_total 16-byte chunks =====
+    const int t = threadIdx.x;
+    const uint32_t kc_magic = ((1u << 24) + (uint32_t)p.kc_total - 1u) / (uint32_t)p.kc_total;
+    const uint32_t sA_u32 = th_smem_u32(sA);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+      const int stage = it % p.num_stages;
+      const uint32_t round = it / p.num_stages;
+      th_wait(&empty_bar[stage], (round & 1u) ^ 1u);
+      const long long m0 = (long long)tile * TH_BM;
+      const uint32_t sbase = sA_u32 + (uint32_t)stage * p.stage_bytes;
+      for (int q = t; q < TH_BM * p.kc_total; q += 32 * TH_PROD_WARPS) {
+        const int row = (int)(((unsigned long long)q * kc_magic) >> 24);
+        const int c = q - row * p.kc_total;
+        const long long m = m0 + row;
+        const bool valid = m < p.M;
+        const __nv_bfloat16* src;
+        if (c < p.kc[0]) src = p.a[0] + (valid ? m : 0) * p.lda[0] + p.col0[0] + c * 8;
+        else src = p.a[1] + (valid ? m : 0) * p.lda[1] + p.col0[1] + (c - p.kc[0]) * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + (uint32_t)c * p.a_plane_bytes + (uint32_t)row * 16u),
+                     "l"(src), "r"(valid ? 16 : 0) : "memory");
+      }
+      // the mbarrier receives this thread's arrival once all of its cp.async above have landed
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(th_smem_u32(&full_bar[stage])) : "memory");
+    }
+  } else if (warp == TH_PROD_WARPS) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(TH_BM >> 4) << 24);
+    const uint32_t sA_u32 = th_smem_u32(sA), sW_u32 = th_smem_u32(sW);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1u;
+      const int stage = it % p.num_stages;
+      const uint32_t round = it / p.num_stages;
+      th_wait(&tmem_empty_bar[acc], ((it >> 1) & 1u) ^ 1u);
+      th_wait(&full_bar[stage], round & 1u);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) data -> visible to the MMA (async proxy)
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t a0 = sA_u32 + (uint32_t)stage * p.stage_bytes;
+        for (int k = 0; k < p.planes / 2; ++k) {
+          const uint64_t adesc = th_desc(a0 + (uint32_t)(2 * k) * p.a_plane_bytes, p.a_plane_bytes, 128u);
+          const uint64_t bdesc = th_desc(sW_u32 + (uint32_t)(2 * k) * p.w_plane_bytes, p.w_plane_bytes, 128u);
+          th_umma(tmem_base + acc * (uint32_t)p.block_n, adesc, bdesc, idesc, k != 0 ? 1u : 0u);
+        }
+        th_commit(&empty_bar[stage]);
+        th_commit(&tmem_full_bar[acc]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue (8 warps): TMEM -> bias / residual / activation -> global =====
+    const int ew = warp - (TH_PROD_WARPS + 1);
+    const int lg = warp & 3;
+    const int half = ew >> 2;
+    const int r = lg * 32 + lane;
+    const int esz = (p.out_dtype == TDEED_F32) ? 4 : 2;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & 1u;
+      const long long m = (long long)tile * TH_BM + r;
+      const bool row_ok = m < p.M;
+      const uint32_t tmem_row = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * (uint32_t)p.block_n;
+      bool waited = false;
+      for (int c0 = half * 32; c0 < p.N; c0 += 64) {
+        uint4 rraw[8];
+        const bool has_res = p.residual != nullptr && row_ok;
+        if (has_res) {
+          if (esz == 4) {
+            const float* rp = reinterpret_cast<const float*>(p.residual) + m * p.ldr + c0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (c0 + 4 * q < p.N) rraw[q] = *reinterpret_cast<const uint4*>(rp + 4 * q);
+          } else {
+            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + m * p.ldr + c0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (c0 + 8 * q < p.N) rraw[q] = *reinterpret_cast<const uint4*>(rp + 8 * q);
+          }
+        }
+        if (!waited) {
+          th_wait(&tmem_full_bar[acc], (it >> 1) & 1u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          waited = true;
+        }
+        uint32_t v32[32];
+        th_ld32(tmem_row + (uint32_t)c0, v32);
+        if (!row_ok) continue;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int n = c0 + 8 * h;
+          if (n >= p.N) continue;
+          float v[8];
+          const float4 b0 = *reinterpret_cast<const float4*>(s_bias + n);
+          const float4 b1 = *reinterpret_cast<const float4*>(s_bias + n + 4);
+          v[0] = __uint_as_float(v32[8 * h + 0]) + b0.x; v[1] = __uint_as_float(v32[8 * h + 1]) + b0.y;
+          v[2] = __uint_as_float(v32[8 * h + 2]) + b0.z; v[3] = __uint_as_float(v32[8 * h + 3]) + b0.w;
+          v[4] = __uint_as_float(v32[8 * h + 4]) + b1.x; v[5] = __uint_as_float(v32[8 * h + 5]) + b1.y;
+          v[6] = __uint_as_float(v32[8 * h + 6]) + b1.z; v[7] = __uint_as_float(v32[8 * h + 7]) + b1.w;
+          if (has_res) {
+            if (esz == 4) {
+              const uint4 ra = rraw[2 * h], rb = rraw[2 * h + 1];
+              v[0] += __uint_as_float(ra.x); v[1] += __uint_as_float(ra.y); v[2] += __uint_as_float(ra.z); v[3] += __uint_as_float(ra.w);
+              v[4] += __uint_as_float(rb.x); v[5] += __uint_as_float(rb.y); v[6] += __uint_as_float(rb.z); v[7] += __uint_as_float(rb.w);
+            } else {
+              const uint4 ra = rraw[h];
+              const uint32_t w4[4] = {ra.x, ra.y, ra.z, ra.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                v[2 * q] += __uint_as_float(w4[q] << 16);
+                v[2 * q + 1] += __uint_as_float(w4[q] & 0xffff0000u);
+              }
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = apply_act_rt(v[q], p.act);
+          if (esz == 4) store8(reinterpret_cast<float*>(p.out) + m * p.ldo + n, v);
+          else store8(reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo + n, v);
+        }
+      }
+      if (!waited) th_wait(&tmem_full_bar[acc], (it >> 1) & 1u);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      th_arrive(&tmem_empty_bar[acc]);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == TH_PROD_WARPS) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// true when the thin kernel covers the problem (bf16, single k-block, one n-tile, no gather)
+bool gemm_thin_applicable(int N, int K, int nseg, const tdeed_gemm_seg* segs, int gstride) {
+  if (gstride > 1 || K > 64 || K % 8 != 0 || N > 256 || N % 8 != 0) return false;
+  for (int s = 0; s < nseg; ++s)
+    if (segs[s].k % 8 != 0 || segs[s].col0 % 8 != 0 || segs[s].lda % 8 != 0 || (reinterpret_cast<uintptr_t>(segs[s].a) & 15) != 0) return false;
+  return true;
+}
+
+int gemm_thin_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* segs, const void* W, const float* bias,
+                     const void* residual, long long ldr, int res_dtype, int act, void* out, long long ldo, int out_dtype,
+                     cudaStream_t st) {
+  TDEED_REQUIRE(M > 0 && M < (1LL << 31) - TH_BM, TDEED_ERR_SHAPE, "gemm_thin: M=%lld out of range", M);
+  TDEED_REQUIRE(!residual || res_dtype == out_dtype, TDEED_ERR_UNSUPPORTED, "gemm_thin: the residual must have the output's dtype");
+  TDEED_REQUIRE((reinterpret_cast<uintptr_t>(W) & 15) == 0, TDEED_ERR_SHAPE, "gemm_thin: W must be 16-byte aligned");
+  ThinParams p{};
+  p.M = M; p.N = N; p.K = K; p.nseg = nseg;
+  for (int s = 0; s < TDEED_GEMM_MAX_SEGS; ++s) {
+    const tdeed_gemm_seg& g = segs[s < nseg ? s : 0];
+    p.a[s] = (const __nv_bfloat16*)g.a; p.lda[s] = g.lda; p.col0[s] = g.col0; p.kc[s] = (s < nseg) ? g.k / 8 : 0;
+  }
+  if (nseg == 1) p.kc[0] = K / 8;
+  p.kc_total = K / 8;
+  p.planes = 2 * ((K + 15) / 16);
+  p.block_n = (N + 15) / 16 * 16;
+  if (p.block_n < 32) p.block_n = 32;
+  p.a_plane_bytes = TH_BM * 16 + 16;            // +16 B: consecutive chunk planes start 4 banks apart
+  p.w_plane_bytes = (uint32_t)p.block_n * 16 + 16;
+  p.stage_bytes = (uint32_t)p.planes * p.a_plane_bytes;
+  p.m_tiles = (int)ceil_div_ll(M, TH_BM);
+  p.W = (const __nv_bfloat16*)W; p.bias = bias; p.residual = residual; p.ldr = ldr; p.act = act;
+  p.out = out; p.ldo = ldo; p.out_dtype = out_dtype;
+  uint32_t cols = 32;
+  while ((int)cols < 2 * p.block_n + 16) cols <<= 1;
+  if (cols > 512) cols = 512;
+  p.tmem_cols = cols;
+  const size_t fixed = (size_t)p.planes * p.w_plane_bytes + (2 * TH_MAX_STAGES + 6) * sizeof(uint64_t) + (size_t)p.block_n * sizeof(float) + 128;
+  int stages = (int)((200 * 1024 - fixed) / p.stage_bytes);
+  if (stages > TH_MAX_STAGES) stages = TH_MAX_STAGES;
+  TDEED_REQUIRE(stages >= 2, TDEED_ERR_UNSUPPORTED, "gemm_thin: N=%d K=%d does not fit", N, K);
+  p.num_stages = stages;
+  const size_t smem = fixed + (size_t)stages * p.stage_bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_thin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    TDEED_REQUIRE(e == cudaSuccess, TDEED_ERR_CUDA, "gemm_thin: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    attr_set = true;
+  }
+  const int grid = p.m_tiles < kNumSMs ? p.m_tiles : kNumSMs;
+  gemm_thin_kernel<<<grid, TH_THREADS, smem, st>>>(p);
+  return check_launch("tdeed_gemm_fwd(tcgen05 thin-K)");
+}
+
+}  // namespace tdeed

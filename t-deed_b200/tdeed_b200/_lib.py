@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), 'lib', 'libtdeed_sm100.so')
 F32, BF16, U8 = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 SHIFT_GSM, SHIFT_GSF = 0, 1
-GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = 0, 1, 2
+GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, GEMM_TCGEN05_THIN = 0, 1, 2, 3
 GEMM_MAX_SEGS = 2
 
 c_int, c_ll, c_float, c_double, c_vp = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_double, ctypes.c_void_p

@@ -54,7 +54,7 @@ def _gemm_case(dev, dtype, m, n, ks, act, with_res, backend, gather=None, seed=0
     elif act == L.ACT_GELU:
         ref = torch.nn.functional.gelu(ref)
     # the tcgen05 kernel stages residual and output in the same tile -> they share a dtype; a bf16 output adds one rounding
-    out_dtype = dtype if (with_res and backend == L.GEMM_TCGEN05) else torch.float32
+    out_dtype = dtype if (with_res and backend in (L.GEMM_TCGEN05, L.GEMM_TCGEN05_THIN)) else torch.float32
     out = ops.gemm(segs, w.to(dev), bias.to(dev), residual=res.to(dev) if with_res else None, act=act, rows=m,
                    out_dtype=out_dtype, backend=backend,
                    gather=(gather[0], gather[2], gather[3]) if gather else None)
@@ -84,6 +84,15 @@ def test_gemm_tcgen05_bf16(dev, m, n, ks):
     from tdeed_b200 import _lib as L
     for act, res in ((L.ACT_NONE, False), (L.ACT_RELU, True), (L.ACT_GELU, False)):
         assert _gemm_case(dev, torch.bfloat16, m, n, ks, act, res, L.GEMM_TCGEN05) < 2e-5
+
+
+@pytest.mark.parametrize('m,n,ks', [(128, 32, (32,)), (300, 24, (24,)), (100000, 24, (32,)), (5000, 56, (24,)), (4097, 56, (56,)),
+                                    (777, 152, (16, 40)), (1000, 256, (64,)), (333, 64, (40, 24)), (60000, 152, (16, 40))])
+def test_gemm_tcgen05_thin_k(dev, m, n, ks):
+    """Thin-K tcgen05 kernel (cp.async producers into the no-swizzle UMMA layout, resident weights)."""
+    from tdeed_b200 import _lib as L
+    for act, res in ((L.ACT_NONE, False), (L.ACT_RELU, True), (L.ACT_GELU, False)):
+        assert _gemm_case(dev, torch.bfloat16, m, n, ks, act, res, L.GEMM_TCGEN05_THIN) < 2e-5
 
 
 @pytest.mark.parametrize('n,k,gather', [(152, 56, (2, 3, 14, 10)), (56, 24, (2, 2, 7, 9)), (24, 32, (2, 1, 6, 300)),
