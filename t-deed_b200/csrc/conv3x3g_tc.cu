@@ -248,7 +248,12 @@ extern "C" int tdeed_conv3x3g_tc_fwd(const void* in, int n, int h, int w, int c,
   p.ntiles = (int)nt;
   p.nchunks_real = c / 8;
   p.pairs_total = (c + 15) / 16;
-  const int nblk = ceil_div(p.pairs_total, C3T_MAX_PAIRS);
+  // channel pairs per CTA: at most 8 (128 channels), fewer when the staged window of a wide frame would not fit
+  const size_t per_pair = (size_t)9 * 512 + (size_t)p.nplanes * 2 * p.npos_pad * 16 + 64;
+  int max_pairs = (int)((200 * 1024 - (size_t)p.npos * p.nplanes * sizeof(int)) / per_pair);
+  if (max_pairs > C3T_MAX_PAIRS) max_pairs = C3T_MAX_PAIRS;
+  TDEED_REQUIRE(max_pairs >= 1, TDEED_ERR_UNSUPPORTED, "tdeed_conv3x3g_tc_fwd: frame width %d too large for the staged window", w);
+  const int nblk = ceil_div(p.pairs_total, max_pairs);
   p.pairs_blk = ceil_div(p.pairs_total, nblk);
   uint32_t cols = 32;
   while ((int)cols < p.pairs_blk * 16) cols <<= 1;

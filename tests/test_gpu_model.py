@@ -126,3 +126,27 @@ def test_full_size_clip_fp32_vs_oracle(dev):
         pred16, _ = m._model(frames.to(dev), inference=True)
     assert rel_err(pred16['im_feat'].cpu().numpy(), logits_ref.numpy()) < BF16_TOL_LOGITS
     assert rel_err(pred16['displ_feat'].cpu().numpy(), displ_ref.numpy()) < BF16_TOL_DISPL
+
+
+def test_soccernetball_challenge_shape_vs_oracle(dev):
+    """SoccerNetBall challenge2 geometry (RegNetY-800MF + GSF, double head 13+18, uncropped 448 x 796 frames, displacement
+    radius 4) on a short clip, against the CPU oracle: exercises the wide-frame tiling paths (W = 398 / 199 / 100 / 50 / 25)."""
+    cfg = O.named_config('SoccerNetBall_challenge2', clip_len=6)
+    sd = O.random_state(cfg, 21)
+    g = torch.Generator().manual_seed(4)
+    frames = torch.randint(0, 256, (1, 6, 3, 448, 796), generator=g, dtype=torch.uint8)
+    with torch.no_grad():
+        logits_ref, displ_ref = O.forward(sd, cfg, frames)
+    m = build(cfg, sd, dev)
+    m._model.eval()
+    with torch.no_grad():
+        pred, _ = m._model(frames.to(dev), inference=True)
+    assert pred['im_feat'].shape == (1, 6, 31)
+    assert rel_err(pred['im_feat'].cpu().numpy(), logits_ref.numpy()) < FP32_TOL
+    assert rel_err(pred['displ_feat'].cpu().numpy(), displ_ref.numpy()) < FP32_TOL
+    with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
+        pred16, _ = m._model(frames.to(dev), inference=True)
+    assert rel_err(pred16['im_feat'].cpu().numpy(), logits_ref.numpy()) < BF16_TOL_LOGITS
+    assert rel_err(pred16['displ_feat'].cpu().numpy(), displ_ref.numpy()) < BF16_TOL_DISPL
+    cls, probs = m.predict(frames, use_amp=True)
+    assert probs.shape == (1, 6, 13) and np.isfinite(probs).all()          # softmax over the first head only
