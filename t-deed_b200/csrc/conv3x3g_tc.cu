@@ -16,7 +16,7 @@
 
 namespace tdeed {
 
-constexpr int C3T_THREADS = 128;
+constexpr int C3T_THREADS = 32 * (4 + 1 + 4);   // 4 producer warps, MMA warp, 4 epilogue warps
 constexpr int C3T_MAX_PAIRS = 8;     // 128 channels per CTA
 
 struct C3TParams {
@@ -80,23 +80,33 @@ __device__ __forceinline__ void c3_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+__device__ __forceinline__ void c3_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(c3_smem_u32(bar)) : "memory");
+}
+
+// Warp roles: warps 0-3 producers (position table + cp.async staging of the next tile's window into one of two
+// input buffers), warp 4 MMA issuer, warps 5-8 epilogue (TMEM lanes = rows), two TMEM accumulators: staging of tile
+// i+1, the MMAs of tile i and the epilogue of tile i-1 overlap inside one CTA.
 __global__ void __launch_bounds__(C3T_THREADS)
 conv3x3g_tc_kernel(const C3TParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int pair0 = blockIdx.y * p.pairs_blk;
   const int np = min(p.pairs_blk, p.pairs_total - pair0);
   const int nch = 2 * np;                        // staged chunk planes (a trailing zero plane pads odd chunk counts)
   const int chunk0 = 2 * pair0;
-  // ceil(2^24 / d): (i * m) >> 24 is the exact quotient for i < 2^16
-  const uint32_t div_nch = ((1u << 24) + (uint32_t)nch - 1u) / (uint32_t)nch;
-  const uint32_t div_perpos = ((1u << 24) + (uint32_t)(p.nplanes * nch) - 1u) / (uint32_t)(p.nplanes * nch);
+  const int nch_real = min(nch, p.nchunks_real - chunk0);
+  const size_t in_bytes = (size_t)p.nplanes * 2 * p.pairs_blk * p.npos_pad * 16;
   uint8_t* sW = smem;                                              // [pairs_blk][9][512]
-  uint8_t* sIn = sW + (size_t)p.pairs_blk * 9 * 512;               // [nplanes][nch][npos_pad][16]
-  float* s_bias = reinterpret_cast<float*>(sIn + (size_t)p.nplanes * 2 * p.pairs_blk * p.npos_pad * 16);
-  uint64_t* s_bar = reinterpret_cast<uint64_t*>(s_bias + p.pairs_blk * 16);
-  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(s_bar + 1);
-  int* s_tbl = reinterpret_cast<int*>(s_bar + 2);                  // [npos][nplanes]
+  uint8_t* sIn = sW + (size_t)p.pairs_blk * 9 * 512;               // [2][nplanes][nch][npos_pad][16]
+  float* s_bias = reinterpret_cast<float*>(sIn + 2 * in_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + p.pairs_blk * 16);
+  uint64_t* full_bar = bars;          // [2] input buffer staged          (128 async arrivals)
+  uint64_t* empty_bar = bars + 2;     // [2] input buffer consumed        (tcgen05.commit)
+  uint64_t* tfull_bar = bars + 4;     // [2] accumulator ready            (tcgen05.commit)
+  uint64_t* tempty_bar = bars + 6;    // [2] accumulator drained          (128 epilogue threads)
+  uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 8);
+  int* s_tbl = reinterpret_cast<int*>(bars + 10);                  // [2][npos][nplanes]
 
   for (int i = tid; i < np * 9 * 32; i += C3T_THREADS)
     reinterpret_cast<uint4*>(sW)[i] = reinterpret_cast<const uint4*>(p.wimg + (size_t)pair0 * 9 * 512)[i];
@@ -104,11 +114,24 @@ conv3x3g_tc_kernel(const C3TParams p) {
     const int ch = pair0 * 16 + i;
     s_bias[i] = ch < p.C ? p.bias[ch] : 0.f;
   }
+  // chunk planes beyond the tensor's channels are never staged: zero them once in both buffers
+  for (int i = tid; i < 2 * p.nplanes * (nch - nch_real) * p.npos_pad; i += C3T_THREADS) {
+    const int s = i % p.npos_pad;
+    const int c = (i / p.npos_pad) % (nch - nch_real);
+    const int pl = (i / (p.npos_pad * (nch - nch_real))) % p.nplanes;
+    const int buf = i / (p.npos_pad * (nch - nch_real) * p.nplanes);
+    *reinterpret_cast<uint4*>(sIn + buf * in_bytes + ((size_t)(pl * nch + nch_real + c) * p.npos_pad + s) * 16) = make_uint4(0u, 0u, 0u, 0u);
+  }
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(c3_smem_u32(s_bar)), "r"(1));
+    for (int i = 0; i < 2; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(c3_smem_u32(&full_bar[i])), "r"(128));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(c3_smem_u32(&empty_bar[i])), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(c3_smem_u32(&tfull_bar[i])), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(c3_smem_u32(&tempty_bar[i])), "r"(128));
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {
+  if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(c3_smem_u32(s_tmem)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -117,97 +140,119 @@ conv3x3g_tc_kernel(const C3TParams p) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *s_tmem;
-  const uint32_t tmem_lane = tmem_base + ((uint32_t)(warp * 32) << 16);
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t acc_cols = (uint32_t)p.pairs_blk * 16u;
   const uint32_t plane_bytes = (uint32_t)p.npos_pad * 16u;
-  uint32_t phase = 0;
 
-  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
-    const long long q0 = (long long)tile * 128;
-    const long long q_lo = q0 + p.min_off;
-
-    // ---- per-tile position table: pixel index of every staged (position, parity plane), or -1 for padding ----
-    for (int e = tid; e < p.npos * p.nplanes; e += C3T_THREADS) {
-      const int s = e / p.nplanes, pl = e - s * p.nplanes;
-      const long long L = q_lo + s;
-      int pix = -1;
-      if (L >= 0 && L < p.total_pos) {
+  if (warp < 4) {
+    // ===== producers (128 threads) =====
+    const int per_pos = p.nplanes * nch_real;
+    const uint32_t div_nch = ((1u << 24) + (uint32_t)nch_real - 1u) / (uint32_t)nch_real;
+    const uint32_t div_perpos = ((1u << 24) + (uint32_t)per_pos - 1u) / (uint32_t)per_pos;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u;
+      c3_wait(&empty_bar[buf], ((it >> 1) & 1u) ^ 1u);
+      const long long q_lo = (long long)tile * 128 + p.min_off;
+      int* tbl = s_tbl + buf * (p.npos * p.nplanes);
+      // per-tile position table: pixel index of every staged (position, parity plane), or -1 for padding
+      for (int e = tid; e < p.npos * p.nplanes; e += 128) {
+        const int s = e / p.nplanes, pl = e - s * p.nplanes;
+        const long long L = q_lo + s;
+        int pix = -1;
+        if (L >= 0 && L < p.total_pos) {
+          const int Li = (int)L;
+          const int f = Li / p.G;
+          const int rem = Li - f * p.G;
+          const int U = rem / p.GW, V = rem - U * p.GW;
+          const int iy = p.stride * (U - 1) + (pl >> 1), ix = p.stride * (V - 1) + (pl & 1);
+          if (U >= 1 && V >= 1 && iy < p.H && ix < p.W) pix = (f * p.H + iy) * p.W + ix;
+        }
+        tbl[e] = pix;
+      }
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      // stage the input window with cp.async (zero-fill for padding): [plane][chunk][position] x 16 B
+      const uint32_t sIn_u32 = c3_smem_u32(sIn + buf * in_bytes);
+      for (int i = tid; i < p.npos * per_pos; i += 128) {
+        const int s = (int)(((unsigned long long)i * div_perpos) >> 24);
+        const int j = i - s * per_pos;
+        const int pl = (int)(((unsigned long long)j * div_nch) >> 24);
+        const int c = j - pl * nch_real;
+        const int pix = tbl[s * p.nplanes + pl];
+        const bool valid = pix >= 0;
+        const __nv_bfloat16* src = valid ? p.in + (size_t)pix * p.C + (size_t)(chunk0 + c) * 8 : p.in;
+        const uint32_t dst = sIn_u32 + (uint32_t)((pl * nch + c) * p.npos_pad + s) * 16u;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(c3_smem_u32(&full_bar[buf])) : "memory");
+    }
+  } else if (warp == 4) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(16 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t b0 = c3_smem_u32(sW);
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u;
+      c3_wait(&tempty_bar[buf], ((it >> 1) & 1u) ^ 1u);
+      c3_wait(&full_bar[buf], (it >> 1) & 1u);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0) {
+        const uint32_t a0 = c3_smem_u32(sIn + buf * in_bytes);
+        for (int pp = 0; pp < np; ++pp) {
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const uint32_t a = a0 + ((uint32_t)(p.tap_plane[t] * nch + 2 * pp) * (uint32_t)p.npos_pad + (uint32_t)(p.tap_off[t] - p.min_off)) * 16u;
+            const uint32_t b = b0 + (uint32_t)(pp * 9 + t) * 512u;
+            c3_umma(tmem_base + buf * acc_cols + (uint32_t)pp * 16u, c3_desc(a, plane_bytes, 128u), c3_desc(b, 128u, 256u), idesc, t != 0 ? 1u : 0u);
+          }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(c3_smem_u32(&empty_bar[buf])) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(c3_smem_u32(&tfull_bar[buf])) : "memory");
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===== epilogue (4 warps): row = position; bias + ReLU -> bf16 NHWC =====
+    const int lg = warp & 3;
+    const int r = lg * 32 + lane;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1u;
+      const long long L = (long long)tile * 128 + r;
+      bool ok = L < p.total_pos;
+      size_t obase = 0;
+      if (ok) {
         const int Li = (int)L;
         const int f = Li / p.G;
         const int rem = Li - f * p.G;
         const int U = rem / p.GW, V = rem - U * p.GW;
-        const int iy = p.stride * (U - 1) + (pl >> 1), ix = p.stride * (V - 1) + (pl & 1);
-        if (U >= 1 && V >= 1 && iy < p.H && ix < p.W) pix = (f * p.H + iy) * p.W + ix;
+        ok = U >= 1 && U <= p.Ho && V >= 1 && V <= p.Wo;
+        obase = (((size_t)f * p.Ho + (U - 1)) * p.Wo + (V - 1)) * p.C + (size_t)pair0 * 16;
       }
-      s_tbl[e] = pix;
-    }
-    __syncthreads();
-    // ---- stage the input window with cp.async (zero-fill for padding): [plane][chunk][position] x 16 B ----
-    const int per_pos = p.nplanes * nch;
-    const uint32_t sIn_u32 = c3_smem_u32(sIn);
-    for (int i = tid; i < p.npos * per_pos; i += C3T_THREADS) {
-      const int s = (int)(((unsigned long long)i * div_perpos) >> 24);
-      const int j = i - s * per_pos;
-      const int pl = (int)(((unsigned long long)j * div_nch) >> 24);
-      const int c = j - pl * nch;
-      const int pix = s_tbl[s * p.nplanes + pl];
-      const bool valid = pix >= 0 && chunk0 + c < p.nchunks_real;
-      const __nv_bfloat16* src = valid ? p.in + (size_t)pix * p.C + (size_t)(chunk0 + c) * 8 : p.in;
-      const uint32_t dst = sIn_u32 + (uint32_t)((pl * nch + c) * p.npos_pad + s) * 16u;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");   // previous tile's tcgen05.ld are complete
-    __syncthreads();
-
-    if (tid == 0) {
+      c3_wait(&tfull_bar[buf], (it >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t a0 = c3_smem_u32(sIn), b0 = c3_smem_u32(sW);
+      const uint32_t tmem_lane = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * acc_cols;
       for (int pp = 0; pp < np; ++pp) {
+        uint32_t v32[16];
+        c3_ld16(tmem_lane + (uint32_t)pp * 16u, v32);
+        if (!ok) continue;
 #pragma unroll
-        for (int t = 0; t < 9; ++t) {
-          const uint32_t a = a0 + ((uint32_t)(p.tap_plane[t] * nch + 2 * pp) * (uint32_t)p.npos_pad + (uint32_t)(p.tap_off[t] - p.min_off)) * 16u;
-          const uint32_t b = b0 + (uint32_t)(pp * 9 + t) * 512u;
-          c3_umma(tmem_base + (uint32_t)pp * 16u, c3_desc(a, plane_bytes, 128u), c3_desc(b, 128u, 256u), idesc, t != 0 ? 1u : 0u);
+        for (int hh = 0; hh < 2; ++hh) {
+          if (pair0 * 16 + pp * 16 + 8 * hh >= p.C) continue;
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) v[q] = fmaxf(__uint_as_float(v32[8 * hh + q]) + s_bias[pp * 16 + 8 * hh + q], 0.f);
+          store8(p.out + obase + pp * 16 + 8 * hh, v);
         }
       }
-      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(c3_smem_u32(s_bar)) : "memory");
-    }
-    c3_wait(s_bar, phase);
-    phase ^= 1u;
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-
-    // ---- epilogue: row = position; bias + ReLU -> bf16 NHWC ----
-    const long long L = q0 + tid;
-    bool ok = L < p.total_pos;
-    size_t obase = 0;
-    if (ok) {
-      const int f = (int)(L / p.G);
-      const int rem = (int)(L - (long long)f * p.G);
-      const int U = rem / p.GW, V = rem - U * p.GW;
-      ok = U >= 1 && U <= p.Ho && V >= 1 && V <= p.Wo;
-      obase = (((size_t)f * p.Ho + (U - 1)) * p.Wo + (V - 1)) * p.C + (size_t)pair0 * 16;
-    }
-    for (int pp = 0; pp < np; ++pp) {
-      uint32_t v32[16];
-      c3_ld16(tmem_lane + (uint32_t)pp * 16u, v32);
-      if (!ok) continue;
-#pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        if (pair0 * 16 + pp * 16 + 8 * hh >= p.C) continue;
-        float v[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] = fmaxf(__uint_as_float(v32[8 * hh + q]) + s_bias[pp * 16 + 8 * hh + q], 0.f);
-        store8(p.out + obase + pp * 16 + 8 * hh, v);
-      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      c3_arrive(&tempty_bar[buf]);
     }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 4) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
   }
@@ -249,17 +294,17 @@ extern "C" int tdeed_conv3x3g_tc_fwd(const void* in, int n, int h, int w, int c,
   p.nchunks_real = c / 8;
   p.pairs_total = (c + 15) / 16;
   // channel pairs per CTA: at most 8 (128 channels), fewer when the staged window of a wide frame would not fit
-  const size_t per_pair = (size_t)9 * 512 + (size_t)p.nplanes * 2 * p.npos_pad * 16 + 64;
-  int max_pairs = (int)((200 * 1024 - (size_t)p.npos * p.nplanes * sizeof(int)) / per_pair);
+  const size_t per_pair = (size_t)9 * 512 + 2 * (size_t)p.nplanes * 2 * p.npos_pad * 16 + 64;     // two input buffers
+  int max_pairs = (int)((200 * 1024 - 2 * (size_t)p.npos * p.nplanes * sizeof(int)) / per_pair);
   if (max_pairs > C3T_MAX_PAIRS) max_pairs = C3T_MAX_PAIRS;
   TDEED_REQUIRE(max_pairs >= 1, TDEED_ERR_UNSUPPORTED, "tdeed_conv3x3g_tc_fwd: frame width %d too large for the staged window", w);
   const int nblk = ceil_div(p.pairs_total, max_pairs);
   p.pairs_blk = ceil_div(p.pairs_total, nblk);
   uint32_t cols = 32;
-  while ((int)cols < p.pairs_blk * 16) cols <<= 1;
+  while ((int)cols < 2 * p.pairs_blk * 16) cols <<= 1;          // two accumulators
   p.tmem_cols = cols;
-  const size_t smem = (size_t)p.pairs_blk * 9 * 512 + (size_t)p.nplanes * 2 * p.pairs_blk * p.npos_pad * 16 +
-                      (size_t)p.pairs_blk * 16 * sizeof(float) + 16 + (size_t)p.npos * p.nplanes * sizeof(int);
+  const size_t smem = (size_t)p.pairs_blk * 9 * 512 + 2 * (size_t)p.nplanes * 2 * p.pairs_blk * p.npos_pad * 16 +
+                      (size_t)p.pairs_blk * 16 * sizeof(float) + 10 * sizeof(uint64_t) + 2 * (size_t)p.npos * p.nplanes * sizeof(int) + 64;
   TDEED_REQUIRE((long long)p.npos * p.nplanes * 2 * p.pairs_blk < 65536, TDEED_ERR_UNSUPPORTED, "tdeed_conv3x3g_tc_fwd: tile too large");
   TDEED_REQUIRE(smem <= 227 * 1024, TDEED_ERR_UNSUPPORTED, "tdeed_conv3x3g_tc_fwd: width %d needs %zu B of shared memory", w, smem);
   static size_t smem_set = 48 * 1024;
