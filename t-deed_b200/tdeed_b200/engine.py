@@ -378,10 +378,10 @@ class InferenceEngine:
         return self.heads(x)
 
     # ------------------------------------------------------------------ CUDA graph replay
-    def forward_graphed(self, frames, flip=False):
+    def forward_graphed(self, frames, flip=False, crop=None):
         """Same as forward() but replays a captured CUDA graph (static shapes).  Returns views of
         static output buffers that are overwritten by the next call with the same key."""
-        key = (tuple(frames.shape), frames.dtype, bool(flip))
+        key = (tuple(frames.shape), frames.dtype, bool(flip), crop)
         ent = self._graphs.get(key)
         if ent is None:
             static_in = torch.empty_like(frames)
@@ -390,13 +390,13 @@ class InferenceEngine:
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(2):               # warm-up: sets kernel attributes, primes the allocator
-                    self.forward(static_in, flip=flip)
+                    self.forward(static_in, flip=flip, crop=crop)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             n0 = self.launches
             with torch.cuda.graph(graph):
-                outs = self.forward(static_in, flip=flip)
+                outs = self.forward(static_in, flip=flip, crop=crop)
             ent = dict(graph=graph, static_in=static_in, outs=outs, launches=self.launches - n0)
             self._graphs[key] = ent
         ent['static_in'].copy_(frames, non_blocking=True)

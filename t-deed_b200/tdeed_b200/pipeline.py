@@ -32,6 +32,41 @@ class VideoScores:
         return ops.extract_events(self.scores, self.support, threshold)
 
 
+_cudart = None
+
+
+def _memcpy2d_async(dst_ptr, dpitch, src_ptr, spitch, width, height, stream):
+    """cudaMemcpy2DAsync(host -> device) through the CUDA runtime PyTorch already loaded (plumbing, not compute)."""
+    global _cudart
+    if _cudart is None:
+        import ctypes
+        import glob
+        import os
+        lib = None
+        for soname in ('libcudart.so.12', 'libcudart.so.13', 'libcudart.so'):   # the copy PyTorch already mapped
+            try:
+                lib = ctypes.CDLL(soname)
+                break
+            except OSError:
+                pass
+        for pat in () if lib is not None else (os.path.join(os.path.dirname(torch.__file__), 'lib', 'libcudart*.so*'),
+                    os.path.join(os.path.dirname(torch.__file__), '..', 'nvidia', 'cuda_runtime', 'lib', 'libcudart.so*'),
+                    '/usr/local/cuda/lib64/libcudart.so*'):
+            hits = sorted(glob.glob(pat))
+            if hits:
+                lib = ctypes.CDLL(hits[0])
+                break
+        if lib is None:
+            raise RuntimeError('libcudart not found')
+        lib.cudaMemcpy2DAsync.restype = ctypes.c_int
+        lib.cudaMemcpy2DAsync.argtypes = [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
+                                          ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p]
+        _cudart = lib
+    rc = _cudart.cudaMemcpy2DAsync(dst_ptr, dpitch, src_ptr, spitch, width, height, 1, stream)   # 1 = cudaMemcpyHostToDevice
+    if rc != 0:
+        raise RuntimeError('cudaMemcpy2DAsync failed with cudaError %d' % rc)
+
+
 class ClipUploader:
     """Double-buffered host->device staging of clip batches on a side stream, so the PCIe copy of batch i+1
     overlaps the kernels of batch i (the reference blocks on `.to(device)` inside predict, model/model.py:340-342).
@@ -43,8 +78,14 @@ class ClipUploader:
             up.release()                           # call after enqueuing the readers of x
     """
 
-    def __init__(self, batch_shape, device, dtype=torch.uint8):
+    def __init__(self, batch_shape, device, dtype=torch.uint8, crop=None):
+        """crop = (y0, x0, h, w): upload only that window of every frame (the columns/rows the network's center crop
+        keeps) with a strided 2D DMA — 44 % fewer PCIe bytes for 224x398 frames cropped to 224x224.  The returned
+        device tensor then has shape (B, T, 3, h, w) and must be run with crop offsets (0, 0)."""
         self.stream = torch.cuda.Stream(device=device)
+        self.crop = crop
+        if crop is not None:
+            batch_shape = tuple(batch_shape[:-2]) + (crop[2], crop[3])
         self.bufs = [torch.empty(batch_shape, dtype=dtype, device=device) for _ in range(2)]
         self.ready = [torch.cuda.Event() for _ in range(2)]
         self.free = [torch.cuda.Event() for _ in range(2)]
@@ -57,7 +98,18 @@ class ClipUploader:
         with torch.cuda.stream(self.stream):
             if self._used[k]:
                 self.stream.wait_event(self.free[k])         # readers of this buffer (two uploads ago) are done
-            self.bufs[k][:n].copy_(host_clips, non_blocking=True)
+            if self.crop is None:
+                self.bufs[k][:n].copy_(host_clips, non_blocking=True)
+            else:
+                assert host_clips.is_contiguous() and host_clips.is_pinned() and host_clips.dtype == torch.uint8
+                y0, x0, h, w = self.crop
+                in_h, in_w = host_clips.shape[-2:]
+                planes = host_clips.numel() // (in_h * in_w)
+                dst = self.bufs[k][:n]
+                if h == in_h:           # rows of all planes are equally spaced: one 2D copy for the whole batch
+                    _memcpy2d_async(dst.data_ptr(), w, host_clips.data_ptr() + x0, in_w, w, planes * in_h, self.stream.cuda_stream)
+                else:                   # vertical crop too: one 2D copy per plane would be too many calls -> 3D not exposed; fall back
+                    dst.copy_(host_clips[..., y0:y0 + h, x0:x0 + w], non_blocking=True)
             self.ready[k].record(self.stream)
         torch.cuda.current_stream().wait_event(self.ready[k])
         self._k = k
