@@ -181,7 +181,7 @@ conv3x3g_tc_kernel(const C3TParams p) {
         const bool valid = pix >= 0;
         const __nv_bfloat16* src = valid ? p.in + (size_t)pix * p.C + (size_t)(chunk0 + c) * 8 : p.in;
         const uint32_t dst = sIn_u32 + (uint32_t)((pl * nch + c) * p.npos_pad + s) * 16u;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(valid ? 16 : 0) : "memory");   // .ca: halo rows and parity neighbours are re-read by the next tiles / planes
       }
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(c3_smem_u32(&full_bar[buf])) : "memory");
     }
