@@ -110,9 +110,10 @@ int tdeed_conv3x3g_tc_fwd(const void* in, int n, int h, int w, int c, int stride
 
 /* (4) squeeze-excite, in place: x *= sigmoid(fc2(relu(fc1(mean_hw(x))))).  timm SEModule.
  * x: NHWC [n, hw, c]; w1 [rd][c], b1 [rd], w2t [rd][c] (fc2 weight TRANSPOSED so that channel reads coalesce),
- * b2 [c]; all fp32. */
+ * b2 [c]; all fp32.  workspace: fp32, tdeed_se_workspace_floats(n, c) elements (per-frame means and scales). */
+long long tdeed_se_workspace_floats(int n, int c);
 int tdeed_se_fwd(int dtype, void* x, int n, int hw, int c, int rd,
-                 const float* w1, const float* b1, const float* w2t, const float* b2, void* stream);
+                 const float* w1, const float* b1, const float* w2t, const float* b2, float* workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (5) Gate-Shift module on the first `fold` channels of x (model/shift.py:64-93):

@@ -33,80 +33,87 @@ __device__ inline void frame_channel_sums(const T* __restrict__ x, int hw, int c
   __syncthreads();
 }
 
-constexpr int SE_MAX_F = 4;    // frames per CTA (template parameter NF in {1, 2, 4})
+// Squeeze-excite as three kernels (r1e: the fused one-CTA-per-frame kernel fetched the 2*rd*c fc weights — 270 KB at
+// 7x7x368, 7x the frame's own activations — once per frame and was the slowest op of every stage-4 block):
+//   1. se_mean_kernel   per frame: channel means (fixed-order reduction)                       -> mean [n][c]
+//   2. se_fc_kernel     per SE_FR frames: fc1 + ReLU + fc2 + sigmoid, weights fetched once per CTA -> scale [n][c]
+//   3. se_scale_kernel  elementwise x *= scale[frame][channel], full-grid streaming pass
+constexpr int SE_FR = 8;
 
-// A CTA handles `fpc` consecutive frames so that the fc weights (2 * rd * c floats — more bytes than a 7x7 frame's
-// activations) are fetched from L2 once per CTA instead of once per frame (r1c: the 7x7x368 SE launches were the
-// slowest although their tensors are the smallest).
-template <typename T, int NF>
+template <typename T>
 __global__ void __launch_bounds__(SE_THREADS)
-se_kernel(T* __restrict__ x, int n, int hw, int c, int rd, const float* __restrict__ w1,
-          const float* __restrict__ b1, const float* __restrict__ w2t, const float* __restrict__ b2) {
+se_mean_kernel(const T* __restrict__ x, int hw, int c, float* __restrict__ mean) {
   extern __shared__ float smem[];
   const int c8n = c / 8;
   const int S = SE_THREADS / c8n > 0 ? SE_THREADS / c8n : 1;
-  float* s_part = smem;                          // [S][c]
-  float* s_mean = s_part + (size_t)S * c;        // [fpc][c]   (later reused as the scale)
-  float* s_hid = s_mean + (size_t)NF * c;        // [NF][rd]
-  const int f0 = blockIdx.x * NF;
-  const int nf = min(NF, n - f0);
+  float* s_part = smem;
+  float* s_sum = s_part + (size_t)S * c;
+  const int f = blockIdx.x;
+  frame_channel_sums(x + (size_t)f * hw * c, hw, c, s_part, s_sum);
   const float inv = 1.f / (float)hw;
+  for (int ch = threadIdx.x; ch < c; ch += SE_THREADS) mean[(size_t)f * c + ch] = s_sum[ch] * inv;
+}
 
-  for (int f = 0; f < nf; ++f) {
-    frame_channel_sums(x + (size_t)(f0 + f) * hw * c, hw, c, s_part, s_mean + (size_t)f * c);
-  }
-  for (int i = threadIdx.x; i < nf * c; i += SE_THREADS) s_mean[i] *= inv;
+__global__ void __launch_bounds__(SE_THREADS)
+se_fc_kernel(const float* __restrict__ mean, int n, int c, int rd, const float* __restrict__ w1,
+             const float* __restrict__ b1, const float* __restrict__ w2t, const float* __restrict__ b2,
+             float* __restrict__ scale) {
+  extern __shared__ float smem[];
+  float* s_mean = smem;                         // [SE_FR][c]
+  float* s_hid = s_mean + (size_t)SE_FR * c;    // [SE_FR][rd]
+  const int f0 = blockIdx.x * SE_FR;
+  const int nf = min(SE_FR, n - f0);
+  for (int i = threadIdx.x; i < SE_FR * c; i += SE_THREADS) s_mean[i] = (i < nf * c) ? mean[(size_t)f0 * c + i] : 0.f;
   __syncthreads();
-
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int r = warp; r < rd; r += SE_THREADS / 32) {
-    float acc[NF];
+    float acc[SE_FR];
 #pragma unroll
-    for (int f = 0; f < NF; ++f) acc[f] = 0.f;
+    for (int f = 0; f < SE_FR; ++f) acc[f] = 0.f;
     for (int ch = lane; ch < c; ch += 32) {
       const float wv = w1[(size_t)r * c + ch];
 #pragma unroll
-      for (int f = 0; f < NF; ++f)
-        if (f < nf) acc[f] = fmaf(wv, s_mean[f * c + ch], acc[f]);
+      for (int f = 0; f < SE_FR; ++f) acc[f] = fmaf(wv, s_mean[f * c + ch], acc[f]);
     }
     const float bb = b1[r];
 #pragma unroll
-    for (int f = 0; f < NF; ++f) {
-      if (f < nf) {                                  // nf is CTA-uniform
-        const float sres = warp_sum(acc[f]);
-        if (lane == 0) s_hid[f * rd + r] = fmaxf(sres + bb, 0.f);
-      }
+    for (int f = 0; f < SE_FR; ++f) {
+      const float sres = warp_sum(acc[f]);
+      if (lane == 0) s_hid[f * rd + r] = fmaxf(sres + bb, 0.f);
     }
   }
   __syncthreads();
   for (int ch = threadIdx.x; ch < c; ch += SE_THREADS) {
-    float acc[NF];
+    float acc[SE_FR];
     const float bb = b2[ch];
 #pragma unroll
-    for (int f = 0; f < NF; ++f) acc[f] = bb;
+    for (int f = 0; f < SE_FR; ++f) acc[f] = bb;
     for (int r = 0; r < rd; ++r) {
       const float wv = w2t[(size_t)r * c + ch];      // coalesced over ch
 #pragma unroll
-      for (int f = 0; f < NF; ++f)
-        if (f < nf) acc[f] = fmaf(wv, s_hid[f * rd + r], acc[f]);
+      for (int f = 0; f < SE_FR; ++f) acc[f] = fmaf(wv, s_hid[f * rd + r], acc[f]);
     }
 #pragma unroll
-    for (int f = 0; f < NF; ++f)
-      if (f < nf) s_mean[f * c + ch] = sigmoidf_(acc[f]);    // s_mean now holds the scale (each thread owns its channel)
+    for (int f = 0; f < SE_FR; ++f)
+      if (f < nf) scale[(size_t)(f0 + f) * c + ch] = sigmoidf_(acc[f]);
   }
-  __syncthreads();
-  T* xf = x + (size_t)f0 * hw * c;
-  const int per_frame = hw * c8n;
-  for (int q = threadIdx.x; q < nf * per_frame; q += SE_THREADS) {
-    const int f = q / per_frame, rem = q - f * per_frame;
-    const int c8 = rem % c8n;
-    float v[8];
-    T* ptr = xf + (size_t)q * 8;                              // frames are contiguous: element offset = q * 8
-    load8(ptr, v);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] *= s_mean[f * c + c8 * 8 + j];
-    store8(ptr, v);
-  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SE_THREADS)
+se_scale_kernel(T* __restrict__ x, long long total8, int per_frame8, int c8n, int c, const float* __restrict__ scale) {
+  const long long q = (long long)blockIdx.x * SE_THREADS + threadIdx.x;
+  if (q >= total8) return;
+  const long long f = q / per_frame8;
+  const int c8 = (int)(q % c8n);
+  float v[8];
+  T* ptr = x + q * 8;
+  load8(ptr, v);
+  const float4 s0 = *reinterpret_cast<const float4*>(scale + f * c + c8 * 8);
+  const float4 s1 = *reinterpret_cast<const float4*>(scale + f * c + c8 * 8 + 4);
+  v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w;
+  v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
+  store8(ptr, v);
 }
 
 template <typename T>
@@ -133,38 +140,48 @@ static size_t part_floats(int c) {
 
 }  // namespace tdeed
 
+extern "C" long long tdeed_se_workspace_floats(int n, int c) { return 2LL * n * c; }
+
 extern "C" int tdeed_se_fwd(int dtype, void* x, int n, int hw, int c, int rd, const float* w1, const float* b1,
-                            const float* w2, const float* b2, void* stream) {
+                            const float* w2, const float* b2, float* workspace, void* stream) {
   using namespace tdeed;
-  TDEED_REQUIRE(x && w1 && b1 && w2 && b2, TDEED_ERR_SHAPE, "tdeed_se_fwd: null pointer");
-  TDEED_REQUIRE(n > 0 && hw > 0 && c > 0 && c % 8 == 0 && c <= 2048 && rd > 0, TDEED_ERR_SHAPE,
+  TDEED_REQUIRE(x && w1 && b1 && w2 && b2 && workspace, TDEED_ERR_SHAPE, "tdeed_se_fwd: null pointer");
+  TDEED_REQUIRE(n > 0 && hw > 0 && c > 0 && c % 8 == 0 && c <= 2048 && rd > 0 && rd <= 1024, TDEED_ERR_SHAPE,
                 "tdeed_se_fwd: bad shape n=%d hw=%d c=%d rd=%d", n, hw, c, rd);
-  // frames per CTA: enough that a CTA's activation bytes outweigh the fc weights it has to fetch
-  const size_t frame_bytes = (size_t)hw * c * (dtype == TDEED_BF16 ? 2 : 4);
-  const size_t weight_bytes = (size_t)2 * rd * c * sizeof(float);
-  int fpc = (int)((weight_bytes + frame_bytes - 1) / frame_bytes);
-  // ... but never at the price of parallelism: the sums / scale passes are latency-bound streams, so keep at least
-  // 8 CTAs per SM in flight (r1d: 8 frames per CTA at 3900 frames was 1.8x SLOWER than one frame per CTA)
-  if (fpc > n / (8 * kNumSMs)) fpc = n / (8 * kNumSMs);
-  fpc = fpc >= 4 ? 4 : (fpc >= 2 ? 2 : 1);
-  const size_t smem = (part_floats(c) + (size_t)fpc * (c + rd)) * sizeof(float);
-  TDEED_REQUIRE(smem <= 200 * 1024, TDEED_ERR_UNSUPPORTED, "tdeed_se_fwd: c=%d rd=%d need %zu B of shared memory", c, rd, smem);
+  TDEED_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, TDEED_ERR_SHAPE, "tdeed_se_fwd: workspace must be 16-byte aligned");
+  float* mean = workspace;
+  float* scale = workspace + (size_t)n * c;
   cudaStream_t st = (cudaStream_t)stream;
-  const int grid = ceil_div(n, fpc);
-  if (smem > 48 * 1024) fpc = 1;     // keep to the default shared-memory carve-out (c <= 2048 always fits with NF = 1)
-  const size_t smem1 = (part_floats(c) + (size_t)fpc * (c + rd)) * sizeof(float);
-#define TDEED_SE_LAUNCH(TT, NFV) se_kernel<TT, NFV><<<ceil_div(n, NFV), SE_THREADS, smem1, st>>>((TT*)x, n, hw, c, rd, w1, b1, w2, b2)
+  const size_t smem_mean = (part_floats(c) + (size_t)c) * sizeof(float);
+  const size_t smem_fc = (size_t)SE_FR * (c + rd) * sizeof(float);
+  if (smem_fc > 48 * 1024) {
+    static bool set = false;
+    if (!set) {
+      cudaError_t e = cudaFuncSetAttribute(se_fc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+      TDEED_REQUIRE(e == cudaSuccess, TDEED_ERR_CUDA, "tdeed_se_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      set = true;
+    }
+  }
+  const long long total8 = (long long)n * hw * (c / 8);
+  const unsigned scale_grid = (unsigned)ceil_div_ll(total8, SE_THREADS);
   if (dtype == TDEED_BF16) {
-    if (fpc == 4) TDEED_SE_LAUNCH(__nv_bfloat16, 4); else if (fpc == 2) TDEED_SE_LAUNCH(__nv_bfloat16, 2); else TDEED_SE_LAUNCH(__nv_bfloat16, 1);
+    se_mean_kernel<__nv_bfloat16><<<n, SE_THREADS, smem_mean, st>>>((const __nv_bfloat16*)x, hw, c, mean);
   } else if (dtype == TDEED_F32) {
-    if (fpc == 4) TDEED_SE_LAUNCH(float, 4); else if (fpc == 2) TDEED_SE_LAUNCH(float, 2); else TDEED_SE_LAUNCH(float, 1);
+    se_mean_kernel<float><<<n, SE_THREADS, smem_mean, st>>>((const float*)x, hw, c, mean);
   } else {
     set_error("tdeed_se_fwd: dtype %d", dtype);
     return TDEED_ERR_UNSUPPORTED;
   }
-#undef TDEED_SE_LAUNCH
-  (void)grid;
-  return check_launch("tdeed_se_fwd");
+  int rc = check_launch("tdeed_se_fwd(mean)");
+  if (rc) return rc;
+  se_fc_kernel<<<ceil_div(n, SE_FR), SE_THREADS, smem_fc, st>>>(mean, n, c, rd, w1, b1, w2, b2, scale);
+  rc = check_launch("tdeed_se_fwd(fc)");
+  if (rc) return rc;
+  if (dtype == TDEED_BF16)
+    se_scale_kernel<__nv_bfloat16><<<scale_grid, SE_THREADS, 0, st>>>((__nv_bfloat16*)x, total8, hw * (c / 8), c / 8, c, scale);
+  else
+    se_scale_kernel<float><<<scale_grid, SE_THREADS, 0, st>>>((float*)x, total8, hw * (c / 8), c / 8, c, scale);
+  return check_launch("tdeed_se_fwd(scale)");
 }
 
 extern "C" int tdeed_pool_posenc_fwd(int dtype, const void* x, int n, int hw, int c, int clip_len,

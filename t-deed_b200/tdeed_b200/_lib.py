@@ -49,7 +49,8 @@ SIGNATURES = {
                                c_vp, c_ll, c_int, c_int, c_vp, c_ll, c_int, c_int, c_vp]),
     'tdeed_conv3x3g_fwd': (c_int, [c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     'tdeed_conv3x3g_tc_fwd': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
-    'tdeed_se_fwd': (c_int, [c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'tdeed_se_workspace_floats': (c_ll, [c_int, c_int]),
+    'tdeed_se_fwd': (c_int, [c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     'tdeed_gsf_workspace_floats': (c_ll, [c_int, c_int, c_int, c_int, c_int]),
     'tdeed_gsf_fwd': (c_int, [c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
                               c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),

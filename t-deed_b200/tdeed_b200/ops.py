@@ -96,8 +96,9 @@ def conv3x3g_tc(x, wimg, bias, stride, out=None):
 
 def se_(x, w1, b1, w2, b2):
     n, h, w, c = x.shape
+    ws = torch.empty(int(L.load().tdeed_se_workspace_floats(n, c)), dtype=torch.float32, device=x.device)
     L.check(L.load().tdeed_se_fwd(L.dtype_code(x.dtype), L.ptr(x), n, h * w, c, w1.shape[0], L.ptr(w1), L.ptr(b1),
-                                  L.ptr(w2), L.ptr(b2), L.stream()), 'se')
+                                  L.ptr(w2), L.ptr(b2), L.ptr(ws), L.stream()), 'se')
     return x
 
 
