@@ -38,7 +38,7 @@ gsf_q_kernel(const T* __restrict__ x, int h, int w, int c, int fold, int rows_pe
   const int half = fold / 2;
   const int wp = w + 2;
   const int rp = rows_per_cta + 2;
-  const int plane = rp * wp + 1;                 // +1: odd-ish plane pitch spreads the channel planes over banks
+  const int plane = (rp * wp + 4) | 1;           // +4: the last strip may read past the row end; odd pitch spreads planes over banks
   float4* s_w = reinterpret_cast<float4*>(smem); // [9][fold] : (kt0, kt1, kt2, -)
   float* s_z = smem + 9 * fold * 4;              // [fold][plane]
   const int f = blockIdx.y;
@@ -74,34 +74,52 @@ gsf_q_kernel(const T* __restrict__ x, int h, int w, int c, int fold, int rows_pe
   }
   __syncthreads();
 
+  // compute: a thread owns a strip of 4 horizontally adjacent pixels, so every z value feeds up to 3 taps x 3 temporal
+  // slices and every weight fetch feeds 4 pixels (the one-pixel-per-thread version ran at 85 % L1TEX: shared-memory bound)
   const int hw = h * w;
-  for (int p = threadIdx.x; p < rows * w; p += GS_THREADS) {
-    const int py = p / w, px = p - py * w;
-    const float* zc = s_z + py * wp + px;          // top-left of the 3x3 window in a channel plane
-    float a[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int strips = (w + 3) / 4;
+  for (int it = threadIdx.x; it < rows * strips; it += GS_THREADS) {
+    const int py = it / strips, x0 = (it - py * strips) * 4;
+    float acc[2][3][4];
+#pragma unroll
+    for (int g = 0; g < 2; ++g)
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[g][k][q] = 0.f;
 #pragma unroll
     for (int g = 0; g < 2; ++g) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
       for (int ci = 0; ci < half; ++ci) {
         const int ch = g * half + ci;
-        const float* zp = zc + ch * plane;
+        const float* zp = s_z + ch * plane + py * wp + x0;   // top-left of the strip's 3 x 6 window
+        float zr[3][6];
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int j = 0; j < 6; ++j) zr[dy][j] = zp[dy * wp + j];   // columns past the row end are only used by masked pixels
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
           for (int dx = 0; dx < 3; ++dx) {
-            const float zv = zp[dy * wp + dx];
             const float4 w4 = s_w[(dy * 3 + dx) * fold + ch];
-            a0 = fmaf(zv, w4.x, a0);
-            a1 = fmaf(zv, w4.y, a1);
-            a2 = fmaf(zv, w4.z, a2);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float zv = zr[dy][q + dx];
+              acc[g][0][q] = fmaf(zv, w4.x, acc[g][0][q]);
+              acc[g][1][q] = fmaf(zv, w4.y, acc[g][1][q]);
+              acc[g][2][q] = fmaf(zv, w4.z, acc[g][2][q]);
+            }
           }
       }
-      a[3 * g] = a0; a[3 * g + 1] = a1; a[3 * g + 2] = a2;
     }
-    float2* q = reinterpret_cast<float2*>(Q + ((size_t)f * hw + (size_t)(y0 + py) * w + px) * 6);
-    q[0] = make_float2(a[0], a[1]);
-    q[1] = make_float2(a[2], a[3]);
-    q[2] = make_float2(a[4], a[5]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (x0 + q >= w) break;
+      float2* qo = reinterpret_cast<float2*>(Q + ((size_t)f * hw + (size_t)(y0 + py) * w + x0 + q) * 6);
+      qo[0] = make_float2(acc[0][0][q], acc[0][1][q]);
+      qo[1] = make_float2(acc[0][2][q], acc[1][0][q]);
+      qo[2] = make_float2(acc[1][1][q], acc[1][2][q]);
+    }
   }
 }
 
@@ -249,8 +267,8 @@ static int launch_gsf(int mode, const void* x, int clips, int clip_len, int h, i
   // kernel 1: rows per CTA so that the staged z tile fits the shared-memory budget
   const size_t w_bytes = (size_t)9 * fold * 16;
   int rows = h;
-  while (rows > 1 && w_bytes + (size_t)fold * ((size_t)(rows + 2) * (w + 2) + 1) * 4 > (size_t)GS_Q_SMEM_BUDGET) rows = (rows + 1) / 2;
-  const size_t smem_q = w_bytes + (size_t)fold * ((size_t)(rows + 2) * (w + 2) + 1) * 4;
+  while (rows > 1 && w_bytes + (size_t)fold * ((size_t)(rows + 2) * (w + 2) + 5) * 4 > (size_t)GS_Q_SMEM_BUDGET) rows = (rows + 1) / 2;
+  const size_t smem_q = w_bytes + (size_t)fold * ((size_t)(rows + 2) * (w + 2) + 5) * 4;
   TDEED_REQUIRE(smem_q <= 200 * 1024, TDEED_ERR_UNSUPPORTED, "tdeed_gsf_fwd: a single row of %d px x %d ch does not fit shared memory", w, fold);
   auto kq = gsf_q_kernel<T>;
   static size_t q_set = 48 * 1024;
