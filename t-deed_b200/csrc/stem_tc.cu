@@ -93,6 +93,42 @@ __device__ __forceinline__ void st_store_row(uint8_t* tile, int r, const uint32_
     *reinterpret_cast<uint4*>(base + kc * 128) = make_uint4(wds[4 * kc], wds[4 * kc + 1], wds[4 * kc + 2], wds[4 * kc + 3]);
 }
 
+// u8 frames: every patch row is 33 contiguous source bytes -> fetch it as <= 10 ALIGNED 32-bit words (4x fewer load
+// instructions than byte loads).  Item i = (channel, patch row, word) of thread tid, iteration k.
+constexpr int ST_WORDS = 10;                                    // ceil((33 + 3) / 4) + 1
+constexpr int ST_ITEMS = 3 * ST_PH * ST_WORDS;
+constexpr int ST_WITERS = (ST_ITEMS + ST_THREADS - 1) / ST_THREADS;
+
+__device__ __forceinline__ void stem_load_words(const StemTcParams& p, int tile, int tid, uint32_t (&wv)[ST_WITERS], int (&koff)[ST_WITERS]) {
+  const int txi = tile % p.tiles_x, tyi = (tile / p.tiles_x) % p.tiles_y, f = tile / (p.tiles_x * p.tiles_y);
+  const int iy0 = 2 * tyi * ST_TH - 1, ix0 = 2 * txi * ST_TW - 1;
+  const uint8_t* lo_ok = reinterpret_cast<const uint8_t*>(p.frames);
+  const uint8_t* hi_ok = lo_ok + p.frames_bytes;
+  const uint8_t* fb = lo_ok + (size_t)f * 3 * p.in_h * p.in_w;
+#pragma unroll
+  for (int k = 0; k < ST_WITERS; ++k) {
+    const int i = tid + k * ST_THREADS;
+    const int wq = i % ST_WORDS, py = (i / ST_WORDS) % ST_PH, ci = i / (ST_WORDS * ST_PH);
+    const int y = iy0 + py;
+    koff[k] = INT_MIN;
+    wv[k] = 0u;
+    if (i < ST_ITEMS && y >= 0 && y < p.h) {
+      // source span of this patch row: offsets 0..32 <-> x = ix0 + (flip ? 32 - o : o)
+      const int s_lo = p.flip ? (p.w - 1 - (ix0 + ST_PW - 1)) : ix0;
+      const uint8_t* row = fb + ((size_t)ci * p.in_h + (p.crop_y + y)) * p.in_w + p.crop_x + s_lo;
+      const int mis = (int)(reinterpret_cast<uintptr_t>(row) & 3);
+      const uint8_t* wp = row - mis + 4 * wq;
+      koff[k] = 4 * wq - mis;
+      if (wp >= lo_ok && wp + 4 <= hi_ok) {
+        wv[k] = *reinterpret_cast<const uint32_t*>(wp);
+      } else {                                                // first / last word of the whole tensor: byte-wise
+        for (int b = 0; b < 4; ++b)
+          if (wp + b >= lo_ok && wp + b < hi_ok) wv[k] |= (uint32_t)wp[b] << (8 * b);
+      }
+    }
+  }
+}
+
 template <typename TIn>
 __global__ void __launch_bounds__(ST_THREADS)
 stem_tc_kernel(const StemTcParams p) {
@@ -150,6 +186,10 @@ stem_tc_kernel(const StemTcParams p) {
   const TIn* frames = reinterpret_cast<const TIn*>(p.frames);
   const int sub_oh = (p.oh + p.stem_sub - 1) / p.stem_sub, sub_ow = (p.ow + p.stem_sub - 1) / p.stem_sub;
 
+  uint32_t wv[ST_WITERS];
+  int koff[ST_WITERS];
+  if (sizeof(TIn) == 1 && (int)blockIdx.x < p.num_tiles) stem_load_words(p, blockIdx.x, tid, wv, koff);
+
   for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
     const int txi = tile % p.tiles_x, tyi = (tile / p.tiles_x) % p.tiles_y, f = tile / (p.tiles_x * p.tiles_y);
     const int oy0 = tyi * ST_TH, ox0 = txi * ST_TW;
@@ -158,44 +198,13 @@ stem_tc_kernel(const StemTcParams p) {
 
     // ---- normalised input patch (zero padding applies in normalised space) ----
     if (sizeof(TIn) == 1) {
-      // u8 frames: every patch row is 33 contiguous source bytes -> fetch it as <= 10 ALIGNED 32-bit words (4x fewer
-      // load instructions than byte loads; the staging loop was 44 % of the stall samples in ncu r1c), all of a
-      // thread's words in flight before the first use, then LUT-normalise byte by byte.
-      constexpr int kWords = 10;                                   // ceil((33 + 3) / 4) + 1
-      constexpr int kItems = 3 * ST_PH * kWords;
-      constexpr int kIters = (kItems + ST_THREADS - 1) / ST_THREADS;
-      const uint8_t* fb = reinterpret_cast<const uint8_t*>(fbase);
-      const uint8_t* lo_ok = reinterpret_cast<const uint8_t*>(p.frames);
-      const uint8_t* hi_ok = lo_ok + p.frames_bytes;
-      uint32_t wv[kIters];
-      int koff[kIters];                                            // source offset (relative to the row span) of byte 0, or INT_MIN
+      // the words of THIS tile were requested one iteration ago (software pipelining: the global latency of the patch
+      // is hidden behind the previous tile's MMAs and epilogue); LUT-normalise them byte by byte
 #pragma unroll
-      for (int k = 0; k < kIters; ++k) {
-        const int i = tid + k * ST_THREADS;
-        const int wq = i % kWords, py = (i / kWords) % ST_PH, ci = i / (kWords * ST_PH);
-        const int y = iy0 + py;
-        koff[k] = INT_MIN;
-        wv[k] = 0u;
-        if (i < kItems && y >= 0 && y < p.h) {
-          // source span of this patch row: offsets 0..32 <-> x = ix0 + (flip ? 32 - k : k)
-          const int s_lo = p.flip ? (p.w - 1 - (ix0 + ST_PW - 1)) : ix0;
-          const uint8_t* row = fb + ((size_t)ci * p.in_h + (p.crop_y + y)) * p.in_w + p.crop_x + s_lo;
-          const int mis = (int)(reinterpret_cast<uintptr_t>(row) & 3);
-          const uint8_t* wp = row - mis + 4 * wq;
-          koff[k] = 4 * wq - mis;
-          if (wp >= lo_ok && wp + 4 <= hi_ok) {
-            wv[k] = *reinterpret_cast<const uint32_t*>(wp);
-          } else {                                                // first / last word of the whole tensor: byte-wise
-            for (int b = 0; b < 4; ++b)
-              if (wp + b >= lo_ok && wp + b < hi_ok) wv[k] |= (uint32_t)wp[b] << (8 * b);
-          }
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < kIters; ++k) {
+      for (int k = 0; k < ST_WITERS; ++k) {
         if (koff[k] == INT_MIN) continue;
         const int i = tid + k * ST_THREADS;
-        const int py = (i / kWords) % ST_PH, ci = i / (kWords * ST_PH);
+        const int py = (i / ST_WORDS) % ST_PH, ci = i / (ST_WORDS * ST_PH);
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           const int o = koff[k] + b;
@@ -256,6 +265,7 @@ stem_tc_kernel(const StemTcParams p) {
       }
       st_store_row(sA, tid, wds);
     }
+    if (sizeof(TIn) == 1 && tile + (int)gridDim.x < p.num_tiles) stem_load_words(p, tile + gridDim.x, tid, wv, koff);   // prefetch
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
     if (tid == 0) {
