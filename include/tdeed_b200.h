@@ -216,4 +216,7 @@ int tdeed_nms(const int* frame, const int* label, const float* score, const int*
 #ifdef __cplusplus
 }
 #endif
+
+#include "tdeed_b200_train.h" /* training-step entry points */
+
 #endif /* TDEED_B200_H_ */

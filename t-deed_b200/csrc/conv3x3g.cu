@@ -17,7 +17,7 @@ constexpr int C3_MAX_UNITS = 16;   // output octets per CTA
 template <typename T, int STRIDE>
 __global__ void __launch_bounds__(C3_THREADS)
 conv3x3g_kernel(const T* __restrict__ in, int h, int w, int c, int gw, const float* __restrict__ weight,
-                const float* __restrict__ bias, T* __restrict__ out, int oh, int ow, int units_per_cta) {
+                const float* __restrict__ bias, T* __restrict__ out, int oh, int ow, int units_per_cta, int relu) {
   extern __shared__ __align__(16) float s_w[];
   const int n_units = c / 8;
   const int u0 = blockIdx.y * units_per_cta;
@@ -94,7 +94,7 @@ conv3x3g_kernel(const T* __restrict__ in, int h, int w, int c, int gw, const flo
 
   float b[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) b[j] = bias[u * 8 + j];
+  for (int j = 0; j < 8; ++j) b[j] = bias ? bias[u * 8 + j] : 0.f;
   T* fout = out + (size_t)f * oh * ow * c;
 #pragma unroll
   for (int p = 0; p < C3_PX; ++p) {
@@ -102,14 +102,14 @@ conv3x3g_kernel(const T* __restrict__ in, int h, int w, int c, int gw, const flo
     if (ox >= ow) break;
     float r[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) r[j] = fmaxf(acc[p][j] + b[j], 0.f);
+    for (int j = 0; j < 8; ++j) r[j] = relu ? fmaxf(acc[p][j] + b[j], 0.f) : acc[p][j] + b[j];
     store8(fout + ((size_t)oy * ow + ox) * c + u * 8, r);
   }
 }
 
 template <typename T, int STRIDE>
 static int launch_conv3(const void* in, int n, int h, int w, int c, int gw, const float* weight, const float* bias,
-                        void* out, cudaStream_t st) {
+                        void* out, int relu, cudaStream_t st) {
   const int oh = (h + STRIDE - 1) / STRIDE, ow = (w + STRIDE - 1) / STRIDE;
   const int n_units = c / 8;
   const int upc = n_units < C3_MAX_UNITS ? n_units : C3_MAX_UNITS;
@@ -123,29 +123,41 @@ static int launch_conv3(const void* in, int n, int h, int w, int c, int gw, cons
     smem_set = smem;
   }
   dim3 grid(ceil_div(oh * strips * upc, C3_THREADS), ceil_div(n_units, upc), n);
-  kern<<<grid, C3_THREADS, smem, st>>>((const T*)in, h, w, c, gw, weight, bias, (T*)out, oh, ow, upc);
+  kern<<<grid, C3_THREADS, smem, st>>>((const T*)in, h, w, c, gw, weight, bias, (T*)out, oh, ow, upc, relu);
   return check_launch("tdeed_conv3x3g_fwd");
 }
 
 }  // namespace tdeed
 
-extern "C" int tdeed_conv3x3g_fwd(int dtype, const void* in, int n, int h, int w, int c, int group_width, int stride,
-                                  const float* weight, const float* bias, void* out, void* stream) {
+static int conv3x3g_dispatch(const char* name, int dtype, const void* in, int n, int h, int w, int c, int group_width, int stride,
+                             const float* weight, const float* bias, int relu, void* out, void* stream) {
   using namespace tdeed;
-  TDEED_REQUIRE(in && weight && bias && out, TDEED_ERR_SHAPE, "tdeed_conv3x3g_fwd: null pointer");
+  TDEED_REQUIRE(in && weight && out, TDEED_ERR_SHAPE, "%s: null pointer", name);
   TDEED_REQUIRE(n > 0 && n <= 65535 && h > 0 && w > 0 && c > 0 && c % group_width == 0, TDEED_ERR_SHAPE,
-                "tdeed_conv3x3g_fwd: bad shape n=%d %dx%dx%d gw=%d", n, h, w, c, group_width);
+                "%s: bad shape n=%d %dx%dx%d gw=%d", name, n, h, w, c, group_width);
   TDEED_REQUIRE(group_width == 8 || group_width == 16, TDEED_ERR_UNSUPPORTED,
-                "tdeed_conv3x3g_fwd: group width %d (RegNetY-200MF/800MF use 8/16)", group_width);
-  TDEED_REQUIRE(stride == 1 || stride == 2, TDEED_ERR_UNSUPPORTED, "tdeed_conv3x3g_fwd: stride %d", stride);
+                "%s: group width %d (RegNetY-200MF/800MF use 8/16)", name, group_width);
+  TDEED_REQUIRE(stride == 1 || stride == 2, TDEED_ERR_UNSUPPORTED, "%s: stride %d", name, stride);
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == TDEED_BF16) {
-    return stride == 1 ? launch_conv3<__nv_bfloat16, 1>(in, n, h, w, c, group_width, weight, bias, out, st)
-                       : launch_conv3<__nv_bfloat16, 2>(in, n, h, w, c, group_width, weight, bias, out, st);
+    return stride == 1 ? launch_conv3<__nv_bfloat16, 1>(in, n, h, w, c, group_width, weight, bias, out, relu, st)
+                       : launch_conv3<__nv_bfloat16, 2>(in, n, h, w, c, group_width, weight, bias, out, relu, st);
   } else if (dtype == TDEED_F32) {
-    return stride == 1 ? launch_conv3<float, 1>(in, n, h, w, c, group_width, weight, bias, out, st)
-                       : launch_conv3<float, 2>(in, n, h, w, c, group_width, weight, bias, out, st);
+    return stride == 1 ? launch_conv3<float, 1>(in, n, h, w, c, group_width, weight, bias, out, relu, st)
+                       : launch_conv3<float, 2>(in, n, h, w, c, group_width, weight, bias, out, relu, st);
   }
-  set_error("tdeed_conv3x3g_fwd: dtype %d", dtype);
+  set_error("%s: dtype %d", name, dtype);
   return TDEED_ERR_UNSUPPORTED;
+}
+
+extern "C" int tdeed_conv3x3g_fwd(int dtype, const void* in, int n, int h, int w, int c, int group_width, int stride,
+                                  const float* weight, const float* bias, void* out, void* stream) {
+  TDEED_REQUIRE(bias, TDEED_ERR_SHAPE, "tdeed_conv3x3g_fwd: null pointer");
+  return conv3x3g_dispatch("tdeed_conv3x3g_fwd", dtype, in, n, h, w, c, group_width, stride, weight, bias, 1, out, stream);
+}
+
+// training: the raw convolution (no bias, no activation); BatchNorm statistics are taken from this output
+extern "C" int tdeed_conv3x3g_raw_fwd(int dtype, const void* in, int n, int h, int w, int c, int group_width, int stride,
+                                      const float* weight, void* out, void* stream) {
+  return conv3x3g_dispatch("tdeed_conv3x3g_raw_fwd", dtype, in, n, h, w, c, group_width, stride, weight, nullptr, 0, out, stream);
 }

@@ -210,7 +210,7 @@ template <typename T>
 __global__ void __launch_bounds__(GS_THREADS)
 gsf_blend_kernel(const T* __restrict__ x, int clip_len, int hw, int c, int fold, int mode,
                  const float* __restrict__ gate, const float* __restrict__ wgt, T* __restrict__ out, int ld_out,
-                 long long total) {
+                 long long total, int copy_tail) {
   const long long idx = (long long)blockIdx.x * GS_THREADS + threadIdx.x;
   if (idx >= total) return;
   const int o8n = ld_out / 8;
@@ -248,6 +248,7 @@ gsf_blend_kernel(const T* __restrict__ x, int clip_len, int hw, int c, int fold,
         v = ys + r;
       }
     }
+    else if (copy_tail && jo < c) v = Elem<T>::ld(xt + jo);   // training: materialise the concat [gs(x[:, :fold]) | x[:, fold:]]
     o[j] = v;
   }
   store8(out + (size_t)fp * ld_out + o8 * 8, o);
@@ -256,7 +257,7 @@ gsf_blend_kernel(const T* __restrict__ x, int clip_len, int hw, int c, int fold,
 template <typename T>
 static int launch_gsf(int mode, const void* x, int clips, int clip_len, int h, int w, int c, int fold,
                       const float* bn_scale, const float* bn_shift, const float* w3d, const float* b3d,
-                      const float* cc_w, const float* cc_b, float* ws, void* out, int ld_out, cudaStream_t st) {
+                      const float* cc_w, const float* cc_b, float* ws, void* out, int ld_out, int copy_tail, cudaStream_t st) {
   const int n = clips * clip_len, hw = h * w;
   float* gate = ws;
   float* sums = gate + (size_t)n * hw * 2;
@@ -292,7 +293,7 @@ static int launch_gsf(int mode, const void* x, int clips, int clip_len, int h, i
   }
   const long long total = (long long)n * hw * (ld_out / 8);
   gsf_blend_kernel<T><<<(unsigned)ceil_div_ll(total, GS_THREADS), GS_THREADS, 0, st>>>(
-      (const T*)x, clip_len, hw, c, fold, mode, gate, wgt, (T*)out, ld_out, total);
+      (const T*)x, clip_len, hw, c, fold, mode, gate, wgt, (T*)out, ld_out, total, copy_tail);
   return check_launch("tdeed_gsf_fwd(blend)");
 }
 
@@ -303,10 +304,10 @@ extern "C" long long tdeed_gsf_workspace_floats(int clips, int clip_len, int h, 
   return n * h * w * 2 + n * fold * 2 + n * fold + 4 + n * h * w * 6;
 }
 
-extern "C" int tdeed_gsf_fwd(int dtype, int mode, const void* x, int clips, int clip_len, int h, int w, int c, int fold,
-                             const float* bn_scale, const float* bn_shift, const float* conv3d_w, const float* conv3d_b,
-                             const float* cc_w, const float* cc_b, float* workspace, void* out, int ld_out,
-                             void* stream) {
+static int gsf_dispatch(int dtype, int mode, const void* x, int clips, int clip_len, int h, int w, int c, int fold,
+                        const float* bn_scale, const float* bn_shift, const float* conv3d_w, const float* conv3d_b,
+                        const float* cc_w, const float* cc_b, float* workspace, void* out, int ld_out, int copy_tail,
+                        void* stream) {
   using namespace tdeed;
   TDEED_REQUIRE(x && bn_scale && bn_shift && conv3d_w && conv3d_b && workspace && out, TDEED_ERR_SHAPE,
                 "tdeed_gsf_fwd: null pointer");
@@ -318,10 +319,27 @@ extern "C" int tdeed_gsf_fwd(int dtype, int mode, const void* x, int clips, int 
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == TDEED_BF16)
     return launch_gsf<__nv_bfloat16>(mode, x, clips, clip_len, h, w, c, fold, bn_scale, bn_shift, conv3d_w, conv3d_b,
-                                     cc_w, cc_b, workspace, out, ld_out, st);
+                                     cc_w, cc_b, workspace, out, ld_out, copy_tail, st);
   if (dtype == TDEED_F32)
     return launch_gsf<float>(mode, x, clips, clip_len, h, w, c, fold, bn_scale, bn_shift, conv3d_w, conv3d_b, cc_w, cc_b,
-                             workspace, out, ld_out, st);
+                             workspace, out, ld_out, copy_tail, st);
   set_error("tdeed_gsf_fwd: dtype %d", dtype);
   return TDEED_ERR_UNSUPPORTED;
+}
+
+extern "C" int tdeed_gsf_fwd(int dtype, int mode, const void* x, int clips, int clip_len, int h, int w, int c, int fold,
+                             const float* bn_scale, const float* bn_shift, const float* conv3d_w, const float* conv3d_b,
+                             const float* cc_w, const float* cc_b, float* workspace, void* out, int ld_out,
+                             void* stream) {
+  return gsf_dispatch(dtype, mode, x, clips, clip_len, h, w, c, fold, bn_scale, bn_shift, conv3d_w, conv3d_b, cc_w, cc_b,
+                      workspace, out, ld_out, 0, stream);
+}
+
+// training: writes the full concat y = [gs(x[:, :fold]) | x[:, fold:]] as [frames*h*w, c] (model/shift.py:89-93); the
+// workspace (gate, per-frame sums, fusion weights) is what tdeed_gsf_bwd reads back.
+extern "C" int tdeed_gsf_cat_fwd(int dtype, int mode, const void* x, int clips, int clip_len, int h, int w, int c, int fold,
+                                 const float* bn_scale, const float* bn_shift, const float* conv3d_w, const float* conv3d_b,
+                                 const float* cc_w, const float* cc_b, float* workspace, void* out, void* stream) {
+  return gsf_dispatch(dtype, mode, x, clips, clip_len, h, w, c, fold, bn_scale, bn_shift, conv3d_w, conv3d_b, cc_w, cc_b,
+                      workspace, out, c, 1, stream);
 }

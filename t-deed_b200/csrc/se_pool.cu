@@ -101,19 +101,18 @@ se_fc_kernel(const float* __restrict__ mean, int n, int c, int rd, const float* 
 
 template <typename T>
 __global__ void __launch_bounds__(SE_THREADS)
-se_scale_kernel(T* __restrict__ x, long long total8, int per_frame8, int c8n, int c, const float* __restrict__ scale) {
+se_scale_kernel(const T* x, T* out, long long total8, int per_frame8, int c8n, int c, const float* __restrict__ scale) {
   const long long q = (long long)blockIdx.x * SE_THREADS + threadIdx.x;
   if (q >= total8) return;
   const long long f = q / per_frame8;
   const int c8 = (int)(q % c8n);
   float v[8];
-  T* ptr = x + q * 8;
-  load8(ptr, v);
+  load8(x + q * 8, v);
   const float4 s0 = *reinterpret_cast<const float4*>(scale + f * c + c8 * 8);
   const float4 s1 = *reinterpret_cast<const float4*>(scale + f * c + c8 * 8 + 4);
   v[0] *= s0.x; v[1] *= s0.y; v[2] *= s0.z; v[3] *= s0.w;
   v[4] *= s1.x; v[5] *= s1.y; v[6] *= s1.z; v[7] *= s1.w;
-  store8(ptr, v);
+  store8(out + q * 8, v);
 }
 
 template <typename T>
@@ -142,8 +141,8 @@ static size_t part_floats(int c) {
 
 extern "C" long long tdeed_se_workspace_floats(int n, int c) { return 2LL * n * c; }
 
-extern "C" int tdeed_se_fwd(int dtype, void* x, int n, int hw, int c, int rd, const float* w1, const float* b1,
-                            const float* w2, const float* b2, float* workspace, void* stream) {
+static int se_forward(int dtype, const void* x, void* out, int n, int hw, int c, int rd, const float* w1, const float* b1,
+                      const float* w2, const float* b2, float* workspace, void* stream) {
   using namespace tdeed;
   TDEED_REQUIRE(x && w1 && b1 && w2 && b2 && workspace, TDEED_ERR_SHAPE, "tdeed_se_fwd: null pointer");
   TDEED_REQUIRE(n > 0 && hw > 0 && c > 0 && c % 8 == 0 && c <= 2048 && rd > 0 && rd <= 1024, TDEED_ERR_SHAPE,
@@ -178,10 +177,23 @@ extern "C" int tdeed_se_fwd(int dtype, void* x, int n, int hw, int c, int rd, co
   rc = check_launch("tdeed_se_fwd(fc)");
   if (rc) return rc;
   if (dtype == TDEED_BF16)
-    se_scale_kernel<__nv_bfloat16><<<scale_grid, SE_THREADS, 0, st>>>((__nv_bfloat16*)x, total8, hw * (c / 8), c / 8, c, scale);
+    se_scale_kernel<__nv_bfloat16><<<scale_grid, SE_THREADS, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, total8, hw * (c / 8), c / 8, c, scale);
   else
-    se_scale_kernel<float><<<scale_grid, SE_THREADS, 0, st>>>((float*)x, total8, hw * (c / 8), c / 8, c, scale);
+    se_scale_kernel<float><<<scale_grid, SE_THREADS, 0, st>>>((const float*)x, (float*)out, total8, hw * (c / 8), c / 8, c, scale);
   return check_launch("tdeed_se_fwd(scale)");
+}
+
+extern "C" int tdeed_se_fwd(int dtype, void* x, int n, int hw, int c, int rd, const float* w1, const float* b1,
+                            const float* w2, const float* b2, float* workspace, void* stream) {
+  return se_forward(dtype, x, x, n, hw, c, rd, w1, b1, w2, b2, workspace, stream);
+}
+
+// training: out-of-place (the unscaled activation is needed by the backward pass); workspace keeps the per-frame means
+// [n][c] and scales [n][c] for tdeed_se_bwd
+extern "C" int tdeed_se_train_fwd(int dtype, const void* x, void* out, int n, int hw, int c, int rd, const float* w1,
+                                  const float* b1, const float* w2t, const float* b2, float* workspace, void* stream) {
+  TDEED_REQUIRE(out, TDEED_ERR_SHAPE, "tdeed_se_train_fwd: null pointer");
+  return se_forward(dtype, x, out, n, hw, c, rd, w1, b1, w2t, b2, workspace, stream);
 }
 
 extern "C" int tdeed_pool_posenc_fwd(int dtype, const void* x, int n, int hw, int c, int clip_len,
@@ -198,4 +210,181 @@ extern "C" int tdeed_pool_posenc_fwd(int dtype, const void* x, int n, int hw, in
     pool_posenc_kernel<float><<<n, SE_THREADS, smem, st>>>((const float*)x, hw, c, clip_len, temp_enc, out);
   else { set_error("tdeed_pool_posenc_fwd: dtype %d", dtype); return TDEED_ERR_UNSUPPORTED; }
   return check_launch("tdeed_pool_posenc_fwd");
+}
+
+// ---- squeeze-excite backward -------------------------------------------------------------------------------------
+//   u = x * s[f, c]:   ds[f,c] = sum_hw du * x;   dv = ds * s (1 - s);   h = relu(W1 m + b1);
+//   dh = (W2^T dv) * (h > 0);   dm = W1^T dh;   dx = du * s + dm / hw
+// Weight gradients are left to tdeed_gemm_tn / tdeed_colsum on the per-frame vectors written to `vec`:
+//   vec = dv [n][c] | dh [n][rd] | h [n][rd] | dm [n][c]
+namespace tdeed {
+
+template <typename T>
+__global__ void __launch_bounds__(SE_THREADS)
+se_bwd_ds_kernel(const T* __restrict__ x, const T* __restrict__ du, int hw, int c, float* __restrict__ ds) {
+  extern __shared__ float smem[];
+  const int c8n = c / 8;
+  const int S = SE_THREADS / c8n > 0 ? SE_THREADS / c8n : 1;
+  float* s_part = smem;
+  const size_t base = (size_t)blockIdx.x * hw * c;
+  for (int q = threadIdx.x; q < c8n * S; q += SE_THREADS) {
+    const int c8 = q % c8n, seg = q / c8n;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int p = seg; p < hw; p += S) {
+      float a[8], b[8];
+      load8(x + base + (size_t)p * c + c8 * 8, a);
+      load8(du + base + (size_t)p * c + c8 * 8, b);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(a[j], b[j], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_part[seg * c + c8 * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += SE_THREADS) {
+    float s = 0.f;
+    for (int seg = 0; seg < S; ++seg) s += s_part[seg * c + ch];
+    ds[(size_t)blockIdx.x * c + ch] = s;
+  }
+}
+
+// one CTA per frame (the fc matrices are small next to the activations in training batches)
+__global__ void __launch_bounds__(SE_THREADS)
+se_bwd_fc_kernel(const float* __restrict__ mean, const float* __restrict__ scale, const float* __restrict__ ds, int c, int rd,
+                 const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2t,
+                 float* __restrict__ dv_out, float* __restrict__ dh_out, float* __restrict__ h_out, float* __restrict__ dm_out) {
+  extern __shared__ float smem[];
+  float* s_m = smem;            // [c]
+  float* s_dv = s_m + c;        // [c]
+  float* s_h = s_dv + c;        // [rd]
+  float* s_dh = s_h + rd;       // [rd]
+  const int f = blockIdx.x;
+  for (int ch = threadIdx.x; ch < c; ch += SE_THREADS) {
+    const float s = scale[(size_t)f * c + ch];
+    const float dv = ds[(size_t)f * c + ch] * s * (1.f - s);
+    s_m[ch] = mean[(size_t)f * c + ch];
+    s_dv[ch] = dv;
+    dv_out[(size_t)f * c + ch] = dv;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int r = warp; r < rd; r += SE_THREADS / 32) {
+    float a = 0.f, g = 0.f;
+    for (int ch = lane; ch < c; ch += 32) {
+      a = fmaf(w1[(size_t)r * c + ch], s_m[ch], a);
+      g = fmaf(w2t[(size_t)r * c + ch], s_dv[ch], g);
+    }
+    a = warp_sum(a);
+    g = warp_sum(g);
+    if (lane == 0) {
+      const float hv = fmaxf(a + b1[r], 0.f);
+      const float dh = hv > 0.f ? g : 0.f;
+      s_h[r] = hv;
+      s_dh[r] = dh;
+      h_out[(size_t)f * rd + r] = hv;
+      dh_out[(size_t)f * rd + r] = dh;
+    }
+  }
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += SE_THREADS) {
+    float a = 0.f;
+    for (int r = 0; r < rd; ++r) a = fmaf(w1[(size_t)r * c + ch], s_dh[r], a);
+    dm_out[(size_t)f * c + ch] = a;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SE_THREADS)
+se_bwd_dx_kernel(const T* __restrict__ du, long long total8, int per_frame8, int c8n, int c, float inv_hw,
+                 const float* __restrict__ scale, const float* __restrict__ dm, T* __restrict__ dx) {
+  const long long q = (long long)blockIdx.x * SE_THREADS + threadIdx.x;
+  if (q >= total8) return;
+  const long long f = q / per_frame8;
+  const int c0 = (int)(q % c8n) * 8;
+  float v[8];
+  load8(du + q * 8, v);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = fmaf(v[j], scale[f * c + c0 + j], dm[f * c + c0 + j] * inv_hw);
+  store8(dx + q * 8, v);
+}
+
+// dz[f, p, :] = dfeat[f, :] / hw (backward of the global average pool), and d temp_enc[t, :] = sum_b dfeat[b*T + t, :]
+template <typename T>
+__global__ void __launch_bounds__(SE_THREADS)
+pool_bwd_kernel(const float* __restrict__ dfeat, long long total8, int per_frame8, int c8n, int c, float inv_hw, T* __restrict__ dz) {
+  const long long q = (long long)blockIdx.x * SE_THREADS + threadIdx.x;
+  if (q >= total8) return;
+  const long long f = q / per_frame8;
+  const int c0 = (int)(q % c8n) * 8;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = dfeat[f * c + c0 + j] * inv_hw;
+  store8(dz + q * 8, v);
+}
+
+__global__ void temp_enc_bwd_kernel(const float* __restrict__ dfeat, int clips, int clip_len, int c, float* __restrict__ dte) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= clip_len * c) return;
+  float s = 0.f;
+  for (int b = 0; b < clips; ++b) s += dfeat[(size_t)b * clip_len * c + i];
+  dte[i] = s;
+}
+
+}  // namespace tdeed
+
+extern "C" long long tdeed_se_bwd_vec_floats(int n, int c, int rd) { return (long long)n * (3LL * c + 2LL * rd); }
+
+extern "C" int tdeed_se_bwd(int dtype, const void* x, const void* du, int n, int hw, int c, int rd, const float* w1,
+                            const float* b1, const float* w2t, const float* fwd_workspace, void* dx, float* vec, void* stream) {
+  using namespace tdeed;
+  TDEED_REQUIRE(x && du && w1 && b1 && w2t && fwd_workspace && dx && vec, TDEED_ERR_SHAPE, "tdeed_se_bwd: null pointer");
+  TDEED_REQUIRE(n > 0 && hw > 0 && c > 0 && c % 8 == 0 && c <= 2048 && rd > 0 && rd <= 1024, TDEED_ERR_SHAPE,
+                "tdeed_se_bwd: bad shape n=%d hw=%d c=%d rd=%d", n, hw, c, rd);
+  const float* mean = fwd_workspace;
+  const float* scale = fwd_workspace + (size_t)n * c;
+  float* dv = vec;
+  float* dh = dv + (size_t)n * c;
+  float* hh = dh + (size_t)n * rd;
+  float* dm = hh + (size_t)n * rd;
+  float* ds = dm + (size_t)n * c;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem_ds = part_floats(c) * sizeof(float);
+  const size_t smem_fc = (size_t)(2 * c + 2 * rd) * sizeof(float);
+  const long long total8 = (long long)n * hw * (c / 8);
+  const unsigned grid = (unsigned)ceil_div_ll(total8, SE_THREADS);
+  if (dtype == TDEED_BF16)
+    se_bwd_ds_kernel<__nv_bfloat16><<<n, SE_THREADS, smem_ds, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)du, hw, c, ds);
+  else if (dtype == TDEED_F32)
+    se_bwd_ds_kernel<float><<<n, SE_THREADS, smem_ds, st>>>((const float*)x, (const float*)du, hw, c, ds);
+  else { set_error("tdeed_se_bwd: dtype %d", dtype); return TDEED_ERR_UNSUPPORTED; }
+  int rc = check_launch("tdeed_se_bwd(ds)");
+  if (rc) return rc;
+  se_bwd_fc_kernel<<<n, SE_THREADS, smem_fc, st>>>(mean, scale, ds, c, rd, w1, b1, w2t, dv, dh, hh, dm);
+  rc = check_launch("tdeed_se_bwd(fc)");
+  if (rc) return rc;
+  if (dtype == TDEED_BF16)
+    se_bwd_dx_kernel<__nv_bfloat16><<<grid, SE_THREADS, 0, st>>>((const __nv_bfloat16*)du, total8, hw * (c / 8), c / 8, c, 1.f / hw, scale, dm, (__nv_bfloat16*)dx);
+  else
+    se_bwd_dx_kernel<float><<<grid, SE_THREADS, 0, st>>>((const float*)du, total8, hw * (c / 8), c / 8, c, 1.f / hw, scale, dm, (float*)dx);
+  return check_launch("tdeed_se_bwd(dx)");
+}
+
+extern "C" int tdeed_pool_posenc_bwd(int dtype, const float* dfeat, int clips, int clip_len, int hw, int c, void* dz,
+                                     float* d_temp_enc, void* stream) {
+  using namespace tdeed;
+  TDEED_REQUIRE(dfeat && dz && d_temp_enc, TDEED_ERR_SHAPE, "tdeed_pool_posenc_bwd: null pointer");
+  TDEED_REQUIRE(clips > 0 && clip_len > 0 && hw > 0 && c > 0 && c % 8 == 0, TDEED_ERR_SHAPE, "tdeed_pool_posenc_bwd: bad shape");
+  const long long n = (long long)clips * clip_len;
+  const long long total8 = n * hw * (c / 8);
+  const unsigned grid = (unsigned)ceil_div_ll(total8, SE_THREADS);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == TDEED_BF16)
+    pool_bwd_kernel<__nv_bfloat16><<<grid, SE_THREADS, 0, st>>>(dfeat, total8, hw * (c / 8), c / 8, c, 1.f / hw, (__nv_bfloat16*)dz);
+  else if (dtype == TDEED_F32)
+    pool_bwd_kernel<float><<<grid, SE_THREADS, 0, st>>>(dfeat, total8, hw * (c / 8), c / 8, c, 1.f / hw, (float*)dz);
+  else { set_error("tdeed_pool_posenc_bwd: dtype %d", dtype); return TDEED_ERR_UNSUPPORTED; }
+  int rc = check_launch("tdeed_pool_posenc_bwd");
+  if (rc) return rc;
+  temp_enc_bwd_kernel<<<ceil_div(clip_len * c, 256), 256, 0, st>>>(dfeat, clips, clip_len, c, d_temp_enc);
+  return check_launch("tdeed_pool_posenc_bwd(temp_enc)");
 }

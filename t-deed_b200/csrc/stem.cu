@@ -18,7 +18,7 @@ template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(STEM_TW * STEM_TH)
 stem_kernel(const TIn* __restrict__ frames, int in_h, int in_w, int crop_y, int crop_x, int h, int w, int flip,
             const float* __restrict__ weight, const float* __restrict__ bias, TOut* __restrict__ out,
-            int oh, int ow) {
+            int oh, int ow, int relu, int unit_input) {
   __shared__ float s_in[3][STEM_PH][STEM_PWP];
   __shared__ __align__(16) float s_w[27][STEM_CO];   // [ci*9 + ky*3 + kx][co]
   __shared__ float s_b[STEM_CO];
@@ -31,7 +31,7 @@ stem_kernel(const TIn* __restrict__ frames, int in_h, int in_w, int crop_y, int 
     const int co = i % STEM_CO, tap = i / STEM_CO;
     s_w[tap][co] = weight[co * 27 + tap];
   }
-  if (tid < STEM_CO) s_b[tid] = bias[tid];
+  if (tid < STEM_CO) s_b[tid] = bias ? bias[tid] : 0.f;
 
   const float mean[3] = {0.485f, 0.456f, 0.406f};
   const float stdv[3] = {0.229f, 0.224f, 0.225f};
@@ -44,7 +44,7 @@ stem_kernel(const TIn* __restrict__ frames, int in_h, int in_w, int crop_y, int 
     if (y >= 0 && y < h && x >= 0 && x < w) {
       const int sx = flip ? (w - 1 - x) : x;
       const float raw = (float)fbase[((size_t)ci * in_h + (crop_y + y)) * in_w + (crop_x + sx)];
-      v = (raw / 255.f - mean[ci]) / stdv[ci];
+      v = ((unit_input ? raw : raw / 255.f) - mean[ci]) / stdv[ci];
     }
     s_in[ci][py][px] = v;
   }
@@ -77,7 +77,7 @@ stem_kernel(const TIn* __restrict__ frames, int in_h, int in_w, int crop_y, int 
     for (int q = 0; q < STEM_CO / 8; ++q) {
       float v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = fmaxf(acc[8 * q + j], 0.f);
+      for (int j = 0; j < 8; ++j) v[j] = relu ? fmaxf(acc[8 * q + j], 0.f) : acc[8 * q + j];
       store8(o + 8 * q, v);
     }
   }
@@ -85,33 +85,50 @@ stem_kernel(const TIn* __restrict__ frames, int in_h, int in_w, int crop_y, int 
 
 template <typename TIn, typename TOut>
 static int launch_stem(const void* frames, int n, int in_h, int in_w, int cy, int cx, int h, int w, int flip,
-                       const float* weight, const float* bias, void* out, cudaStream_t st) {
+                       const float* weight, const float* bias, void* out, int relu, int unit_input, cudaStream_t st) {
   const int oh = (h + 1) / 2, ow = (w + 1) / 2;
   dim3 grid(ceil_div(ow, STEM_TW), ceil_div(oh, STEM_TH), n), block(STEM_TW, STEM_TH);
   stem_kernel<TIn, TOut><<<grid, block, 0, st>>>((const TIn*)frames, in_h, in_w, cy, cx, h, w, flip, weight, bias,
-                                                 (TOut*)out, oh, ow);
+                                                 (TOut*)out, oh, ow, relu, unit_input);
   return check_launch("tdeed_stem_fwd");
 }
 
 }  // namespace tdeed
 
+static int stem_dispatch(const char* name, const void* frames, int frames_dtype, int n_frames, int in_h, int in_w,
+                         int crop_y, int crop_x, int h, int w, int flip, const float* weight, const float* bias, int relu,
+                         int unit_input, void* out, int out_dtype, void* stream) {
+  using namespace tdeed;
+  TDEED_REQUIRE(frames && weight && out, TDEED_ERR_SHAPE, "%s: null pointer", name);
+  TDEED_REQUIRE(n_frames > 0 && n_frames <= 65535 && h > 0 && w > 0 && crop_y >= 0 && crop_x >= 0 &&
+                crop_y + h <= in_h && crop_x + w <= in_w, TDEED_ERR_SHAPE,
+                "%s: bad geometry n=%d in=%dx%d crop=(%d,%d) %dx%d", name, n_frames, in_h, in_w, crop_y, crop_x, h, w);
+  cudaStream_t st = (cudaStream_t)stream;
+#define STEM_CASE(DI, TI, DO, TO) \
+  if (frames_dtype == DI && out_dtype == DO) \
+    return launch_stem<TI, TO>(frames, n_frames, in_h, in_w, crop_y, crop_x, h, w, flip, weight, bias, out, relu, unit_input, st);
+  STEM_CASE(TDEED_U8, uint8_t, TDEED_BF16, __nv_bfloat16)
+  STEM_CASE(TDEED_U8, uint8_t, TDEED_F32, float)
+  STEM_CASE(TDEED_F32, float, TDEED_BF16, __nv_bfloat16)
+  STEM_CASE(TDEED_F32, float, TDEED_F32, float)
+#undef STEM_CASE
+  set_error("%s: unsupported dtypes %d -> %d", name, frames_dtype, out_dtype);
+  return TDEED_ERR_UNSUPPORTED;
+}
+
 extern "C" int tdeed_stem_fwd(const void* frames, int frames_dtype, int n_frames, int in_h, int in_w,
                               int crop_y, int crop_x, int h, int w, int flip,
                               const float* weight, const float* bias, void* out, int out_dtype, void* stream) {
-  using namespace tdeed;
-  TDEED_REQUIRE(frames && weight && bias && out, TDEED_ERR_SHAPE, "tdeed_stem_fwd: null pointer");
-  TDEED_REQUIRE(n_frames > 0 && n_frames <= 65535 && h > 0 && w > 0 && crop_y >= 0 && crop_x >= 0 &&
-                crop_y + h <= in_h && crop_x + w <= in_w, TDEED_ERR_SHAPE,
-                "tdeed_stem_fwd: bad geometry n=%d in=%dx%d crop=(%d,%d) %dx%d", n_frames, in_h, in_w, crop_y, crop_x, h, w);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (frames_dtype == TDEED_U8 && out_dtype == TDEED_BF16)
-    return launch_stem<uint8_t, __nv_bfloat16>(frames, n_frames, in_h, in_w, crop_y, crop_x, h, w, flip, weight, bias, out, st);
-  if (frames_dtype == TDEED_U8 && out_dtype == TDEED_F32)
-    return launch_stem<uint8_t, float>(frames, n_frames, in_h, in_w, crop_y, crop_x, h, w, flip, weight, bias, out, st);
-  if (frames_dtype == TDEED_F32 && out_dtype == TDEED_BF16)
-    return launch_stem<float, __nv_bfloat16>(frames, n_frames, in_h, in_w, crop_y, crop_x, h, w, flip, weight, bias, out, st);
-  if (frames_dtype == TDEED_F32 && out_dtype == TDEED_F32)
-    return launch_stem<float, float>(frames, n_frames, in_h, in_w, crop_y, crop_x, h, w, flip, weight, bias, out, st);
-  set_error("tdeed_stem_fwd: unsupported dtypes %d -> %d", frames_dtype, out_dtype);
-  return TDEED_ERR_UNSUPPORTED;
+  TDEED_REQUIRE(bias, TDEED_ERR_SHAPE, "tdeed_stem_fwd: null pointer");
+  return stem_dispatch("tdeed_stem_fwd", frames, frames_dtype, n_frames, in_h, in_w, crop_y, crop_x, h, w, flip, weight, bias, 1, 0,
+                       out, out_dtype, stream);
+}
+
+// training: raw stem convolution (no BN fold, no ReLU).  unit_input != 0: frames are floats already divided by 255
+// (the state the reference's augmentation pipeline leaves them in, model/model.py:107-118).
+extern "C" int tdeed_stem_raw_fwd(const void* frames, int frames_dtype, int unit_input, int n_frames, int in_h, int in_w,
+                                  int crop_y, int crop_x, int h, int w, int flip, const float* weight, void* out,
+                                  int out_dtype, void* stream) {
+  return stem_dispatch("tdeed_stem_raw_fwd", frames, frames_dtype, n_frames, in_h, in_w, crop_y, crop_x, h, w, flip, weight, nullptr,
+                       0, unit_input, out, out_dtype, stream);
 }

@@ -1,0 +1,242 @@
+// Training-mode BatchNorm around the convolutions (timm ConvNormAct / BatchNormAct2d in train(); the reference trains the
+// whole backbone, model/model.py:202).  The conv kernels write the RAW convolution output y [M, C] (M = frames*H*W); then
+//   tdeed_bn_stats     per-channel batch mean / biased variance (+ running-statistics update, momentum 0.1, unbiased var)
+//   tdeed_bn_act_fwd   z = act(y*scale + shift (+ residual))
+//   tdeed_bn_act_bwd   g = dz * (z > 0);  dgamma = sum g*xhat;  dbeta = sum g;
+//                      dy = scale * (g - dbeta/M - xhat*dgamma/M);  optionally dres = g (shortcut branch)
+// All per-channel reductions are two-stage with a fixed order (per-thread serial -> shared-memory tree in a fixed order ->
+// per-CTA partials summed in double by one thread per channel): bitwise deterministic, no atomics.
+#include "train_reduce.cuh"
+
+namespace tdeed {
+
+// ---- statistics: sums of (x - pivot) and (x - pivot)^2, pivot = first row (kills the E[x^2]-E[x]^2 cancellation) ----
+template <typename T>
+struct StatsOp {
+  const T* x;
+  long long ld;
+  float piv[8];
+  __device__ void begin(int ch0, int nch) { load_n(x + ch0, nch, piv); }
+  __device__ void row(long long r, int ch0, int nch, float (&a0)[8], float (&a1)[8]) {
+    float v[8];
+    load_n(x + r * ld + ch0, nch, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float d = v[j] - piv[j];
+      a0[j] += d;
+      a1[j] = fmaf(d, d, a1[j]);
+    }
+  }
+};
+
+template <typename T>
+__global__ void bn_stats_final_kernel(const T* __restrict__ x, const float* __restrict__ part, int nparts, long long M, int C,
+                                      const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
+                                      float* __restrict__ running_mean, float* __restrict__ running_var,
+                                      float* __restrict__ stats) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= C) return;
+  const int cpad = ((C + 7) / 8) * 8;
+  double s = 0.0, q = 0.0;
+  for (int p = 0; p < nparts; ++p) {
+    s += (double)part[((size_t)p * 2) * cpad + ch];
+    q += (double)part[((size_t)p * 2 + 1) * cpad + ch];
+  }
+  const double piv = (double)Elem<T>::ld(x + ch);
+  const double dm = s / (double)M;
+  const double mean = piv + dm;
+  double var = q / (double)M - dm * dm;
+  if (var < 0.0) var = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
+  stats[ch] = (float)mean;
+  stats[C + ch] = invstd;
+  stats[2 * C + ch] = g * invstd;
+  stats[3 * C + ch] = b - (float)mean * g * invstd;
+  if (running_mean) {
+    const double unb = M > 1 ? var * (double)M / (double)(M - 1) : var;
+    running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)mean;
+    running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unb;
+  }
+}
+
+// ---- forward apply ----
+template <typename T>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_act_fwd_kernel(const T* __restrict__ y, long long total8, int c8n, const float* __restrict__ scale,
+                  const float* __restrict__ shift, const T* __restrict__ residual, int relu, T* __restrict__ out) {
+  const long long q = (long long)blockIdx.x * BN_THREADS + threadIdx.x;
+  if (q >= total8) return;
+  const int c0 = (int)(q % c8n) * 8;
+  float v[8], r[8];
+  load8(y + q * 8, v);
+  if (residual) load8(residual + q * 8, r);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float t = fmaf(v[j], scale[c0 + j], shift[c0 + j]);
+    if (residual) t += r[j];
+    v[j] = relu ? fmaxf(t, 0.f) : t;
+  }
+  store8(out + q * 8, v);
+}
+
+// ---- backward ----
+template <typename T>
+struct BwdOp {
+  const T* dz;
+  const T* z;      // post-activation output (mask), or nullptr when there is no ReLU
+  const T* y;
+  const float* mean;
+  const float* invstd;
+  int C;
+  float mu[8], is[8];
+  __device__ void begin(int ch0, int nch) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mu[j] = j < nch ? mean[ch0 + j] : 0.f;
+      is[j] = j < nch ? invstd[ch0 + j] : 0.f;
+    }
+  }
+  __device__ void row(long long r, int ch0, int nch, float (&a0)[8], float (&a1)[8]) {
+    float g[8], yv[8], zv[8];
+    load8(dz + r * C + ch0, g);
+    load8(y + r * C + ch0, yv);
+    if (z) load8(z + r * C + ch0, zv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gg = (z && !(zv[j] > 0.f)) ? 0.f : g[j];
+      a0[j] += gg;
+      a1[j] = fmaf(gg, (yv[j] - mu[j]) * is[j], a1[j]);
+    }
+  }
+};
+
+__global__ void bn_bwd_final_kernel(const float* __restrict__ part, int nparts, long long M, int C,
+                                    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= C) return;
+  const int cpad = ((C + 7) / 8) * 8;
+  double s = 0.0, q = 0.0;
+  for (int p = 0; p < nparts; ++p) {
+    s += (double)part[((size_t)p * 2) * cpad + ch];
+    q += (double)part[((size_t)p * 2 + 1) * cpad + ch];
+  }
+  if (dbeta) dbeta[ch] = (float)s;
+  if (dgamma) dgamma[ch] = (float)q;
+  coef[ch] = (float)(s / (double)M);
+  coef[C + ch] = (float)(q / (double)M);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BN_THREADS)
+bn_act_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T* __restrict__ y, long long total8, int c8n,
+                        int C, const float* __restrict__ stats, const float* __restrict__ coef, T* __restrict__ dy,
+                        T* __restrict__ dres) {
+  const long long q = (long long)blockIdx.x * BN_THREADS + threadIdx.x;
+  if (q >= total8) return;
+  const int c0 = (int)(q % c8n) * 8;
+  float g[8], yv[8], zv[8], o[8];
+  load8(dz + q * 8, g);
+  load8(y + q * 8, yv);
+  if (z) load8(z + q * 8, zv);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = c0 + j;
+    if (z && !(zv[j] > 0.f)) g[j] = 0.f;
+    const float xhat = (yv[j] - stats[ch]) * stats[C + ch];
+    o[j] = stats[2 * C + ch] * (g[j] - coef[ch] - xhat * coef[C + ch]);
+  }
+  store8(dy + q * 8, o);
+  if (dres) store8(dres + q * 8, g);
+}
+
+template <typename T>
+static int run_stats(const void* x, long long M, int C, long long ld, const float* gamma, const float* beta, float eps,
+                     float momentum, float* rm, float* rv, float* stats, float* ws, cudaStream_t st) {
+  StatsOp<T> op;
+  op.x = (const T*)x;
+  op.ld = ld;
+  const int grid = bn_grid(M, C);
+  bn_reduce_kernel<T, StatsOp<T>><<<grid, BN_THREADS, 0, st>>>(op, M, C, ws);
+  int rc = check_launch("tdeed_bn_stats(partial)");
+  if (rc) return rc;
+  bn_stats_final_kernel<T><<<ceil_div(C, 128), 128, 0, st>>>((const T*)x, ws, grid, M, C, gamma, beta, eps, momentum, rm, rv, stats);
+  return check_launch("tdeed_bn_stats(final)");
+}
+
+template <typename T>
+static int run_bwd(const void* dz, const void* z, const void* y, long long M, int C, const float* stats, float* dgamma,
+                   float* dbeta, void* dy, void* dres, float* ws, cudaStream_t st) {
+  BwdOp<T> op;
+  op.dz = (const T*)dz;
+  op.z = (const T*)z;
+  op.y = (const T*)y;
+  op.mean = stats;
+  op.invstd = stats + C;
+  op.C = C;
+  const int grid = bn_grid(M, C);
+  const int cpad = ((C + 7) / 8) * 8;
+  float* coef = ws + (size_t)BN_MAX_GRID * 2 * cpad;
+  bn_reduce_kernel<T, BwdOp<T>><<<grid, BN_THREADS, 0, st>>>(op, M, C, ws);
+  int rc = check_launch("tdeed_bn_act_bwd(partial)");
+  if (rc) return rc;
+  bn_bwd_final_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, grid, M, C, dgamma, dbeta, coef);
+  rc = check_launch("tdeed_bn_act_bwd(final)");
+  if (rc) return rc;
+  const long long total8 = M * (C / 8);
+  bn_act_bwd_apply_kernel<T><<<(unsigned)ceil_div_ll(total8, BN_THREADS), BN_THREADS, 0, st>>>(
+      (const T*)dz, (const T*)z, (const T*)y, total8, C / 8, C, stats, coef, (T*)dy, (T*)dres);
+  return check_launch("tdeed_bn_act_bwd(apply)");
+}
+
+}  // namespace tdeed
+
+extern "C" long long tdeed_bn_workspace_floats(int C) {
+  const long long cpad = ((C + 7) / 8) * 8;
+  return (long long)tdeed::BN_MAX_GRID * 2 * cpad + 2 * cpad;
+}
+
+extern "C" int tdeed_bn_stats(int dtype, const void* x, long long M, int C, long long ld, const float* gamma,
+                              const float* beta, float eps, float momentum, float* running_mean, float* running_var,
+                              float* stats, float* workspace, void* stream) {
+  using namespace tdeed;
+  TDEED_REQUIRE(x && stats && workspace, TDEED_ERR_SHAPE, "tdeed_bn_stats: null pointer");
+  TDEED_REQUIRE(M > 0 && C > 0 && C <= 2048 && ld >= C && ld % 8 == 0 && (running_mean == nullptr) == (running_var == nullptr),
+                TDEED_ERR_SHAPE, "tdeed_bn_stats: bad shape M=%lld C=%d ld=%lld", M, C, ld);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == TDEED_BF16) return run_stats<__nv_bfloat16>(x, M, C, ld, gamma, beta, eps, momentum, running_mean, running_var, stats, workspace, st);
+  if (dtype == TDEED_F32) return run_stats<float>(x, M, C, ld, gamma, beta, eps, momentum, running_mean, running_var, stats, workspace, st);
+  set_error("tdeed_bn_stats: dtype %d", dtype);
+  return TDEED_ERR_UNSUPPORTED;
+}
+
+extern "C" int tdeed_bn_act_fwd(int dtype, const void* y, long long M, int C, const float* stats, const void* residual,
+                                int relu, void* out, void* stream) {
+  using namespace tdeed;
+  TDEED_REQUIRE(y && stats && out, TDEED_ERR_SHAPE, "tdeed_bn_act_fwd: null pointer");
+  TDEED_REQUIRE(M > 0 && C > 0 && C % 8 == 0, TDEED_ERR_SHAPE, "tdeed_bn_act_fwd: bad shape M=%lld C=%d", M, C);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total8 = M * (C / 8);
+  const unsigned grid = (unsigned)ceil_div_ll(total8, BN_THREADS);
+  if (dtype == TDEED_BF16)
+    bn_act_fwd_kernel<__nv_bfloat16><<<grid, BN_THREADS, 0, st>>>((const __nv_bfloat16*)y, total8, C / 8, stats + 2 * C, stats + 3 * C,
+                                                                   (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)out);
+  else if (dtype == TDEED_F32)
+    bn_act_fwd_kernel<float><<<grid, BN_THREADS, 0, st>>>((const float*)y, total8, C / 8, stats + 2 * C, stats + 3 * C,
+                                                           (const float*)residual, relu, (float*)out);
+  else { set_error("tdeed_bn_act_fwd: dtype %d", dtype); return TDEED_ERR_UNSUPPORTED; }
+  return check_launch("tdeed_bn_act_fwd");
+}
+
+extern "C" int tdeed_bn_act_bwd(int dtype, const void* dz, const void* z, const void* y, long long M, int C,
+                                const float* stats, float* dgamma, float* dbeta, void* dy, void* dres, float* workspace,
+                                void* stream) {
+  using namespace tdeed;
+  TDEED_REQUIRE(dz && y && stats && dy && workspace, TDEED_ERR_SHAPE, "tdeed_bn_act_bwd: null pointer");
+  TDEED_REQUIRE(M > 0 && C > 0 && C % 8 == 0 && C <= 2048, TDEED_ERR_SHAPE, "tdeed_bn_act_bwd: bad shape M=%lld C=%d", M, C);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == TDEED_BF16) return run_bwd<__nv_bfloat16>(dz, z, y, M, C, stats, dgamma, dbeta, dy, dres, workspace, st);
+  if (dtype == TDEED_F32) return run_bwd<float>(dz, z, y, M, C, stats, dgamma, dbeta, dy, dres, workspace, st);
+  set_error("tdeed_bn_act_bwd: dtype %d", dtype);
+  return TDEED_ERR_UNSUPPORTED;
+}

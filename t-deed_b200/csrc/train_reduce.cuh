@@ -1,0 +1,76 @@
+// Deterministic per-channel (column) reductions shared by the training kernels.
+#pragma once
+#include "common.cuh"
+
+namespace tdeed {
+
+constexpr int BN_THREADS = 256;
+constexpr int BN_MAX_GRID = kNumSMs * 4;
+
+struct BnLayout {
+  int c8n, rpi;   // channel octets; rows handled per CTA iteration
+};
+__host__ __device__ inline BnLayout bn_layout(int C) {
+  BnLayout l;
+  l.c8n = (C + 7) / 8;
+  l.rpi = BN_THREADS / l.c8n;
+  return l;
+}
+
+// Generic column reduction: OP::row(v-arrays) -> two accumulators per channel.  part: [grid][2][c8n*8]
+template <typename T, typename OP>
+__global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(OP op, long long M, int C, float* __restrict__ part) {
+  __shared__ float s_acc[BN_THREADS * 16];
+  const BnLayout l = bn_layout(C);
+  const int c8 = threadIdx.x % l.c8n, lr = threadIdx.x / l.c8n;
+  const bool active = lr < l.rpi;
+  float a0[8], a1[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a0[j] = a1[j] = 0.f;
+  if (active) {
+    const int nch = min(8, C - c8 * 8);
+    op.begin(c8 * 8, nch);
+    for (long long r = (long long)blockIdx.x * l.rpi + lr; r < M; r += (long long)gridDim.x * l.rpi) op.row(r, c8 * 8, nch, a0, a1);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    s_acc[threadIdx.x * 16 + j] = a0[j];
+    s_acc[threadIdx.x * 16 + 8 + j] = a1[j];
+  }
+  __syncthreads();
+  const int cpad = l.c8n * 8;
+  for (int i = threadIdx.x; i < 2 * cpad; i += BN_THREADS) {
+    const int which = i / cpad, ch = i - which * cpad;
+    float s = 0.f;
+    for (int q = 0; q < l.rpi; ++q) s += s_acc[(q * l.c8n + ch / 8) * 16 + which * 8 + (ch & 7)];
+    part[((size_t)blockIdx.x * 2 + which) * cpad + ch] = s;
+  }
+}
+
+template <typename T>
+__device__ inline void load_n(const T* p, int nch, float (&v)[8]) {
+  if (nch == 8) {
+    load8(p, v);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = j < nch ? Elem<T>::ld(p + j) : 0.f;
+  }
+}
+
+
+// out[i] = sum_p part[p][i], summed in double in a fixed order
+static __global__ void partial_sum_kernel(const float* __restrict__ part, int nparts, long long count, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  double s = 0.0;
+  for (int p = 0; p < nparts; ++p) s += (double)part[(size_t)p * count + i];
+  out[i] = (float)s;
+}
+
+inline int bn_grid(long long M, int C) {
+  const BnLayout l = bn_layout(C);
+  const long long need = ceil_div_ll(M, l.rpi);
+  return (int)(need < BN_MAX_GRID ? need : BN_MAX_GRID);
+}
+
+}  // namespace tdeed

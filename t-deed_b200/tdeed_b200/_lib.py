@@ -71,6 +71,58 @@ SIGNATURES = {
                           c_vp, c_vp]),
 }
 
+# include/tdeed_b200_train.h
+c_ull = ctypes.c_ulonglong
+SIGNATURES.update({
+    'tdeed_bn_workspace_floats': (c_ll, [c_int]),
+    'tdeed_bn_stats': (c_int, [c_int, c_vp, c_ll, c_int, c_ll, c_vp, c_vp, c_float, c_float, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'tdeed_bn_act_fwd': (c_int, [c_int, c_vp, c_ll, c_int, c_vp, c_vp, c_int, c_vp, c_vp]),
+    'tdeed_bn_act_bwd': (c_int, [c_int, c_vp, c_vp, c_vp, c_ll, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'tdeed_gemm_tn_workspace_floats': (c_ll, [c_ll, c_int, c_int]),
+    'tdeed_gemm_tn': (c_int, [c_int, c_vp, c_ll, c_int, c_vp, c_ll, c_ll, c_int, c_int, c_int, c_int, c_int, c_float, c_vp,
+                              c_ll, c_vp, c_vp]),
+    'tdeed_colsum_workspace_floats': (c_ll, [c_ll, c_int]),
+    'tdeed_colsum': (c_int, [c_int, c_vp, c_ll, c_int, c_ll, c_vp, c_vp, c_vp]),
+    'tdeed_strided_add': (c_int, [c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    'tdeed_stem_raw_fwd': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp,
+                                   c_int, c_vp]),
+    'tdeed_stem_bwd_weight_workspace_floats': (c_ll, []),
+    'tdeed_stem_bwd_weight': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int,
+                                      c_vp, c_vp, c_vp]),
+    'tdeed_conv3x3g_raw_fwd': (c_int, [c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    'tdeed_conv3x3g_bwd_data': (c_int, [c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    'tdeed_conv3x3g_bwd_weight_workspace_floats': (c_ll, [c_int, c_int, c_int, c_int, c_int, c_int]),
+    'tdeed_conv3x3g_bwd_weight': (c_int, [c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    'tdeed_se_train_fwd': (c_int, [c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'tdeed_se_bwd_vec_floats': (c_ll, [c_int, c_int, c_int]),
+    'tdeed_se_bwd': (c_int, [c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'tdeed_pool_posenc_bwd': (c_int, [c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    'tdeed_gsf_cat_fwd': (c_int, [c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
+                                  c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'tdeed_gsf_bwd_workspace_floats': (c_ll, [c_int, c_int, c_int, c_int, c_int]),
+    'tdeed_gsf_bwd': (c_int, [c_int, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
+                              c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'tdeed_chan_ln_fwd': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'tdeed_chan_ln_bwd': (c_int, [c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'tdeed_maxpool_bwd': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    'tdeed_sgp_branch_bwd_workspace_floats': (c_ll, [c_int, c_int, c_int]),
+    'tdeed_sgp_branch_bwd': (c_int, [c_vp, c_ll, c_vp, c_vp, c_vp, c_ll, c_int, c_int, c_int, c_int, c_int,
+                                     ctypes.POINTER(c_vp), ctypes.POINTER(c_vp), c_vp, c_vp, c_vp]),
+    'tdeed_groupnorm_bwd': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'tdeed_gelu_fwd': (c_int, [c_vp, c_ll, c_vp, c_int, c_vp]),
+    'tdeed_gelu_bwd': (c_int, [c_vp, c_vp, c_ll, c_vp, c_int, c_vp]),
+    'tdeed_upsample_bwd': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
+    'tdeed_cast_f32': (c_int, [c_vp, c_ll, c_vp, c_int, c_vp]),
+    'tdeed_dropout_fwd': (c_int, [c_vp, c_ll, c_float, c_ull, c_vp, c_vp, c_vp]),
+    'tdeed_dropout_bwd': (c_int, [c_vp, c_vp, c_ll, c_float, c_vp, c_vp, c_vp]),
+    'tdeed_linear_fwd': (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_vp]),
+    'tdeed_linear_bwd_data': (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp]),
+    'tdeed_ce_mse_loss': (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'tdeed_adamw_step': (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_double, c_double, c_double, c_double, c_double, c_int,
+                                 c_float, c_vp, c_vp]),
+    'tdeed_axpy': (c_int, [c_vp, c_float, c_ll, c_vp, c_vp]),
+})
+
 _lib = None
 
 

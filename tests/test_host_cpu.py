@@ -21,10 +21,14 @@ def _args(cfg):
 
 def test_library_exports_every_declared_symbol():
     from tdeed_b200 import _lib
-    header = open(os.path.join(ROOT, 'include', 'tdeed_b200.h')).read()
+    header = ''.join(open(os.path.join(ROOT, 'include', h)).read() for h in ('tdeed_b200.h', 'tdeed_b200_train.h'))
     declared = set(re.findall(r'\b(tdeed_[a-z0-9_]+)\s*\(', header))
     declared -= {'tdeed_gemm_seg', 'tdeed_status'}
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    # argument counts of the ctypes prototypes == the header's
+    for name, args in re.findall(r'\b(tdeed_[a-z0-9_]+)\s*\(([^)]*)\)\s*;', re.sub(r'/\*.*?\*/', '', header, flags=re.S)):
+        n = 0 if args.strip() in ('', 'void') else len(args.split(','))
+        assert n == len(_lib.SIGNATURES[name][1]), (name, n, len(_lib.SIGNATURES[name][1]))
     lib = ctypes.CDLL(_lib.LIB_PATH)           # loads without a GPU
     for name in declared:
         assert hasattr(lib, name), name
