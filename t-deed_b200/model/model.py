@@ -69,8 +69,25 @@ class TDEEDModel(BaseRGBModel):
                 self._pred_displ = FCLayers(self._feat_dim, 1)
 
             self.croping = args.crop_dim
+            # per-clip training augmentation of the reference (model/model.py:77-84); torchvision ops on device floats.
+            # Assign nn.Identity() to disable (parity tests do).
+            try:
+                import torchvision.transforms as T
+                self.augmentation = T.Compose([
+                    T.RandomApply([T.ColorJitter(hue=0.2)], p=0.25),
+                    T.RandomApply([T.ColorJitter(saturation=(0.7, 1.2))], p=0.25),
+                    T.RandomApply([T.ColorJitter(brightness=(0.7, 1.2))], p=0.25),
+                    T.RandomApply([T.ColorJitter(contrast=(0.7, 1.2))], p=0.25),
+                    T.RandomApply([T.GaussianBlur(5)], p=0.25),
+                    T.RandomHorizontalFlip(),
+                ])
+            except ImportError:      # pragma: no cover
+                self.augmentation = nn.Identity()
             self._engines = {}
             self._engine_versions = {}
+            self._flat = None
+            self._train_engines = {}
+            self._train_calls = 0
 
         # ---- engine management -------------------------------------------------------------
         def engine_config(self):
@@ -87,7 +104,84 @@ class TDEEDModel(BaseRGBModel):
             if tr is None:
                 tr = list(self.parameters()) + list(self.buffers())
                 self.__dict__['_tracked'] = tr
-            return sum(t._version for t in tr) + (1 << 40) * int(self._double_head)
+            flat_ver = self._flat.version if self.__dict__.get('_flat') is not None else 0
+            return sum(t._version for t in tr) + (1 << 40) * int(self._double_head) + (1 << 20) * flat_ver
+
+        # ---- training ------------------------------------------------------------------------
+        def flat_params(self):
+            """Parameters re-homed into one flat fp32 buffer (+ flat gradient / bf16 shadow), see tdeed_b200/optim.py."""
+            from tdeed_b200.optim import FlatParams
+            if self._flat is None or not self._flat.valid():
+                self._flat = FlatParams(self)
+                self._train_engines.clear()
+            return self._flat
+
+        def train_engine(self, precision):
+            from tdeed_b200.train_engine import TrainEngine
+            flat = self.flat_params()
+            eng = self._train_engines.get(precision)
+            if eng is None:
+                adt = torch.bfloat16 if precision == 'bf16' else torch.float32
+                buffers = dict(self.named_buffers())
+                eng = TrainEngine(self.engine_config(), flat.P, buffers, flat.G, act_dtype=adt,
+                                  shadow=flat.S if precision == 'bf16' else None)
+                self._train_engines[precision] = eng
+            return eng
+
+        def train_step(self, frame, label, labelD=None, fg_weight=5, grad_scale=1.0, accumulate=False, precision='bf16',
+                       dropout_p=None):
+            """Forward (train mode) + loss + backward on the sm_100a kernels (model/model.py:262-324 of the reference).
+            frame: (B,T,3,H,W) uint8 | float valued 0..255, already mixed up.  label: int64 (B*T) | float (B*T, K).
+            Gradients of grad_scale * loss land in p.grad (added to the existing ones when accumulate).  Returns the
+            loss as a device tensor [3] = (total, CE, MSE) — no host sync."""
+            from tdeed_b200 import train_ops as TO
+            flat = self.flat_params()
+            eng = self.train_engine(precision)
+            if precision == 'bf16':
+                flat.refresh_shadow()
+            b, t, _, H, W = frame.shape
+            # crop: same random window for the whole batch (RandomCrop on the flattened batch, model/model.py:115)
+            if self.croping is not None:
+                ch = cw = self.croping
+                cy = int(torch.randint(0, H - ch + 1, (1,)).item()) if H > ch else 0
+                cx = int(torch.randint(0, W - cw + 1, (1,)).item()) if W > cw else 0
+            else:
+                cy, cx, ch, cw = 0, 0, H, W
+            unit = False
+            if not isinstance(self.augmentation, nn.Identity):
+                x = frame[..., cy:cy + ch, cx:cx + cw].float() / 255.
+                for i in range(b):
+                    x[i] = self.augmentation(x[i])
+                frame, unit, cy, cx = x.contiguous(), True, 0, 0
+            elif frame.dtype not in (torch.uint8, torch.float32):
+                frame = frame.float()
+            frame = frame.contiguous()
+            self._train_calls += 1
+            if dropout_p is None:            # nn.Dropout() of the FC heads (model/modules.py:366-376): p = 0.5 in train mode
+                dropout_p = float(self._pred_fine.dropout.p) if self.training else 0.0
+            hard = label if not label.dtype.is_floating_point else None
+            soft = label.float().contiguous() if label.dtype.is_floating_point else None
+            tgt = flat.G if not accumulate and grad_scale == 1.0 else None
+            if tgt is None:                     # accumulate / scale: write into a scratch buffer, then axpy
+                scratch = torch.zeros_like(flat.g)
+                eng.G = {n: scratch[o:o + cnt].view(flat.P[n].shape) for n, (o, cnt) in flat.offsets.items()}
+            else:
+                eng.G = flat.G
+            logits, displ = eng.forward(frame, (cy, cx, ch, cw), unit_input=unit,
+                                        dropout_p=dropout_p, seed=self._train_calls)
+            loss = eng.loss(logits, displ, hard.reshape(-1).contiguous() if hard is not None else None, soft,
+                            labelD.reshape(-1).float().contiguous() if (labelD is not None and displ is not None) else None,
+                            fg_weight=fg_weight)
+            eng.backward()
+            if tgt is None:
+                if accumulate:
+                    TO.axpy_(scratch, grad_scale, flat.g)
+                else:
+                    flat.g.zero_()
+                    TO.axpy_(scratch, grad_scale, flat.g)
+            flat.attach_grads()
+            self._last_train = (logits.view(b, t, -1), displ.view(b, t) if displ is not None else None)
+            return loss
 
         def engine(self, precision):
             """InferenceEngine for the current weights ('bf16' | 'fp32'); re-prepared when parameters changed."""
@@ -110,9 +204,10 @@ class TDEEDModel(BaseRGBModel):
             """x: (B, T, 3, H, W) valued 0..255 (uint8 or float).  Returns what the reference returns:
             ({'im_feat': logits, 'displ_feat': displ}, y) when radi_displacement > 0 else (logits, y)."""
             if not inference:
-                raise NotImplementedError(
-                    'tdeed_b200: the training forward/backward path (sm_100a backward kernels) is not built yet; '
-                    'inference (inference=True / predict / epoch(optimizer=None)) is')
+                raise RuntimeError(
+                    'tdeed_b200: the train-mode forward has no torch.autograd graph — the backward pass is hand-written '
+                    'sm_100a kernels.  Use Impl.train_step(frame, label, labelD) (what TDEEDModel.epoch(optimizer=...) '
+                    'calls): it runs forward + loss + backward and leaves the gradients in p.grad')
             precision = 'bf16' if torch.is_autocast_enabled() else 'fp32'
             eng = self.engine(precision)
             if x.dtype not in (torch.uint8, torch.float32):
@@ -136,6 +231,21 @@ class TDEEDModel(BaseRGBModel):
             print('  CNN features:', sum(p.numel() for p in self._features.parameters()))
             print('  Temporal:', sum(p.numel() for p in self._temp_fine.parameters()))
             print('  Head:', sum(p.numel() for p in self._pred_fine.parameters()))
+
+    train_precision = 'bf16'     # 'fp32' runs the exact CUDA-core kernels (parity mode)
+
+    def _sync_gradients(self, optimizer):
+        """Data-parallel training (one process per GPU): NCCL all-reduce of the flat gradient buffer over NVLink; the mean
+        is folded into the fused AdamW kernel (grad_scale = 1 / world).  No-op for a single process."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return
+        flat = self._model.flat_params()
+        dist.all_reduce(flat.g)
+        if hasattr(optimizer, 'grad_scale'):
+            optimizer.grad_scale = 1.0 / dist.get_world_size()
+        else:
+            flat.g.mul_(1.0 / dist.get_world_size())
 
     def __init__(self, device='cuda', args=None):
         self.device = device
@@ -203,6 +313,33 @@ class TDEEDModel(BaseRGBModel):
                     map_labels.append(labels_aux.cpu())
 
                 label = label.flatten() if len(label.shape) == 2 else label.view(-1, label.shape[-1])
+
+                if optimizer is not None:
+                    # training: forward (train mode) + loss + backward are sm_100a kernels (tdeed_b200/train_engine.py);
+                    # the reference's `step(optimizer, scaler, loss / acc_grad_iter, ...)` (model/modules.py:388-401)
+                    # becomes gradient accumulation into p.grad + optimizer.step()
+                    if self._model._double_head:
+                        raise NotImplementedError('tdeed_b200: joint-dataset (double head) training is not built yet')
+                    first = batch_idx % acc_grad_iter == 0
+                    loss_dev = self._model.train_step(frame, label, labelD if 'labelD' in batch.keys() else None,
+                                                      fg_weight=fg_weight, grad_scale=1.0 / acc_grad_iter,
+                                                      accumulate=not first, precision=self.train_precision)
+                    if valMAP:
+                        logits, displ = self._model._last_train
+                        map_preds.append((process_prediction(logits, displ) if displ is not None
+                                          else torch.softmax(logits, dim=2)).cpu())
+                    if (batch_idx + 1) % acc_grad_iter == 0:
+                        self._sync_gradients(optimizer)
+                        if scaler is None:
+                            optimizer.step()
+                        else:
+                            scaler.step(optimizer)
+                            scaler.update()
+                        if lr_scheduler is not None:
+                            lr_scheduler.step()
+                        optimizer.zero_grad()
+                    epoch_loss += float(loss_dev[0])
+                    continue
 
                 with torch.autocast('cuda', dtype=torch.bfloat16):
                     pred, y = self._model(frame, y=label, inference=inference)

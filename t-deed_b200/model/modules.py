@@ -51,7 +51,11 @@ class BaseRGBModel(ABCModel):
     def get_optimizer(self, opt_args):
         # bf16 autocast needs no loss scaling: a disabled GradScaler keeps `step()` call-compatible
         # with the reference (modules.py:37-39 returns GradScaler() iff device == 'cuda').
-        return torch.optim.AdamW(self._get_params(), **opt_args), \
+        # The optimizer is a real torch.optim.Optimizer (schedulers / state_dict work) whose step is ONE fused
+        # tdeed_adamw_step launch over the flat parameter buffer (tdeed_b200/optim.py).
+        from tdeed_b200.optim import FusedAdamW
+        flat = self._model.flat_params() if hasattr(self._model, 'flat_params') else None
+        return FusedAdamW(self._get_params(), flat=flat, **opt_args), \
             torch.amp.GradScaler('cuda', enabled=False) if self.device == 'cuda' else None
 
     """ Assume there is a self._model """

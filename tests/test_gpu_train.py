@@ -1,0 +1,177 @@
+"""GPU parity of the whole training step (forward in train mode + loss + hand-written backward + BN statistics + AdamW)
+through the reference's own entry points (TDEEDModel.epoch / get_optimizer) against
+
+  * tests/golden/train_*.npz — loss, gradients and BN buffers produced by the UNMODIFIED reference (CPU fp32), and
+  * the oracle (oracle/train_oracle.py) evaluated on the GPU box in float64, which gives the noise floor: the reference's own
+    fp32 gradients differ from the float64 ones by 1-3e-2 relative-to-max on these nets (a ReLU / max-pool routing flip
+    moves whole rows of the gradient), so the end-to-end bound on the fp32 kernels is  E <= 4 * max_t E_ref(t) + 1e-4
+    per tensor, while loss / logits / BN statistics are held to 1e-4 and every kernel to 2e-4 in test_gpu_train_ops.py.
+"""
+import os
+import random
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import tdeed_oracle as O
+import train_oracle as TO
+from gen_golden_train import TRAIN_CASES
+from test_oracle_golden import train_case_from_golden, rel_err
+
+
+def _args(cfg):
+    return Namespace(modality='rgb', temporal_arch='ed_sgp_mixer', radi_displacement=cfg.radi_displacement,
+                     feature_arch=cfg.feature_arch, clip_len=cfg.clip_len, n_layers=cfg.n_layers, sgp_ks=cfg.sgp_ks,
+                     sgp_r=cfg.sgp_r, num_classes=cfg.num_classes, crop_dim=cfg.crop_dim)
+
+
+def _model(cfg, sd):
+    import contextlib
+    import io
+    from model.model import TDEEDModel
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = TDEEDModel(device='cuda', args=_args(cfg))
+    m.load(sd)
+    m._model.augmentation = torch.nn.Identity()
+    for mod in m._model.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    return m
+
+
+def _oracle_grads(sd, cfg, frames, label, labelD, dtype):
+    dev = 'cuda'
+    s = {k: (v.to(dev).to(dtype) if v.dtype.is_floating_point else v.to(dev)) for k, v in sd.items()}
+    lab = label.to(dev)
+    if lab.dtype.is_floating_point:
+        lab = lab.to(dtype)
+    loss, logits, displ, grads, after = TO.train_forward_backward(
+        s, cfg, frames.to(dev).to(dtype), lab, labelD.to(dev).to(dtype) if labelD is not None else None)
+    return loss, logits, grads, after
+
+
+@pytest.mark.parametrize('name', sorted(TRAIN_CASES))
+def test_train_step_fp32_matches_reference(name, golden_dir):
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg, sd, frames, label, labelD, g = train_case_from_golden(name, golden_dir)
+    m = _model(cfg, sd)
+    m._model.train()
+    lab = label.cuda()
+    lab = lab.reshape(-1) if lab.dim() == 2 else lab.reshape(-1, lab.shape[-1])
+    loss = m._model.train_step(frames.cuda(), lab, labelD.cuda() if labelD is not None else None, fg_weight=5, precision='fp32')
+    torch.cuda.synchronize()
+    # loss and BN buffers: tight
+    assert abs(float(loss[0]) - float(g['loss'])) < 1e-4 * max(1.0, abs(float(g['loss'])))
+    after = m.state_dict()
+    for k in g.files:
+        if k.startswith('after/'):
+            np.testing.assert_allclose(after[k[6:]].cpu().numpy(), g[k], rtol=2e-4, atol=2e-5)
+    # gradients: noise floor from the float64 oracle
+    _, logits64, g64, _ = _oracle_grads(sd, cfg, frames, label, labelD, torch.float64)
+    _, _, g32, _ = _oracle_grads(sd, cfg, frames, label, labelD, torch.float32)
+    mine = {n: p.grad for n, p in m._model.named_parameters()}
+    assert rel_err(m._model._last_train[0].double().cpu().numpy(), logits64.cpu().numpy()) < 1e-4
+    e_ref = {n: rel_err(g32[n].double().cpu().numpy(), g64[n].cpu().numpy()) for n in g64 if g64[n].numel() >= 16}
+    e_mine = {n: rel_err(mine[n].double().cpu().numpy(), g64[n].cpu().numpy()) for n in g64 if g64[n].numel() >= 16}
+    floor = max(e_ref.values())
+    worst = max(e_mine, key=e_mine.get)
+    print('%s: fp32 reference-vs-f64 floor %.2e (median %.2e); kernels-vs-f64 worst %.2e (%s), median %.2e'
+          % (name, floor, float(np.median(list(e_ref.values()))), e_mine[worst], worst, float(np.median(list(e_mine.values())))))
+    assert e_mine[worst] <= 4 * floor + 1e-4, (worst, e_mine[worst], floor)
+    assert float(np.median(list(e_mine.values()))) <= 3 * float(np.median(list(e_ref.values()))) + 1e-5
+    # and directly against the reference's own gradients (golden): norms of every tensor within the same bound
+    names = [str(n) for n in g['grad_names']]
+    for n, (s_, sa, l2) in zip(names, g['grad_stats']):
+        a = mine[n].double().cpu().numpy()
+        if a.size >= 16:
+            assert abs(np.sqrt((a * a).sum()) - l2) <= (4 * floor + 1e-4) * max(l2, 1e-6), (n, 'l2')
+
+
+def _cosines(grads, g64):
+    cos = {}
+    for n, b in g64.items():
+        a, b = grads[n].double().reshape(-1), b.reshape(-1)
+        if a.numel() >= 64:
+            cos[n] = float((a @ b) / (a.norm() * b.norm() + 1e-30))
+    return cos
+
+
+def test_train_step_bf16_vs_reference_autocast(golden_dir):
+    """bf16 storage + tensor-core GEMMs.  Stated tolerance (relative to the reference's own autocast error):
+    the gradient direction of every tensor (cosine against the float64 oracle) must be at least as good as what the
+    reference modules give under torch.autocast(bfloat16) on the same inputs, minus 0.1 / 0.05 (min / median) slack; the
+    loss within 2x the autocast run's own loss error (and 6 %)."""
+    cfg, sd, frames, label, labelD, g = train_case_from_golden('rny002_gsf_displ', golden_dir)
+    m = _model(cfg, sd)
+    m._model.train()
+    lab = label.cuda().reshape(-1)
+    loss = m._model.train_step(frames.cuda(), lab, labelD.cuda(), fg_weight=5, precision='bf16')
+    mine = {n: p.grad for n, p in m._model.named_parameters()}
+    loss64, _, g64, _ = _oracle_grads(sd, cfg, frames, label, labelD, torch.float64)
+    with torch.autocast('cuda', dtype=torch.bfloat16):
+        loss_ac, _, g_ac, _ = _oracle_grads(sd, cfg, frames, label, labelD, torch.float32)
+    c_mine, c_ref = _cosines(mine, g64), _cosines(g_ac, g64)
+    print('loss: kernels bf16 %.4f | autocast reference %.4f | f64 %.4f' % (float(loss[0]), loss_ac, loss64))
+    print('gradient cosine vs f64: kernels min %.3f median %.3f | autocast reference min %.3f median %.3f'
+          % (min(c_mine.values()), float(np.median(list(c_mine.values()))), min(c_ref.values()), float(np.median(list(c_ref.values())))))
+    assert abs(float(loss[0]) - loss64) < max(2 * abs(loss_ac - loss64), 6e-2 * abs(loss64))
+    assert float(np.median(list(c_mine.values()))) >= float(np.median(list(c_ref.values()))) - 0.05
+    assert min(c_mine.values()) >= min(c_ref.values()) - 0.1
+
+
+def test_epoch_mixup_glue_matches_reference_loss(golden_dir):
+    """TDEEDModel.epoch(optimizer=...) end to end: mixup of frames / labels (model/model.py:228-254) + train_step."""
+    name = 'rny002_gsf_mixup'
+    kw, _, wseed, iseed, _ = TRAIN_CASES[name]
+    g = np.load(os.path.join(golden_dir, 'train_%s.npz' % name))
+    cfg = O.Config(**kw)
+    m = _model(cfg, O.random_state(cfg, wseed))
+    m.train_precision = 'fp32'
+    batch = {k[6:]: torch.from_numpy(g[k]) for k in g.files if k.startswith('batch_')}
+
+    class Recording:
+        def zero_grad(self):
+            pass
+
+        def step(self):
+            pass
+
+    random.seed(iseed)
+    loss = m.epoch([batch], optimizer=Recording(), scaler=None, fg_weight=5)
+    assert abs(loss - float(g['loss'])) < 1e-4 * abs(float(g['loss']))
+
+
+def test_epoch_trains_with_fused_adamw_and_scheduler():
+    cfg = O.Config(feature_arch='rny002_gsf', clip_len=8, n_layers=2, sgp_ks=5, sgp_r=4, num_classes=4, radi_displacement=2,
+                   crop_dim=64)
+    m = _model(cfg, O.random_state(cfg, 5))
+    keys_before = list(m.state_dict().keys())
+    gen = torch.Generator().manual_seed(0)
+    batch = {'frame': torch.randint(0, 256, (2, 8, 3, 64, 80), generator=gen, dtype=torch.uint8),
+             'label': torch.randint(0, 5, (2, 8), generator=gen), 'labelD': torch.randint(-2, 3, (2, 8), generator=gen)}
+    opt, scaler = m.get_optimizer({'lr': 3e-4})
+    assert isinstance(opt, torch.optim.Optimizer)
+    sched = torch.optim.lr_scheduler.ChainedScheduler([torch.optim.lr_scheduler.LinearLR(opt, start_factor=0.1, total_iters=3),
+                                                       torch.optim.lr_scheduler.CosineAnnealingLR(opt, 40)])
+    w0 = m.state_dict()['_temp_fine._sgp.0.mlp.0.weight'].clone()
+    losses = [m.epoch([batch, batch], optimizer=opt, scaler=scaler, lr_scheduler=sched, acc_grad_iter=1) for _ in range(12)]
+    print('losses', ['%.3f' % v for v in losses])
+    assert all(np.isfinite(losses)) and min(losses[-3:]) < 0.8 * losses[0]
+    assert list(m.state_dict().keys()) == keys_before
+    assert not torch.equal(m.state_dict()['_temp_fine._sgp.0.mlp.0.weight'], w0)
+    assert int(m.state_dict()['_features.stem.bn.num_batches_tracked']) == 24
+    # gradient accumulation == one step on the concatenated batch statistics-wise is not identical (BN), just check it runs
+    l2 = m.epoch([batch, batch], optimizer=opt, scaler=scaler, acc_grad_iter=2)
+    assert np.isfinite(l2)
+    # inference sees the trained weights (engine cache invalidated by the fused optimizer)
+    cls, probs = m.predict(batch['frame'][:1], use_amp=False)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    ocls, oprobs = O.predict(sd, cfg, batch['frame'][:1])
+    assert np.abs(probs - oprobs).max() < 1e-3
+    # evaluation epoch still works after training
+    assert np.isfinite(m.epoch([batch], optimizer=None))

@@ -204,6 +204,15 @@ def test_se_train(c, rd, hw):
     assert rel(nchw(dx), ps[0].grad) < 1e-4
     assert rel(d_w1, ps[1].grad) < 1e-4 and rel(d_b1, ps[2].grad) < 1e-4
     assert rel(d_w2, ps[3].grad) < 1e-4 and rel(d_b2, ps[4].grad) < 1e-4
+    # bf16 storage
+    xb, dub = nhwc(x).bfloat16(), nhwc(du).bfloat16()
+    ps2 = [t.clone().requires_grad_(True) for t in (nchw(xb.float()), w1, b1, w2, b2)]
+    s2 = torch.sigmoid(F.linear(F.relu(F.linear(ps2[0].mean(dim=(2, 3)), ps2[1], ps2[2])), ps2[3], ps2[4]))
+    (ps2[0] * s2[:, :, None, None]).backward(nchw(dub.float()))
+    ub, wsb = T().se_train_fwd(xb, w1, b1, w2t, b2)
+    dxb, d_w1b, _, d_w2b, _ = T().se_bwd(xb, dub, w1, b1, w2t, wsb)
+    assert rel(nchw(dxb.float()), ps2[0].grad) < 1e-2
+    assert rel(d_w1b, ps2[1].grad) < 1e-3 and rel(d_w2b, ps2[3].grad) < 1e-3
 
 
 def test_pool_posenc_bwd():
@@ -261,6 +270,19 @@ def test_gate_shift_train_fwd_bwd(mode, c, fold, h, w, clips, clip_len):
         for j in (0, 1):
             assert rel(dcc[j, :18], sdr['gs.channel_conv%d.weight' % (j + 1)].grad.reshape(-1)) < 2e-4
             assert rel(dcc[j, 18:], sdr['gs.channel_conv%d.bias' % (j + 1)].grad) < 2e-4
+    # bf16 storage of x / d_cat: same kernels, inputs rounded -> compare against autograd on the rounded inputs
+    xb, dcb, adb = nhwc(x).bfloat16(), nhwc(dcat).bfloat16(), nhwc(add).bfloat16()
+    xr2 = nchw(xb.float()).requires_grad_(True)
+    sdr2 = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    cat2 = torch.cat([O.gate_shift(xr2[:, :fold], sdr2, 'gs', clip_len, mode, train=True), xr2[:, fold:]], dim=1)
+    cat2.backward(nchw(dcb.float()))
+    stats_b = T().bn_stats(xb.view(-1, c), fold, sd['gs.bn.weight'], sd['gs.bn.bias'])
+    catb, wsb = T().gsf_cat_fwd(xb, clips, clip_len, fold, m, stats_b, w3, sd['gs.conv3D.bias'], cc_w, cc_b)
+    assert rel(nchw(catb.view(n, h, w, c).float()), cat2) < 1e-2
+    dxb, dw3b, db3b, dccb, dgamb, dbetb = T().gsf_bwd(xb, dcb, adb, clips, clip_len, fold, m, stats_b, w3, cc_w, wsb)
+    assert rel(nchw(dxb.float()), xr2.grad + nchw(adb.float())) < 2e-2
+    assert rel(dw3b, sdr2['gs.conv3D.weight'].grad.reshape(-1)) < 2e-3
+    assert rel(dgamb, sdr2['gs.bn.weight'].grad) < 2e-3
 
 
 def _branch_sd(C, ks, up, g, sfx=''):
