@@ -161,8 +161,15 @@ def main():
     ap.add_argument('--clips-per-batch', type=int, default=39)
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='infer', choices=['infer', 'train'],
+                    help="infer: BASELINE configs[1] (headline); train: configs[2] FineGym_big training step (bench_train.py)")
+    ap.add_argument('--no-aug', action='store_true', help='train workload: disable the per-clip torchvision augmentation')
+    ap.add_argument('--no-train', action='store_true', help="infer workload: skip the short 'train_step' side measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
+    if args.workload == 'train':
+        import bench_train
+        return bench_train.run_train_reference(args) if args.impl == 'reference' else bench_train.run_train(args)
     if args.impl == 'reference':
         return run_reference(args)
 
@@ -349,6 +356,23 @@ def main():
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
             'kernel_families_ms_per_step': {k_: round(v['ms'], 3) for k_, v in sorted(families.items(), key=lambda kv: -kv[1]['ms'])},
         }
+    # side measurement: the training step (BASELINE configs[2]) at this N, a few steps — reported under 'train_step'
+    train = None
+    if not args.no_train:
+        del video, host_batch, uploader
+        eng._graphs.clear()
+        torch.cuda.empty_cache()
+        try:
+            import bench_train
+            targs = Namespace(steps=3, warmup=3, precision=args.precision, no_aug=False, gpus=args.gpus)
+            tr = bench_train.run_train(targs, quiet=True)
+            if tr is not None:
+                train = {k_: tr[k_] for k_ in ('metric', 'value', 'unit', 'ms_per_step', 'config', 'e2e', 'gpu_launches', 'roofline',
+                                               'kernel_families_ms_per_step')}
+        except Exception as exc:      # the headline line must survive a failure of the side measurement
+            train = {'error': repr(exc)[:300]}
+    if rank == 0:
+        out['train_step'] = train
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

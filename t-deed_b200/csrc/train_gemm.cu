@@ -5,6 +5,7 @@
 //   tdeed_strided_add  dst[f, s*oy, s*ox, :] += src[f, oy, ox, :]   (data gradient of a stride-s 1x1 conv)
 // CUDA-core fp32 accumulation; split over the rows with per-split partial tiles that are summed in a fixed order
 // (deterministic, no atomics).
+#include <cstdlib>
 #include "common.cuh"
 
 namespace tdeed {
@@ -147,10 +148,28 @@ static int run_tn(const void* A, long long lda, const void* B, long long ldb, lo
   return check_launch("tdeed_gemm_tn(reduce)");
 }
 
+// tcgen05 backend (train_gemm_tc.cu): bf16 x bf16, no gather
+bool gemm_tn_tc_applicable(int a_dtype, int b_dtype, const void* A, long long lda, const void* B, long long ldb, long long R,
+                           int gather_stride);
+long long gemm_tn_tc_workspace_floats(long long R, int m, int n);
+int gemm_tn_tc_launch(const void* A, long long lda, const void* B, long long ldb, long long R, int m, int n, float alpha,
+                      float* out, long long ldo, float* ws, cudaStream_t st);
+
+static bool tn_force_simt() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TDEED_GEMM_TN_SIMT");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 }  // namespace tdeed
 
 extern "C" long long tdeed_gemm_tn_workspace_floats(long long R, int m, int n) {
-  return (long long)tdeed::tn_splits(R, m, n) * m * n;
+  const long long a = (long long)tdeed::tn_splits(R, m, n) * m * n;
+  const long long b = tdeed::gemm_tn_tc_workspace_floats(R, m, n);
+  return a > b ? a : b;
 }
 
 extern "C" int tdeed_gemm_tn(int a_dtype, const void* A, long long lda, int b_dtype, const void* B, long long ldb, long long R,
@@ -161,6 +180,8 @@ extern "C" int tdeed_gemm_tn(int a_dtype, const void* A, long long lda, int b_dt
   TDEED_REQUIRE(R > 0 && m > 0 && n > 0 && lda >= m && ldb >= n && ldo >= n && gather_stride >= 1, TDEED_ERR_SHAPE,
                 "tdeed_gemm_tn: bad shape R=%lld m=%d n=%d", R, m, n);
   cudaStream_t st = (cudaStream_t)stream;
+  if (!tn_force_simt() && gemm_tn_tc_applicable(a_dtype, b_dtype, A, lda, B, ldb, R, gather_stride))
+    return gemm_tn_tc_launch(A, lda, B, ldb, R, m, n, alpha, out, ldo, workspace, st);
 #define TN_CASE(DA, TA, DB, TB) \
   if (a_dtype == DA && b_dtype == DB) \
     return run_tn<TA, TB>(A, lda, B, ldb, R, m, n, gather_stride, gather_h, gather_w, out, ldo, alpha, workspace, st);

@@ -116,6 +116,22 @@ def test_gemm_tn(dt_a, dt_b, R, m, n):
     assert rel(out, ref) < 2e-5
 
 
+@pytest.mark.parametrize('R,m,n', [(4096, 64, 64), (20000, 320, 320), (3000, 768, 3072), (777, 152, 88), (100000, 24, 32),
+                                   (6400, 3072, 768), (1500, 368, 2208)])
+def test_gemm_tn_tcgen05(R, m, n):
+    """bf16 x bf16 with 8-aligned leading dims takes the tcgen05 MN-major kernel (train_gemm_tc.cu)."""
+    g = torch.Generator(device=DEV).manual_seed(R + m + n)
+    a = torch.randn((R, m), device=DEV, generator=g).bfloat16()
+    b = torch.randn((R, n), device=DEV, generator=g).bfloat16()
+    out = T().gemm_tn(a, b, m, n, R)
+    ref = a.double().t() @ b.double()
+    assert rel(out, ref) < 1e-4
+    # column slices of wider tensors (leading dim > columns), scaled
+    wide_a = torch.randn((R, m + 16), device=DEV, generator=g).bfloat16()
+    out2 = T().gemm_tn(wide_a[:, 8:], b, m, n, R, alpha=0.5)
+    assert rel(out2, 0.5 * (wide_a[:, 8:8 + m].double().t() @ b.double())) < 1e-4
+
+
 def test_gemm_tn_gather_colsum_strided_add():
     g = torch.Generator(device=DEV).manual_seed(3)
     nfr, h, w, cin, cout = 6, 9, 11, 24, 56
