@@ -54,6 +54,14 @@ int tdeed_conv3x3g_raw_fwd(int dtype, const void* in, int n, int h, int w, int c
                            const float* weight, void* out, void* stream);
 int tdeed_conv3x3g_bwd_data(int dtype, const void* dy, int n, int h, int w, int c, int group_width, int stride,
                             const float* weight, void* dx, void* stream);
+/* tcgen05 variants for bf16 activations: tdeed_conv3_weight_image turns the fp32 weights into the UMMA B tiles that
+ * tdeed_conv3x3g_tc_fwd (tdeed_b200.h 3b) consumes — tdeed_conv3_weight_image_elems(c) bf16 elements; with
+ * transpose_flip = 1 the image is that of the transposed, 180-degree-rotated kernel, so that tdeed_conv3x3g_tc_raw_fwd on
+ * dy (stride 1) is the data gradient of the stride-1 convolution. */
+long long tdeed_conv3_weight_image_elems(int c);
+int tdeed_conv3_weight_image(const float* weight, int c, int group_width, int transpose_flip, void* wimg, void* stream);
+int tdeed_conv3x3g_tc_raw_fwd(const void* in, int n, int h, int w, int c, int stride, const void* wimg, void* out,
+                              void* stream);
 long long tdeed_conv3x3g_bwd_weight_workspace_floats(int n, int h, int w, int c, int group_width, int stride);
 int tdeed_conv3x3g_bwd_weight(int dtype, const void* x, const void* dy, int n, int h, int w, int c, int group_width,
                               int stride, float* dw, float* workspace, void* stream);

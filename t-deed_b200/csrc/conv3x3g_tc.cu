@@ -24,7 +24,7 @@ struct C3TParams {
   __nv_bfloat16* out;
   const float* bias;
   const uint8_t* wimg;       // [pairs_total][9][512 B] canonical UMMA B tiles
-  int n, H, W, C, Ho, Wo, stride;
+  int n, H, W, C, Ho, Wo, stride, relu;
   int GH, GW, G;             // padded position grid per frame
   long long total_pos;
   int ntiles;
@@ -112,7 +112,7 @@ conv3x3g_tc_kernel(const C3TParams p) {
     reinterpret_cast<uint4*>(sW)[i] = reinterpret_cast<const uint4*>(p.wimg + (size_t)pair0 * 9 * 512)[i];
   for (int i = tid; i < np * 16; i += C3T_THREADS) {
     const int ch = pair0 * 16 + i;
-    s_bias[i] = ch < p.C ? p.bias[ch] : 0.f;
+    s_bias[i] = (p.bias && ch < p.C) ? p.bias[ch] : 0.f;
   }
   // chunk planes beyond the tensor's channels are never staged: zero them once in both buffers
   for (int i = tid; i < 2 * p.nplanes * (nch - nch_real) * p.npos_pad; i += C3T_THREADS) {
@@ -241,7 +241,10 @@ conv3x3g_tc_kernel(const C3TParams p) {
           if (pair0 * 16 + pp * 16 + 8 * hh >= p.C) continue;
           float v[8];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) v[q] = fmaxf(__uint_as_float(v32[8 * hh + q]) + s_bias[pp * 16 + 8 * hh + q], 0.f);
+          for (int q = 0; q < 8; ++q) {
+            const float t = __uint_as_float(v32[8 * hh + q]) + s_bias[pp * 16 + 8 * hh + q];
+            v[q] = p.relu ? fmaxf(t, 0.f) : t;
+          }
           store8(p.out + obase + pp * 16 + 8 * hh, v);
         }
       }
@@ -260,15 +263,15 @@ conv3x3g_tc_kernel(const C3TParams p) {
 
 }  // namespace tdeed
 
-extern "C" int tdeed_conv3x3g_tc_fwd(const void* in, int n, int h, int w, int c, int stride, const void* wimg,
-                                     const float* bias, void* out, void* stream) {
+static int conv3x3g_tc_run(const void* in, int n, int h, int w, int c, int stride, const void* wimg, const float* bias, int relu,
+                           void* out, void* stream) {
   using namespace tdeed;
-  TDEED_REQUIRE(in && wimg && bias && out, TDEED_ERR_SHAPE, "tdeed_conv3x3g_tc_fwd: null pointer");
+  TDEED_REQUIRE(in && wimg && out, TDEED_ERR_SHAPE, "tdeed_conv3x3g_tc_fwd: null pointer");
   TDEED_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && (stride == 1 || stride == 2), TDEED_ERR_SHAPE,
                 "tdeed_conv3x3g_tc_fwd: bad shape n=%d %dx%dx%d stride=%d", n, h, w, c, stride);
   C3TParams p{};
   p.in = (const __nv_bfloat16*)in; p.out = (__nv_bfloat16*)out; p.bias = bias; p.wimg = (const uint8_t*)wimg;
-  p.n = n; p.H = h; p.W = w; p.C = c; p.stride = stride;
+  p.n = n; p.H = h; p.W = w; p.C = c; p.stride = stride; p.relu = relu;
   p.Ho = (h + stride - 1) / stride; p.Wo = (w + stride - 1) / stride;
   if (stride == 1) {
     p.GH = h + 2; p.GW = w + 2; p.nplanes = 1;
@@ -322,4 +325,49 @@ extern "C" int tdeed_conv3x3g_tc_fwd(const void* in, int n, int h, int w, int c,
   if (gx > p.ntiles) gx = p.ntiles;
   conv3x3g_tc_kernel<<<dim3(gx, nblk), C3T_THREADS, smem, (cudaStream_t)stream>>>(p);
   return check_launch("tdeed_conv3x3g_tc_fwd");
+}
+
+extern "C" int tdeed_conv3x3g_tc_fwd(const void* in, int n, int h, int w, int c, int stride, const void* wimg,
+                                     const float* bias, void* out, void* stream) {
+  TDEED_REQUIRE(bias, TDEED_ERR_SHAPE, "tdeed_conv3x3g_tc_fwd: null pointer");
+  return conv3x3g_tc_run(in, n, h, w, c, stride, wimg, bias, 1, out, stream);
+}
+
+// training: raw convolution (no bias, no ReLU).  With a weight image built with transpose_flip = 1 (stride 1 only) this is
+// also the DATA GRADIENT of the stride-1 grouped conv: dx = conv(dy, W^T flipped).
+extern "C" int tdeed_conv3x3g_tc_raw_fwd(const void* in, int n, int h, int w, int c, int stride, const void* wimg, void* out,
+                                         void* stream) {
+  return conv3x3g_tc_run(in, n, h, w, c, stride, wimg, nullptr, 0, out, stream);
+}
+
+namespace tdeed {
+// fp32 weights [C][gw][3][3] -> bf16 UMMA B tiles [ceil(C/16)][9 taps][16 out][16 in], each tile in the canonical K-major
+// no-swizzle layout [n/8][k/8][n%8][k%8]; transpose_flip: tile(tap)[ci][co] = W[co][ci][8 - tap] (data-gradient kernel)
+__global__ void conv3_weight_image_kernel(const float* __restrict__ w, int C, int gw, int transpose_flip, __nv_bfloat16* __restrict__ img,
+                                          int total) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int k = idx & 15, nrow = (idx >> 4) & 15, tap = (idx >> 8) % 9, pair = idx / (256 * 9);
+  // tile element (n = output channel 16*pair + nrow, k = input channel 16*pair + k)
+  const int cn = pair * 16 + nrow, ck = pair * 16 + k;
+  float v = 0.f;
+  if (cn < C && ck < C && cn / gw == ck / gw) {
+    if (!transpose_flip) v = w[((size_t)cn * gw + (ck % gw)) * 9 + tap];
+    else v = w[((size_t)ck * gw + (cn % gw)) * 9 + (8 - tap)];
+  }
+  const int off = ((pair * 9 + tap) * 256) + ((nrow >> 3) * 2 + (k >> 3)) * 64 + (nrow & 7) * 8 + (k & 7);
+  img[off] = __float2bfloat16_rn(v);
+}
+}  // namespace tdeed
+
+extern "C" long long tdeed_conv3_weight_image_elems(int c) { return (long long)((c + 15) / 16) * 9 * 256; }
+
+extern "C" int tdeed_conv3_weight_image(const float* weight, int c, int group_width, int transpose_flip, void* wimg, void* stream) {
+  using namespace tdeed;
+  TDEED_REQUIRE(weight && wimg && c > 0 && (group_width == 8 || group_width == 16) && c % group_width == 0, TDEED_ERR_SHAPE,
+                "tdeed_conv3_weight_image: bad arguments");
+  const int total = ((c + 15) / 16) * 9 * 256;
+  conv3_weight_image_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(weight, c, group_width, transpose_flip,
+                                                                                   (__nv_bfloat16*)wimg, total);
+  return check_launch("tdeed_conv3_weight_image");
 }

@@ -4,6 +4,7 @@
 //   tdeed_stem_bwd_weight      dW[co][ci*9+ky*3+kx] of the 3->32 stride-2 stem conv, recomputing the normalised patch
 //                              from the frames (crop / flip / normalise exactly as the forward stem kernel)
 // CUDA-core fp32 accumulation; weight gradients are reduced over per-CTA partials in a fixed order (deterministic).
+#include <cstdlib>
 #include "train_reduce.cuh"
 
 namespace tdeed {
@@ -279,11 +280,29 @@ extern "C" int tdeed_conv3x3g_bwd_data(int dtype, const void* dy, int n, int h, 
   return TDEED_ERR_UNSUPPORTED;
 }
 
+namespace tdeed {
+// tcgen05 backend (train_conv_tc.cu), bf16 activations
+bool conv3x3g_bwd_weight_tc_applicable(int dtype, const void* x, const void* dy, int c);
+long long conv3x3g_bwd_weight_tc_workspace_floats(int n, int h, int w, int c, int gw, int stride);
+int conv3x3g_bwd_weight_tc_launch(const void* x, const void* dy, int n, int h, int w, int c, int gw, int stride, float* dw, float* ws,
+                                  cudaStream_t st);
+static bool conv_force_simt() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TDEED_CONV_BWD_SIMT");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+}  // namespace tdeed
+
 extern "C" long long tdeed_conv3x3g_bwd_weight_workspace_floats(int n, int h, int w, int c, int group_width, int stride) {
   using namespace tdeed;
   const int oh = (h + stride - 1) / stride, ow = (w + stride - 1) / stride;
   const long long total = (long long)n * oh * ceil_div(ow, CW_SEG);
-  return (long long)cw_parts(total, c, group_width) * c * group_width * 9;
+  const long long a = (long long)cw_parts(total, c, group_width) * c * group_width * 9;
+  const long long b = conv3x3g_bwd_weight_tc_workspace_floats(n, h, w, c, group_width, stride);
+  return a > b ? a : b;
 }
 
 extern "C" int tdeed_conv3x3g_bwd_weight(int dtype, const void* x, const void* dy, int n, int h, int w, int c, int group_width,
@@ -293,6 +312,8 @@ extern "C" int tdeed_conv3x3g_bwd_weight(int dtype, const void* x, const void* d
   TDEED_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % group_width == 0 && (group_width == 8 || group_width == 16) &&
                 (stride == 1 || stride == 2), TDEED_ERR_SHAPE, "tdeed_conv3x3g_bwd_weight: bad shape n=%d %dx%dx%d gw=%d s=%d", n, h, w, c, group_width, stride);
   cudaStream_t st = (cudaStream_t)stream;
+  if (!conv_force_simt() && conv3x3g_bwd_weight_tc_applicable(dtype, x, dy, c))
+    return conv3x3g_bwd_weight_tc_launch(x, dy, n, h, w, c, group_width, stride, dw, workspace, st);
   if (dtype == TDEED_BF16)
     return stride == 1 ? launch_bwd_weight<__nv_bfloat16, 1>(x, dy, n, h, w, c, group_width, dw, workspace, st)
                        : launch_bwd_weight<__nv_bfloat16, 2>(x, dy, n, h, w, c, group_width, dw, workspace, st);

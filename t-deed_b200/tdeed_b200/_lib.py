@@ -90,6 +90,9 @@ SIGNATURES.update({
     'tdeed_stem_bwd_weight': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_int,
                                       c_vp, c_vp, c_vp]),
     'tdeed_conv3x3g_raw_fwd': (c_int, [c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    'tdeed_conv3_weight_image_elems': (c_ll, [c_int]),
+    'tdeed_conv3_weight_image': (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp]),
+    'tdeed_conv3x3g_tc_raw_fwd': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     'tdeed_conv3x3g_bwd_data': (c_int, [c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     'tdeed_conv3x3g_bwd_weight_workspace_floats': (c_ll, [c_int, c_int, c_int, c_int, c_int, c_int]),
     'tdeed_conv3x3g_bwd_weight': (c_int, [c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),

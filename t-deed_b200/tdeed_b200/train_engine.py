@@ -122,7 +122,10 @@ class TrainEngine:
         y1 = self._gemm(a1, w1, M)
         st1 = self._bn(y1, cout, c1 + '.bn')
         z1 = T.bn_act_fwd(y1, st1, relu=True)
-        y2 = T.conv3x3g_raw(z1.view(n, h, w, cout), P[p + '.conv2.conv.weight'], self.gw, stride)
+        if self.adt == torch.bfloat16:      # tcgen05 implicit GEMM (conv3x3g_tc.cu), weights re-imaged from the fp32 master
+            y2 = T.conv3x3g_tc_raw(z1.view(n, h, w, cout), T.conv3_weight_image(P[p + '.conv2.conv.weight'], self.gw), stride)
+        else:
+            y2 = T.conv3x3g_raw(z1.view(n, h, w, cout), P[p + '.conv2.conv.weight'], self.gw, stride)
         oh, ow = y2.shape[1:3]
         M2 = n * oh * ow
         st2 = self._bn(y2.view(M2, cout), cout, p + '.conv2.bn')
@@ -296,7 +299,10 @@ class TrainEngine:
         G[p + '.conv2.bn.bias'].copy_(db)
         z1 = r['z1'].view(n, h, w, cout)
         T.conv3x3g_bwd_weight(z1, dy2, self.gw, stride, out=G[p + '.conv2.conv.weight'])
-        dz1 = T.conv3x3g_bwd_data(dy2, (n, h, w, cout), P[p + '.conv2.conv.weight'], self.gw, stride)
+        if self.adt == torch.bfloat16 and stride == 1:   # data gradient = the same tcgen05 conv with the transposed, flipped kernel
+            dz1 = T.conv3x3g_tc_raw(dy2, T.conv3_weight_image(P[p + '.conv2.conv.weight'], self.gw, transpose_flip=True), 1)
+        else:
+            dz1 = T.conv3x3g_bwd_data(dy2, (n, h, w, cout), P[p + '.conv2.conv.weight'], self.gw, stride)
         # conv1 (+BN+ReLU)
         dy1, dg, db, _ = T.bn_act_bwd(dz1.view(M, cout), r['z1'], r['y1'], r['st1'])
         c1 = r['c1']

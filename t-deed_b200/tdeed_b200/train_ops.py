@@ -116,6 +116,23 @@ def conv3x3g_raw(x, weight, group_width, stride):
     return out
 
 
+def conv3_weight_image(weight, group_width, transpose_flip=False):
+    """fp32 [C, gw, 3, 3] -> bf16 UMMA B tiles for the tcgen05 grouped conv (transpose_flip: the data-gradient kernel)."""
+    c = weight.shape[0]
+    img = torch.empty(int(L.load().tdeed_conv3_weight_image_elems(c)), dtype=torch.bfloat16, device=weight.device)
+    L.check(L.load().tdeed_conv3_weight_image(L.ptr(weight), c, group_width, int(transpose_flip), L.ptr(img), L.stream()),
+            'conv3_weight_image')
+    return img
+
+
+def conv3x3g_tc_raw(x, wimg, stride):
+    """bf16 NHWC raw grouped 3x3 convolution on tcgen05 (no bias, no activation)."""
+    n, h, w, c = x.shape
+    out = torch.empty((n, (h + stride - 1) // stride, (w + stride - 1) // stride, c), dtype=x.dtype, device=x.device)
+    L.check(L.load().tdeed_conv3x3g_tc_raw_fwd(L.ptr(x), n, h, w, c, stride, L.ptr(wimg), L.ptr(out), L.stream()), 'conv3x3g_tc_raw')
+    return out
+
+
 def conv3x3g_bwd_data(dy, in_shape, weight, group_width, stride):
     n, h, w, c = in_shape
     dx = torch.empty(in_shape, dtype=dy.dtype, device=dy.device)

@@ -195,6 +195,20 @@ def test_conv3x3g_train(c, gw, stride, h, w):
     assert rel(nchw(dxb.float()), xr.grad) < 2e-2
     dwb = T().conv3x3g_bwd_weight(nhwc(x).bfloat16(), nhwc(dy).bfloat16(), gw, stride)
     assert rel(dwb, wr.grad) < 2e-2
+    # the bf16 path is the tcgen05 kernel (train_conv_tc.cu): exact products of the rounded inputs, fp32 accumulation
+    xq, wq = x.bfloat16().float().requires_grad_(True), wgt.clone().requires_grad_(True)
+    F.conv2d(xq, wq, stride=stride, padding=1, groups=c // gw).backward(dy.bfloat16().float())
+    assert rel(dwb, wq.grad) < 2e-4
+    # tcgen05 raw forward / stride-1 data gradient with device-built weight images (weights rounded to bf16 inside)
+    wb = wgt.bfloat16().float()
+    yq = F.conv2d(x.bfloat16().float(), wb, stride=stride, padding=1, groups=c // gw)
+    yt = T().conv3x3g_tc_raw(nhwc(x).bfloat16(), T().conv3_weight_image(wgt, gw), stride)
+    assert rel(nchw(yt.float()), yq) < 1e-2
+    if stride == 1:
+        dq = dy.bfloat16().float()
+        dxq = torch.nn.grad.conv2d_input(x.shape, wb, dq, stride=1, padding=1, groups=c // gw)
+        dxt = T().conv3x3g_tc_raw(nhwc(dy).bfloat16(), T().conv3_weight_image(wgt, gw, transpose_flip=True), 1)
+        assert rel(nchw(dxt.float()), dxq) < 1e-2
 
 
 @pytest.mark.parametrize('c,rd,hw', [(24, 8, 64), (152, 38, 49), (768, 80, 16)])
