@@ -25,7 +25,8 @@ int tdeed_bn_stats(int dtype, const void* x, long long M, int C, long long ld, c
 int tdeed_bn_act_fwd(int dtype, const void* y, long long M, int C, const float* stats, const void* residual, int relu,
                      void* out, void* stream);
 /* g = dz * (z > 0) (z == NULL: no ReLU);  dgamma = sum g*xhat, dbeta = sum g;  dy = scale*(g - dbeta/M - xhat*dgamma/M);
- * dres (nullable) = g, the gradient of the residual operand.  dy may alias dz. */
+ * dres (nullable) = g, the gradient of the residual operand.  dy may alias dz.  Passing z == y (the same pointer) asks for the
+ * ReLU mask to be recomputed as (y*scale + shift > 0) — valid when the forward had no residual — which saves reading z. */
 int tdeed_bn_act_bwd(int dtype, const void* dz, const void* z, const void* y, long long M, int C, const float* stats,
                      float* dgamma, float* dbeta, void* dy, void* dres, float* workspace, void* stream);
 

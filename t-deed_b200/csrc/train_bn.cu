@@ -34,14 +34,12 @@ __global__ void bn_stats_final_kernel(const T* __restrict__ x, const float* __re
                                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps, float momentum,
                                       float* __restrict__ running_mean, float* __restrict__ running_var,
                                       float* __restrict__ stats) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // warp per channel
   if (ch >= C) return;
   const int cpad = ((C + 7) / 8) * 8;
-  double s = 0.0, q = 0.0;
-  for (int p = 0; p < nparts; ++p) {
-    s += (double)part[((size_t)p * 2) * cpad + ch];
-    q += (double)part[((size_t)p * 2 + 1) * cpad + ch];
-  }
+  double s, q;
+  warp_partial_sums(part, nparts, cpad, ch, s, q);
+  if ((threadIdx.x & 31) != 0) return;
   const double piv = (double)Elem<T>::ld(x + ch);
   const double dm = s / (double)M;
   const double mean = piv + dm;
@@ -60,24 +58,33 @@ __global__ void bn_stats_final_kernel(const T* __restrict__ x, const float* __re
   }
 }
 
-// ---- forward apply ----
+// ---- forward apply.  A thread owns one channel octet (its scale / shift stay in registers) and walks the rows ----
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS)
-bn_act_fwd_kernel(const T* __restrict__ y, long long total8, int c8n, const float* __restrict__ scale,
+bn_act_fwd_kernel(const T* __restrict__ y, long long M, int C, const float* __restrict__ scale,
                   const float* __restrict__ shift, const T* __restrict__ residual, int relu, T* __restrict__ out) {
-  const long long q = (long long)blockIdx.x * BN_THREADS + threadIdx.x;
-  if (q >= total8) return;
-  const int c0 = (int)(q % c8n) * 8;
-  float v[8], r[8];
-  load8(y + q * 8, v);
-  if (residual) load8(residual + q * 8, r);
+  const BnLayout l = bn_layout(C);
+  const int c8 = threadIdx.x % l.c8n, lr = threadIdx.x / l.c8n;
+  if (lr >= l.rpi) return;
+  float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    float t = fmaf(v[j], scale[c0 + j], shift[c0 + j]);
-    if (residual) t += r[j];
-    v[j] = relu ? fmaxf(t, 0.f) : t;
+    sc[j] = scale[c8 * 8 + j];
+    sh[j] = shift[c8 * 8 + j];
   }
-  store8(out + q * 8, v);
+  for (long long r = (long long)blockIdx.x * l.rpi + lr; r < M; r += (long long)gridDim.x * l.rpi) {
+    const long long at = r * C + c8 * 8;
+    float v[8], rr[8];
+    load8(y + at, v);
+    if (residual) load8(residual + at, rr);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = fmaf(v[j], sc[j], sh[j]);
+      if (residual) t += rr[j];
+      v[j] = relu ? fmaxf(t, 0.f) : t;
+    }
+    store8(out + at, v);
+  }
 }
 
 // ---- backward ----
@@ -89,19 +96,27 @@ struct BwdOp {
   const float* mean;
   const float* invstd;
   int C;
-  float mu[8], is[8];
+  int mask_from_y;       // z == y sentinel: ReLU mask recomputed as (y*scale + shift > 0) — saves reading z
+  float mu[8], is[8], sc[8], sh[8];
   __device__ void begin(int ch0, int nch) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       mu[j] = j < nch ? mean[ch0 + j] : 0.f;
       is[j] = j < nch ? invstd[ch0 + j] : 0.f;
+      sc[j] = j < nch ? mean[2 * C + ch0 + j] : 0.f;
+      sh[j] = j < nch ? mean[3 * C + ch0 + j] : 0.f;
     }
   }
   __device__ void row(long long r, int ch0, int nch, float (&a0)[8], float (&a1)[8]) {
     float g[8], yv[8], zv[8];
     load8(dz + r * C + ch0, g);
     load8(y + r * C + ch0, yv);
-    if (z) load8(z + r * C + ch0, zv);
+    if (mask_from_y) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) zv[j] = fmaf(yv[j], sc[j], sh[j]);
+    } else if (z) {
+      load8(z + r * C + ch0, zv);
+    }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float gg = (z && !(zv[j] > 0.f)) ? 0.f : g[j];
@@ -113,14 +128,12 @@ struct BwdOp {
 
 __global__ void bn_bwd_final_kernel(const float* __restrict__ part, int nparts, long long M, int C,
                                     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ coef) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // warp per channel
   if (ch >= C) return;
   const int cpad = ((C + 7) / 8) * 8;
-  double s = 0.0, q = 0.0;
-  for (int p = 0; p < nparts; ++p) {
-    s += (double)part[((size_t)p * 2) * cpad + ch];
-    q += (double)part[((size_t)p * 2 + 1) * cpad + ch];
-  }
+  double s, q;
+  warp_partial_sums(part, nparts, cpad, ch, s, q);
+  if ((threadIdx.x & 31) != 0) return;
   if (dbeta) dbeta[ch] = (float)s;
   if (dgamma) dgamma[ch] = (float)q;
   coef[ch] = (float)(s / (double)M);
@@ -129,25 +142,51 @@ __global__ void bn_bwd_final_kernel(const float* __restrict__ part, int nparts, 
 
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS)
-bn_act_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T* __restrict__ y, long long total8, int c8n,
-                        int C, const float* __restrict__ stats, const float* __restrict__ coef, T* __restrict__ dy,
+bn_act_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T* __restrict__ y, long long M, int C,
+                        const float* __restrict__ stats, const float* __restrict__ coef, T* __restrict__ dy,
                         T* __restrict__ dres) {
-  const long long q = (long long)blockIdx.x * BN_THREADS + threadIdx.x;
-  if (q >= total8) return;
-  const int c0 = (int)(q % c8n) * 8;
-  float g[8], yv[8], zv[8], o[8];
-  load8(dz + q * 8, g);
-  load8(y + q * 8, yv);
-  if (z) load8(z + q * 8, zv);
+  const BnLayout l = bn_layout(C);
+  const int c8 = threadIdx.x % l.c8n, lr = threadIdx.x / l.c8n;
+  if (lr >= l.rpi) return;
+  float mu[8], is[8], sc[8], sh[8], k1[8], k2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int ch = c0 + j;
-    if (z && !(zv[j] > 0.f)) g[j] = 0.f;
-    const float xhat = (yv[j] - stats[ch]) * stats[C + ch];
-    o[j] = stats[2 * C + ch] * (g[j] - coef[ch] - xhat * coef[C + ch]);
+    const int ch = c8 * 8 + j;
+    mu[j] = stats[ch];
+    is[j] = stats[C + ch];
+    sc[j] = stats[2 * C + ch];
+    sh[j] = stats[3 * C + ch];
+    k1[j] = coef[ch];
+    k2[j] = coef[C + ch];
   }
-  store8(dy + q * 8, o);
-  if (dres) store8(dres + q * 8, g);
+  const bool from_y = z == y;
+  for (long long r = (long long)blockIdx.x * l.rpi + lr; r < M; r += (long long)gridDim.x * l.rpi) {
+    const long long at = r * C + c8 * 8;
+    float g[8], yv[8], zv[8], o[8];
+    load8(dz + at, g);
+    load8(y + at, yv);
+    if (from_y) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) zv[j] = fmaf(yv[j], sc[j], sh[j]);
+    } else if (z) {
+      load8(z + at, zv);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (z && !(zv[j] > 0.f)) g[j] = 0.f;
+      const float xhat = (yv[j] - mu[j]) * is[j];
+      o[j] = sc[j] * (g[j] - k1[j] - xhat * k2[j]);
+    }
+    store8(dy + at, o);
+    if (dres) store8(dres + at, g);
+  }
+}
+
+static int bn_apply_grid(long long M, int C) {
+  const BnLayout l = bn_layout(C);
+  const long long need = ceil_div_ll(M, l.rpi);
+  const long long cap = (long long)kNumSMs * 16;
+  return (int)(need < cap ? need : cap);
 }
 
 template <typename T>
@@ -160,7 +199,7 @@ static int run_stats(const void* x, long long M, int C, long long ld, const floa
   bn_reduce_kernel<T, StatsOp<T>><<<grid, BN_THREADS, 0, st>>>(op, M, C, ws);
   int rc = check_launch("tdeed_bn_stats(partial)");
   if (rc) return rc;
-  bn_stats_final_kernel<T><<<ceil_div(C, 128), 128, 0, st>>>((const T*)x, ws, grid, M, C, gamma, beta, eps, momentum, rm, rv, stats);
+  bn_stats_final_kernel<T><<<ceil_div(C, 8), 256, 0, st>>>((const T*)x, ws, grid, M, C, gamma, beta, eps, momentum, rm, rv, stats);
   return check_launch("tdeed_bn_stats(final)");
 }
 
@@ -174,18 +213,18 @@ static int run_bwd(const void* dz, const void* z, const void* y, long long M, in
   op.mean = stats;
   op.invstd = stats + C;
   op.C = C;
+  op.mask_from_y = (z != nullptr && z == y) ? 1 : 0;
   const int grid = bn_grid(M, C);
   const int cpad = ((C + 7) / 8) * 8;
   float* coef = ws + (size_t)BN_MAX_GRID * 2 * cpad;
   bn_reduce_kernel<T, BwdOp<T>><<<grid, BN_THREADS, 0, st>>>(op, M, C, ws);
   int rc = check_launch("tdeed_bn_act_bwd(partial)");
   if (rc) return rc;
-  bn_bwd_final_kernel<<<ceil_div(C, 128), 128, 0, st>>>(ws, grid, M, C, dgamma, dbeta, coef);
+  bn_bwd_final_kernel<<<ceil_div(C, 8), 256, 0, st>>>(ws, grid, M, C, dgamma, dbeta, coef);
   rc = check_launch("tdeed_bn_act_bwd(final)");
   if (rc) return rc;
-  const long long total8 = M * (C / 8);
-  bn_act_bwd_apply_kernel<T><<<(unsigned)ceil_div_ll(total8, BN_THREADS), BN_THREADS, 0, st>>>(
-      (const T*)dz, (const T*)z, (const T*)y, total8, C / 8, C, stats, coef, (T*)dy, (T*)dres);
+  bn_act_bwd_apply_kernel<T><<<bn_apply_grid(M, C), BN_THREADS, 0, st>>>((const T*)dz, (const T*)z, (const T*)y, M, C, stats, coef,
+                                                                         (T*)dy, (T*)dres);
   return check_launch("tdeed_bn_act_bwd(apply)");
 }
 
@@ -216,13 +255,12 @@ extern "C" int tdeed_bn_act_fwd(int dtype, const void* y, long long M, int C, co
   TDEED_REQUIRE(y && stats && out, TDEED_ERR_SHAPE, "tdeed_bn_act_fwd: null pointer");
   TDEED_REQUIRE(M > 0 && C > 0 && C % 8 == 0, TDEED_ERR_SHAPE, "tdeed_bn_act_fwd: bad shape M=%lld C=%d", M, C);
   cudaStream_t st = (cudaStream_t)stream;
-  const long long total8 = M * (C / 8);
-  const unsigned grid = (unsigned)ceil_div_ll(total8, BN_THREADS);
+  const int grid = bn_apply_grid(M, C);
   if (dtype == TDEED_BF16)
-    bn_act_fwd_kernel<__nv_bfloat16><<<grid, BN_THREADS, 0, st>>>((const __nv_bfloat16*)y, total8, C / 8, stats + 2 * C, stats + 3 * C,
+    bn_act_fwd_kernel<__nv_bfloat16><<<grid, BN_THREADS, 0, st>>>((const __nv_bfloat16*)y, M, C, stats + 2 * C, stats + 3 * C,
                                                                    (const __nv_bfloat16*)residual, relu, (__nv_bfloat16*)out);
   else if (dtype == TDEED_F32)
-    bn_act_fwd_kernel<float><<<grid, BN_THREADS, 0, st>>>((const float*)y, total8, C / 8, stats + 2 * C, stats + 3 * C,
+    bn_act_fwd_kernel<float><<<grid, BN_THREADS, 0, st>>>((const float*)y, M, C, stats + 2 * C, stats + 3 * C,
                                                            (const float*)residual, relu, (float*)out);
   else { set_error("tdeed_bn_act_fwd: dtype %d", dtype); return TDEED_ERR_UNSUPPORTED; }
   return check_launch("tdeed_bn_act_fwd");

@@ -233,14 +233,12 @@ struct GsfBnOp {
 
 __global__ void gsf_bn_final_kernel(const float* __restrict__ part, int nparts, long long M, int C, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta, float* __restrict__ coef) {
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  const int ch = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // warp per channel
   if (ch >= C) return;
   const int cpad = ((C + 7) / 8) * 8;
-  double s = 0.0, q = 0.0;
-  for (int p = 0; p < nparts; ++p) {
-    s += (double)part[((size_t)p * 2) * cpad + ch];
-    q += (double)part[((size_t)p * 2 + 1) * cpad + ch];
-  }
+  double s, q;
+  warp_partial_sums(part, nparts, cpad, ch, s, q);
+  if ((threadIdx.x & 31) != 0) return;
   dbeta[ch] = (float)s;
   dgamma[ch] = (float)q;
   coef[ch] = (float)(s / (double)M);
@@ -397,7 +395,7 @@ static int run_gsf_bwd(int mode, const void* x, const void* dcat, const void* ad
   const int grid = bn_grid(M, fold);
   bn_reduce_kernel<T, GsfBnOp<T>><<<grid, BN_THREADS, 0, st>>>(op, M, fold, bnpart);
   if ((rc = check_launch("tdeed_gsf_bwd(bn partial)"))) return rc;
-  gsf_bn_final_kernel<<<ceil_div(fold, 128), 128, 0, st>>>(bnpart, grid, M, fold, dgamma, dbeta, coef);
+  gsf_bn_final_kernel<<<ceil_div(fold, 8), 256, 0, st>>>(bnpart, grid, M, fold, dgamma, dbeta, coef);
   if ((rc = check_launch("tdeed_gsf_bwd(bn final)"))) return rc;
   const long long total8 = M * (c / 8);
   gsf_bwd_final_kernel<T><<<(unsigned)ceil_div_ll(total8, GB_THREADS), GB_THREADS, 0, st>>>(

@@ -17,6 +17,25 @@ __host__ __device__ inline BnLayout bn_layout(int C) {
   return l;
 }
 
+// Final stage of the column reductions: one WARP per channel sums the per-CTA partials part[p][which][ch] (lane l takes
+// p = l, l+32, ... serially, then a fixed xor-shuffle tree) in double.  Deterministic; ~20x faster than one thread per
+// channel walking all partials.  Call with ch uniform across the warp.
+__device__ inline void warp_partial_sums(const float* __restrict__ part, int nparts, int cpad, int ch, double& s, double& q) {
+  const int lane = threadIdx.x & 31;
+  double a = 0.0, b = 0.0;
+  for (int p = lane; p < nparts; p += 32) {
+    a += (double)part[((size_t)p * 2) * cpad + ch];
+    b += (double)part[((size_t)p * 2 + 1) * cpad + ch];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    b += __shfl_xor_sync(0xffffffffu, b, o);
+  }
+  s = a;
+  q = b;
+}
+
 // Generic column reduction: OP::row(v-arrays) -> two accumulators per channel.  part: [grid][2][c8n*8]
 template <typename T, typename OP>
 __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(OP op, long long M, int C, float* __restrict__ part) {

@@ -262,7 +262,7 @@ class TrainEngine:
         for rec in reversed(tape['blocks']):
             dz = self._block_bwd(rec, dz, b, t)
         y0, st0, a0 = tape['stem']
-        dy0, dg, db, _ = T.bn_act_bwd(dz, a0, y0, st0)
+        dy0, dg, db, _ = T.bn_act_bwd(dz, y0, y0, st0)
         G['_features.stem.bn.weight'].copy_(dg)
         G['_features.stem.bn.bias'].copy_(db)
         T.stem_bwd_weight(tape['frames'], tape['unit'], tape['crop'], tape['flip'], dy0, out=G['_features.stem.conv.weight'])
@@ -294,7 +294,7 @@ class TrainEngine:
         G[p + '.se.fc2.weight'].view(d_w2.shape).copy_(d_w2)
         G[p + '.se.fc2.bias'].copy_(d_b2)
         # conv2 (+BN+ReLU)
-        dy2, dg, db, _ = T.bn_act_bwd(dz2, r['z2'], r['y2'], r['st2'])
+        dy2, dg, db, _ = T.bn_act_bwd(dz2, r['y2'], r['y2'], r['st2'])          # mask recomputed from y (no residual)
         G[p + '.conv2.bn.weight'].copy_(dg)
         G[p + '.conv2.bn.bias'].copy_(db)
         z1 = r['z1'].view(n, h, w, cout)
@@ -304,7 +304,7 @@ class TrainEngine:
         else:
             dz1 = T.conv3x3g_bwd_data(dy2, (n, h, w, cout), P[p + '.conv2.conv.weight'], self.gw, stride)
         # conv1 (+BN+ReLU)
-        dy1, dg, db, _ = T.bn_act_bwd(dz1.view(M, cout), r['z1'], r['y1'], r['st1'])
+        dy1, dg, db, _ = T.bn_act_bwd(dz1.view(M, cout), r['y1'], r['y1'], r['st1'])
         c1 = r['c1']
         G[c1 + '.bn.weight'].copy_(dg)
         G[c1 + '.bn.bias'].copy_(db)
@@ -350,7 +350,7 @@ class TrainEngine:
         p = r['p']
         d = self.cfg.feat_dim
         dout_op = dout2d if self.adt == torch.float32 else T.cast(dout2d, self.adt)
-        T.gemm_tn(dout2d, r['a'], d, 4 * d, rows, out=G[p + '.mlp.2.weight'].view(d, 4 * d))
+        T.gemm_tn(dout_op, r['a'], d, 4 * d, rows, out=G[p + '.mlp.2.weight'].view(d, 4 * d))
         T.colsum(dout2d, out=G[p + '.mlp.2.bias'])
         da = self._gemm(dout_op, r['w2t'], rows, out_dtype=torch.float32)           # [rows, 4d]
         dh = T.gelu_bwd(r['h'], da, self.adt)
@@ -400,9 +400,9 @@ class TrainEngine:
         G[p + '.gn.weight'].copy_(dgw)
         G[p + '.gn.bias'].copy_(dgb)
         dpre = T.gelu_bwd(r['pre'], do.view(rows, d), torch.float32)
-        T.gemm_tn(dpre, r['cat_op'], d, 6 * d, rows, out=G[p + '.concat_fc.weight'].view(d, 6 * d))
-        T.colsum(dpre, out=G[p + '.concat_fc.bias'])
         dpre_op = dpre if self.adt == torch.float32 else T.cast(dpre, self.adt)
+        T.gemm_tn(dpre_op, r['cat_op'], d, 6 * d, rows, out=G[p + '.concat_fc.weight'].view(d, 6 * d))
+        T.colsum(dpre, out=G[p + '.concat_fc.bias'])
         dcat = self._gemm(dpre_op, r['wct'], rows, out_dtype=torch.float32)        # [rows, 6d]
         cat = r['cat']
 

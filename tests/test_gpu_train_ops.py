@@ -103,6 +103,11 @@ def test_bn_stats_column_slice_and_no_relu():
     st = T().bn_stats(y, 56, ga, be)
     dy, dgamma, dbeta, _ = T().bn_act_bwd(dz, None, y, st)
     assert rel(dy, yr.grad) < 1e-4 and rel(dgamma, gr.grad) < 1e-4
+    # ReLU without residual: passing z == y recomputes the mask from y instead of reading z
+    yr2, gr2 = y.clone().requires_grad_(True), ga.clone().requires_grad_(True)
+    F.relu(F.batch_norm(yr2, None, None, gr2, be, training=True)).backward(dz)
+    dy2, dgamma2, _, _ = T().bn_act_bwd(dz, y, y, st)
+    assert rel(dy2, yr2.grad) < 1e-4 and rel(dgamma2, gr2.grad) < 1e-4
 
 
 @pytest.mark.parametrize('dt_a,dt_b', [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16), (torch.float32, torch.bfloat16)])
