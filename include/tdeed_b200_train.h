@@ -123,6 +123,9 @@ int tdeed_cast_f32(const float* in, long long n, void* out, int out_dtype, void*
 /* ---- heads, loss, optimizer ---------------------------------------------------------------------------------------- */
 int tdeed_dropout_fwd(const float* x, long long n, float p, unsigned long long seed, float* out, unsigned char* mask,
                       void* stream);
+/* same, with the seed read from device memory (seed_dev[0]*2 + salt): a CUDA graph replay then draws a new mask per step */
+int tdeed_dropout_fwd_devseed(const float* x, long long n, float p, const long long* seed_dev, unsigned long long salt,
+                              float* out, unsigned char* mask, void* stream);
 int tdeed_dropout_bwd(const float* dy, const unsigned char* mask, long long n, float p, const float* add, float* dx,
                       void* stream);
 int tdeed_linear_fwd(const float* x, int M, int C, const float* W, const float* b, int N, float* out, int ldo, void* stream);

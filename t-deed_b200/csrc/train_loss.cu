@@ -28,6 +28,18 @@ __global__ void dropout_fwd_kernel(const float* __restrict__ x, long long n, flo
   out[i] = keep ? x[i] / (1.f - p) : 0.f;
 }
 
+// seed read from device memory (base[0] + salt): lets a CUDA graph replay draw a fresh mask every step
+__global__ void dropout_fwd_devseed_kernel(const float* __restrict__ x, long long n, float p, const long long* __restrict__ seed_dev,
+                                           unsigned long long salt, float* __restrict__ out, uint8_t* __restrict__ mask) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long seed = (unsigned long long)seed_dev[0] * 2ull + salt;
+  const float u = (float)hash_u64(seed * 0x100000001b3ull + (unsigned long long)i) * (1.f / 4294967296.f);
+  const bool keep = u >= p;
+  mask[i] = keep ? 1 : 0;
+  out[i] = keep ? x[i] / (1.f - p) : 0.f;
+}
+
 __global__ void dropout_bwd_kernel(const float* __restrict__ dy, const uint8_t* __restrict__ mask, long long n, float p,
                                    const float* __restrict__ add, float* __restrict__ dx) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -156,6 +168,13 @@ extern "C" int tdeed_dropout_fwd(const float* x, long long n, float p, unsigned 
   TDEED_REQUIRE(x && out && mask && n > 0 && p >= 0.f && p < 1.f, TDEED_ERR_SHAPE, "tdeed_dropout_fwd: bad arguments");
   dropout_fwd_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, p, seed, out, mask);
   return check_launch("tdeed_dropout_fwd");
+}
+
+extern "C" int tdeed_dropout_fwd_devseed(const float* x, long long n, float p, const long long* seed_dev, unsigned long long salt,
+                                         float* out, unsigned char* mask, void* stream) {
+  TDEED_REQUIRE(x && out && mask && seed_dev && n > 0 && p >= 0.f && p < 1.f, TDEED_ERR_SHAPE, "tdeed_dropout_fwd_devseed: bad arguments");
+  dropout_fwd_devseed_kernel<<<(unsigned)ceil_div_ll(n, 256), 256, 0, (cudaStream_t)stream>>>(x, n, p, seed_dev, salt, out, mask);
+  return check_launch("tdeed_dropout_fwd_devseed");
 }
 
 extern "C" int tdeed_dropout_bwd(const float* dy, const unsigned char* mask, long long n, float p, const float* add, float* dx,

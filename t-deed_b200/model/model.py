@@ -87,6 +87,8 @@ class TDEEDModel(BaseRGBModel):
             self._engine_versions = {}
             self._flat = None
             self._train_engines = {}
+            self._train_graphs = {}
+            self.use_train_graph = True      # replay forward+loss+backward as a CUDA graph from the 3rd step of a signature on
             self._train_calls = 0
 
         # ---- engine management -------------------------------------------------------------
@@ -114,6 +116,7 @@ class TDEEDModel(BaseRGBModel):
             if self._flat is None or not self._flat.valid():
                 self._flat = FlatParams(self)
                 self._train_engines.clear()
+                self._train_graphs.clear()
             return self._flat
 
         def train_engine(self, precision):
@@ -129,7 +132,7 @@ class TDEEDModel(BaseRGBModel):
             return eng
 
         def train_step(self, frame, label, labelD=None, fg_weight=5, grad_scale=1.0, accumulate=False, precision='bf16',
-                       dropout_p=None):
+                       dropout_p=None, use_graph=None):
             """Forward (train mode) + loss + backward on the sm_100a kernels (model/model.py:262-324 of the reference).
             frame: (B,T,3,H,W) uint8 | float valued 0..255, already mixed up.  label: int64 (B*T) | float (B*T, K).
             Gradients of grad_scale * loss land in p.grad (added to the existing ones when accumulate).  Returns the
@@ -155,29 +158,74 @@ class TDEEDModel(BaseRGBModel):
                 frame, unit, cy, cx = x.contiguous(), True, 0, 0
             elif frame.dtype not in (torch.uint8, torch.float32):
                 frame = frame.float()
+            if (cy or cx) and (use_graph if use_graph is not None else self.use_train_graph):
+                # a random crop window would make every step a new graph signature: cut the window out first
+                frame, cy, cx = frame[..., cy:cy + ch, cx:cx + cw], 0, 0
             frame = frame.contiguous()
             self._train_calls += 1
             if dropout_p is None:            # nn.Dropout() of the FC heads (model/modules.py:366-376): p = 0.5 in train mode
                 dropout_p = float(self._pred_fine.dropout.p) if self.training else 0.0
-            hard = label if not label.dtype.is_floating_point else None
+            hard = label.reshape(-1).contiguous() if not label.dtype.is_floating_point else None
             soft = label.float().contiguous() if label.dtype.is_floating_point else None
-            tgt = flat.G if not accumulate and grad_scale == 1.0 else None
-            if tgt is None:                     # accumulate / scale: write into a scratch buffer, then axpy
-                scratch = torch.zeros_like(flat.g)
-                eng.G = {n: scratch[o:o + cnt].view(flat.P[n].shape) for n, (o, cnt) in flat.offsets.items()}
-            else:
-                eng.G = flat.G
-            logits, displ = eng.forward(frame, (cy, cx, ch, cw), unit_input=unit,
-                                        dropout_p=dropout_p, seed=self._train_calls)
-            loss = eng.loss(logits, displ, hard.reshape(-1).contiguous() if hard is not None else None, soft,
-                            labelD.reshape(-1).float().contiguous() if (labelD is not None and displ is not None) else None,
-                            fg_weight=fg_weight)
-            eng.backward()
-            if tgt is None:
-                if accumulate:
-                    TO.axpy_(scratch, grad_scale, flat.g)
-                else:
-                    flat.g.zero_()
+            use_d = labelD is not None and self._radi_displacement > 0
+            labD = labelD.reshape(-1).float().contiguous() if use_d else None
+
+            def run(fr, hd, sf, ld, grads):
+                eng.G = grads
+                logits, displ = eng.forward(fr, (cy, cx, ch, cw), unit_input=unit, dropout_p=dropout_p)
+                loss = eng.loss(logits, displ, hd, sf, ld, fg_weight=fg_weight)
+                eng.backward()
+                return loss, logits, displ
+
+            direct = not accumulate and grad_scale == 1.0
+            if use_graph is None:
+                use_graph = self.use_train_graph
+            if use_graph:
+                # CUDA graph of forward + loss + backward for this (shapes, crop, dtypes) signature: ~3500 launches replayed
+                # with one host call.  Inputs are copied into static buffers; gradients land in a static buffer.
+                key = (precision, tuple(frame.shape), frame.dtype, (cy, cx, ch, cw), unit, hard is not None, use_d, dropout_p,
+                       fg_weight, flat.p.data_ptr())
+                ent = self._train_graphs.get(key)
+                if ent is None:                      # first sight of this signature: run eagerly (warms every kernel / allocator)
+                    self._train_graphs[key] = 'warm'
+                    use_graph = False
+                elif ent == 'warm':
+                    st = dict(frame=frame.clone(), hard=hard.clone() if hard is not None else None,
+                              soft=soft.clone() if soft is not None else None, labD=labD.clone() if labD is not None else None,
+                              g=torch.zeros_like(flat.g))
+                    st['G'] = {n: st['g'][o:o + cnt].view(flat.P[n].shape) for n, (o, cnt) in flat.offsets.items()}
+                    torch.cuda.synchronize()
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph):
+                        st['out'] = run(st['frame'], st['hard'], st['soft'], st['labD'], st['G'])
+                    st['graph'] = graph
+                    self._train_graphs[key] = ent = st
+                if use_graph:
+                    ent['frame'].copy_(frame)
+                    if hard is not None:
+                        ent['hard'].copy_(hard)
+                    if soft is not None:
+                        ent['soft'].copy_(soft)
+                    if labD is not None:
+                        ent['labD'].copy_(labD)
+                    ent['graph'].replay()
+                    loss, logits, displ = ent['out']
+                    if accumulate:
+                        TO.axpy_(ent['g'], grad_scale, flat.g)
+                    elif grad_scale == 1.0:
+                        flat.g.copy_(ent['g'])
+                    else:
+                        flat.g.zero_()
+                        TO.axpy_(ent['g'], grad_scale, flat.g)
+            if not use_graph:
+                if direct:
+                    loss, logits, displ = run(frame, hard, soft, labD, flat.G)
+                else:                               # accumulate / scale: write into a scratch buffer, then axpy
+                    scratch = torch.zeros_like(flat.g)
+                    G = {n: scratch[o:o + cnt].view(flat.P[n].shape) for n, (o, cnt) in flat.offsets.items()}
+                    loss, logits, displ = run(frame, hard, soft, labD, G)
+                    if not accumulate:
+                        flat.g.zero_()
                     TO.axpy_(scratch, grad_scale, flat.g)
             flat.attach_grads()
             self._last_train = (logits.view(b, t, -1), displ.view(b, t) if displ is not None else None)

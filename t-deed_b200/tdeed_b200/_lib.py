@@ -117,6 +117,7 @@ SIGNATURES.update({
     'tdeed_upsample_bwd': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     'tdeed_cast_f32': (c_int, [c_vp, c_ll, c_vp, c_int, c_vp]),
     'tdeed_dropout_fwd': (c_int, [c_vp, c_ll, c_float, c_ull, c_vp, c_vp, c_vp]),
+    'tdeed_dropout_fwd_devseed': (c_int, [c_vp, c_ll, c_float, c_vp, c_ull, c_vp, c_vp, c_vp]),
     'tdeed_dropout_bwd': (c_int, [c_vp, c_vp, c_ll, c_float, c_vp, c_vp, c_vp]),
     'tdeed_linear_fwd': (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_vp]),
     'tdeed_linear_bwd_data': (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp]),

@@ -35,6 +35,9 @@ class TrainEngine:
         self.gemm_backend = gemm_backend if act_dtype == torch.bfloat16 else L.GEMM_SIMT
         self.gw = REGNET[cfg.backbone]['group_width']
         self.launch_log = None
+        self._class_weights = {}
+        dev = next(iter(params.values())).device
+        self.seed_dev = torch.full((1,), torch.initial_seed() % (1 << 30), dtype=torch.int64, device=dev)
 
     # ------------------------------------------------------------------ helpers
     def _wop(self, name, rows, cols):
@@ -56,7 +59,7 @@ class TrainEngine:
         return T.bn_stats(y2d, C, self.P[p + '.weight'], self.P[p + '.bias'], self.B[p + '.running_mean'], self.B[p + '.running_var'])
 
     # ------------------------------------------------------------------ forward
-    def forward(self, frames, crop, unit_input=False, flip=False, dropout_p=0.5, seed=0):
+    def forward(self, frames, crop, unit_input=False, flip=False, dropout_p=0.5, seed=None):
         """frames (B,T,3,H,W) u8 | f32 device tensor.  Returns (logits [B*T,K] fp32, displ [B*T] | None) and keeps the tape."""
         cfg, P = self.cfg, self.P
         b, t = frames.shape[:2]
@@ -77,7 +80,10 @@ class TrainEngine:
         o2 = out.reshape(n, d)
         hd = {}
         if dropout_p > 0:
-            xin, hd['mask_c'] = T.dropout_fwd(o2, dropout_p, 2 * seed + 1)
+            if seed is not None:
+                self.seed_dev.fill_(int(seed))
+            self.seed_dev.add_(1)            # device-side step counter: a captured graph draws fresh masks on every replay
+            xin, hd['mask_c'] = T.dropout_fwd_devseed(o2, dropout_p, self.seed_dev, 0)
         else:
             xin = o2
         hd['x_c'] = xin
@@ -85,7 +91,7 @@ class TrainEngine:
         displ = None
         if cfg.radi_displacement > 0:
             if dropout_p > 0:
-                xd, hd['mask_d'] = T.dropout_fwd(o2, dropout_p, 2 * seed + 2)
+                xd, hd['mask_d'] = T.dropout_fwd_devseed(o2, dropout_p, self.seed_dev, 1)
             else:
                 xd = o2
             hd['x_d'] = xd
@@ -224,8 +230,10 @@ class TrainEngine:
         k = logits.shape[1]
         cw = None
         if fg_weight != 1:
-            cw = torch.full((k,), float(fg_weight), dtype=torch.float32, device=logits.device)
-            cw[0] = 1.0
+            cw = self._class_weights.get((k, fg_weight))      # cached: no host->device copy inside a graph capture
+            if cw is None:
+                cw = torch.tensor([1.0] + [float(fg_weight)] * (k - 1), dtype=torch.float32).to(logits.device)
+                self._class_weights[(k, fg_weight)] = cw
         loss, dlogits, ddispl = T.ce_mse_loss(logits, target_hard, target_soft, cw, displ, labelD if displ is not None else None)
         self.tape['dlogits'], self.tape['ddispl'] = dlogits, ddispl
         return loss

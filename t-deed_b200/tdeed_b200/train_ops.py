@@ -318,6 +318,15 @@ def dropout_fwd(x, p, seed):
     return out, mask
 
 
+def dropout_fwd_devseed(x, p, seed_dev, salt):
+    """seed_dev: int64 device tensor [1] (the step counter); mask = f(seed_dev[0]*2 + salt, element index)."""
+    out = torch.empty_like(x)
+    mask = torch.empty(x.shape, dtype=torch.uint8, device=x.device)
+    L.check(L.load().tdeed_dropout_fwd_devseed(L.ptr(x), x.numel(), p, L.ptr(seed_dev), salt, L.ptr(out), L.ptr(mask), L.stream()),
+            'dropout_fwd_devseed')
+    return out, mask
+
+
 def dropout_bwd(dy, mask, p, add=None):
     dx = torch.empty_like(dy)
     L.check(L.load().tdeed_dropout_bwd(L.ptr(dy), L.ptr(mask), dy.numel(), p, L.ptr(add), L.ptr(dx), L.stream()), 'dropout_bwd')

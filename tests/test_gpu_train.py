@@ -175,3 +175,32 @@ def test_epoch_trains_with_fused_adamw_and_scheduler():
     assert np.abs(probs - oprobs).max() < 1e-3
     # evaluation epoch still works after training
     assert np.isfinite(m.epoch([batch], optimizer=None))
+
+
+def test_train_step_cuda_graph_equals_eager(golden_dir):
+    """The captured forward+loss+backward graph (3rd call of a signature on) writes bit-identical gradients."""
+    cfg, sd, frames, label, labelD, g = train_case_from_golden('rny002_gsf_displ', golden_dir)
+    m = _model(cfg, sd)
+    m._model.train()
+    lab, fr, ld = label.cuda().reshape(-1), frames.cuda(), labelD.cuda()
+    flat = m._model.flat_params()
+    buffers0 = {k: v.clone() for k, v in m._model.named_buffers()}
+
+    def reset_buffers():
+        with torch.no_grad():
+            for k, v in m._model.named_buffers():
+                v.copy_(buffers0[k])
+
+    loss_e = m._model.train_step(fr, lab, ld, precision='bf16', use_graph=False).clone()
+    g_e = flat.g.clone()
+    reset_buffers()
+    for i in range(3):                                   # warm (eager), capture + replay, replay
+        loss_g = m._model.train_step(fr, lab, ld, precision='bf16', use_graph=True).clone()
+        assert torch.equal(flat.g, g_e), i
+        assert torch.equal(loss_g, loss_e)
+        if i < 2:
+            reset_buffers()
+    ent = [v for v in m._model._train_graphs.values() if isinstance(v, dict)]
+    assert len(ent) == 1 and 'graph' in ent[0]
+    # running statistics advanced exactly once since the last reset
+    assert int(m.state_dict()['_features.stem.bn.num_batches_tracked']) == int(buffers0['_features.stem.bn.num_batches_tracked']) + 1
