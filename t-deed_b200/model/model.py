@@ -288,12 +288,13 @@ class TDEEDModel(BaseRGBModel):
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
             return
+        from tdeed_b200.parallel import allreduce_gradients
         flat = self._model.flat_params()
-        dist.all_reduce(flat.g)
+        scale = allreduce_gradients(flat.g)
         if hasattr(optimizer, 'grad_scale'):
-            optimizer.grad_scale = 1.0 / dist.get_world_size()
+            optimizer.grad_scale = scale
         else:
-            flat.g.mul_(1.0 / dist.get_world_size())
+            flat.g.mul_(scale)
 
     def __init__(self, device='cuda', args=None):
         self.device = device

@@ -36,3 +36,29 @@ def gather_video_results(local, key=lambda d: d['video']):
     dist.all_gather_object(parts, local)
     merged = [d for part in parts for d in part]
     return sorted(merged, key=key)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# data-parallel training: replicas, per-replica BatchNorm statistics, gradients averaged over ranks
+# ---------------------------------------------------------------------------------------------------------------------
+def allreduce_gradients(flat_grad, bucket_elems=16 << 20):
+    """Sum the flat gradient buffer over all ranks (NCCL over NVLink on the GPU box; gloo in the CPU tests), in buckets of
+    `bucket_elems` elements issued asynchronously and waited on together.  Returns the factor that turns the sum into the
+    mean (1 / world) — the fused AdamW kernel applies it (grad_scale), so no extra pass over the gradients is needed."""
+    rank, ws = world()
+    if ws == 1:
+        return 1.0
+    handles = []
+    n = flat_grad.numel()
+    for lo in range(0, n, bucket_elems):
+        handles.append(dist.all_reduce(flat_grad[lo:min(n, lo + bucket_elems)], op=dist.ReduceOp.SUM, async_op=True))
+    for h in handles:
+        h.wait()
+    return 1.0 / ws
+
+
+def broadcast_parameters(flat_param, src=0):
+    """Make every replica start from rank `src`'s weights (flat parameter buffer, in place)."""
+    rank, ws = world()
+    if ws > 1:
+        dist.broadcast(flat_param, src=src)

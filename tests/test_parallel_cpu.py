@@ -50,3 +50,28 @@ def test_shard_is_deterministic_and_balanced():
         assert sorted(v for s in shards for v in s) == sorted(v for v, _ in VIDEOS)
         loads = [sum(n for v, n in VIDEOS if v in s) for s in shards]
         assert max(loads) - min(loads) <= 300
+
+
+def _grad_worker(rank, ws, port, out):
+    import torch
+    from tdeed_b200.parallel import allreduce_gradients, broadcast_parameters
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=ws)
+    g = torch.arange(1000, dtype=torch.float32) * (rank + 1)
+    scale = allreduce_gradients(g, bucket_elems=300)              # 4 buckets, the last one ragged
+    p = torch.full((10,), float(rank + 5))
+    broadcast_parameters(p, src=0)
+    out[rank] = (g.tolist(), scale, p.tolist())
+    dist.destroy_process_group()
+
+
+def test_data_parallel_gradient_allreduce_world2():
+    """DP training plumbing: bucketed all-reduce of the flat gradient (sum) + the 1/world factor for the fused AdamW."""
+    ws = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_grad_worker, args=(ws, _free_port(), out), nprocs=ws, join=True)
+    want = [3.0 * i for i in range(1000)]
+    for r in range(ws):
+        g, scale, p = out[r]
+        assert g == want and scale == 0.5 and p == [5.0] * 10
