@@ -63,6 +63,10 @@ long long tdeed_conv3_weight_image_elems(int c);
 int tdeed_conv3_weight_image(const float* weight, int c, int group_width, int transpose_flip, void* wimg, void* stream);
 int tdeed_conv3x3g_tc_raw_fwd(const void* in, int n, int h, int w, int c, int stride, const void* wimg, void* out,
                               void* stream);
+/* data gradient of the stride-2 conv on tcgen05: one stride-1 conv over the dy grid per input-pixel parity (py, px), weight
+ * images built with tdeed_conv3_weight_image(transpose_flip = 2 + 2*py + px) and stored back to back in wimgs; each scatters into
+ * dx [n, h, w, c] at pixels (2j+py, 2i+px). */
+int tdeed_conv3x3g_tc_bwd_data_s2(const void* dy, int n, int h, int w, int c, const void* wimgs, void* dx, void* stream);
 long long tdeed_conv3x3g_bwd_weight_workspace_floats(int n, int h, int w, int c, int group_width, int stride);
 int tdeed_conv3x3g_bwd_weight(int dtype, const void* x, const void* dy, int n, int h, int w, int c, int group_width,
                               int stride, float* dw, float* workspace, void* stream);

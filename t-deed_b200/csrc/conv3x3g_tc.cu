@@ -25,6 +25,7 @@ struct C3TParams {
   const float* bias;
   const uint8_t* wimg;       // [pairs_total][9][512 B] canonical UMMA B tiles
   int n, H, W, C, Ho, Wo, stride, relu;
+  int out_H, out_W, out_sy, out_sx, out_oy, out_ox;   // output tensor geometry: pixel (U-1, V-1) -> (sy*(U-1)+oy, sx*(V-1)+ox)
   int GH, GW, G;             // padded position grid per frame
   long long total_pos;
   int ntiles;
@@ -226,8 +227,9 @@ conv3x3g_tc_kernel(const C3TParams p) {
         const int f = Li / p.G;
         const int rem = Li - f * p.G;
         const int U = rem / p.GW, V = rem - U * p.GW;
-        ok = U >= 1 && U <= p.Ho && V >= 1 && V <= p.Wo;
-        obase = (((size_t)f * p.Ho + (U - 1)) * p.Wo + (V - 1)) * p.C + (size_t)pair0 * 16;
+        const int oy = p.out_sy * (U - 1) + p.out_oy, ox = p.out_sx * (V - 1) + p.out_ox;
+        ok = U >= 1 && U <= p.Ho && V >= 1 && V <= p.Wo && oy < p.out_H && ox < p.out_W;
+        obase = (((size_t)f * p.out_H + oy) * p.out_W + ox) * p.C + (size_t)pair0 * 16;
       }
       c3_wait(&tfull_bar[buf], (it >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -263,8 +265,10 @@ conv3x3g_tc_kernel(const C3TParams p) {
 
 }  // namespace tdeed
 
+struct C3TOut { int H, W, sy, sx, oy, ox; };
+
 static int conv3x3g_tc_run(const void* in, int n, int h, int w, int c, int stride, const void* wimg, const float* bias, int relu,
-                           void* out, void* stream) {
+                           void* out, void* stream, const C3TOut* og = nullptr) {
   using namespace tdeed;
   TDEED_REQUIRE(in && wimg && out, TDEED_ERR_SHAPE, "tdeed_conv3x3g_tc_fwd: null pointer");
   TDEED_REQUIRE(n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && (stride == 1 || stride == 2), TDEED_ERR_SHAPE,
@@ -273,6 +277,8 @@ static int conv3x3g_tc_run(const void* in, int n, int h, int w, int c, int strid
   p.in = (const __nv_bfloat16*)in; p.out = (__nv_bfloat16*)out; p.bias = bias; p.wimg = (const uint8_t*)wimg;
   p.n = n; p.H = h; p.W = w; p.C = c; p.stride = stride; p.relu = relu;
   p.Ho = (h + stride - 1) / stride; p.Wo = (w + stride - 1) / stride;
+  if (og) { p.out_H = og->H; p.out_W = og->W; p.out_sy = og->sy; p.out_sx = og->sx; p.out_oy = og->oy; p.out_ox = og->ox; }
+  else { p.out_H = p.Ho; p.out_W = p.Wo; p.out_sy = p.out_sx = 1; p.out_oy = p.out_ox = 0; }
   if (stride == 1) {
     p.GH = h + 2; p.GW = w + 2; p.nplanes = 1;
     for (int t = 0; t < 9; ++t) { p.tap_plane[t] = 0; p.tap_off[t] = (t / 3 - 1) * p.GW + (t % 3 - 1); }
@@ -343,6 +349,9 @@ extern "C" int tdeed_conv3x3g_tc_raw_fwd(const void* in, int n, int h, int w, in
 namespace tdeed {
 // fp32 weights [C][gw][3][3] -> bf16 UMMA B tiles [ceil(C/16)][9 taps][16 out][16 in], each tile in the canonical K-major
 // no-swizzle layout [n/8][k/8][n%8][k%8]; transpose_flip: tile(tap)[ci][co] = W[co][ci][8 - tap] (data-gradient kernel)
+// transpose_flip >= 2: parity kernels of the STRIDE-2 data gradient, (py, px) = ((mode-2) >> 1, (mode-2) & 1): the gradient at
+// input pixels (2j+py, 2i+px) is a stride-1 conv over the dy grid with taps at offsets {0} (parity 0: k = 1) or {0, +1}
+// (parity 1: k = 2, 0) per axis; unused taps are zero.
 __global__ void conv3_weight_image_kernel(const float* __restrict__ w, int C, int gw, int transpose_flip, __nv_bfloat16* __restrict__ img,
                                           int total) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -353,7 +362,14 @@ __global__ void conv3_weight_image_kernel(const float* __restrict__ w, int C, in
   float v = 0.f;
   if (cn < C && ck < C && cn / gw == ck / gw) {
     if (!transpose_flip) v = w[((size_t)cn * gw + (ck % gw)) * 9 + tap];
-    else v = w[((size_t)ck * gw + (cn % gw)) * 9 + (8 - tap)];
+    else if (transpose_flip == 1) v = w[((size_t)ck * gw + (cn % gw)) * 9 + (8 - tap)];
+    else {
+      const int py = (transpose_flip - 2) >> 1, px = (transpose_flip - 2) & 1;
+      const int a = tap / 3 - 1, b = tap % 3 - 1;                     // offsets on the dy grid
+      const int ky = py == 0 ? (a == 0 ? 1 : -1) : (a == 0 ? 2 : (a == 1 ? 0 : -1));
+      const int kx = px == 0 ? (b == 0 ? 1 : -1) : (b == 0 ? 2 : (b == 1 ? 0 : -1));
+      if (ky >= 0 && kx >= 0) v = w[((size_t)ck * gw + (cn % gw)) * 9 + ky * 3 + kx];
+    }
   }
   const int off = ((pair * 9 + tap) * 256) + ((nrow >> 3) * 2 + (k >> 3)) * 64 + (nrow & 7) * 8 + (k & 7);
   img[off] = __float2bfloat16_rn(v);
@@ -364,10 +380,26 @@ extern "C" long long tdeed_conv3_weight_image_elems(int c) { return (long long)(
 
 extern "C" int tdeed_conv3_weight_image(const float* weight, int c, int group_width, int transpose_flip, void* wimg, void* stream) {
   using namespace tdeed;
-  TDEED_REQUIRE(weight && wimg && c > 0 && (group_width == 8 || group_width == 16) && c % group_width == 0, TDEED_ERR_SHAPE,
-                "tdeed_conv3_weight_image: bad arguments");
+  TDEED_REQUIRE(weight && wimg && c > 0 && (group_width == 8 || group_width == 16) && c % group_width == 0 && transpose_flip >= 0 &&
+                transpose_flip <= 5, TDEED_ERR_SHAPE, "tdeed_conv3_weight_image: bad arguments");
   const int total = ((c + 15) / 16) * 9 * 256;
   conv3_weight_image_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(weight, c, group_width, transpose_flip,
                                                                                    (__nv_bfloat16*)wimg, total);
   return check_launch("tdeed_conv3_weight_image");
+}
+
+// Data gradient of the STRIDE-2 grouped conv on tcgen05: four stride-1 convolutions over the dy grid (one per input-pixel
+// parity, weight images built with tdeed_conv3_weight_image mode 2 + 2*py + px), each scattering into dx at (2j+py, 2i+px).
+// wimgs: the four images back to back (tdeed_conv3_weight_image_elems(c) elements each).  dx: NHWC [n, h, w, c] bf16.
+extern "C" int tdeed_conv3x3g_tc_bwd_data_s2(const void* dy, int n, int h, int w, int c, const void* wimgs, void* dx, void* stream) {
+  TDEED_REQUIRE(dy && wimgs && dx && n > 0 && h > 0 && w > 0, TDEED_ERR_SHAPE, "tdeed_conv3x3g_tc_bwd_data_s2: bad arguments");
+  const int oh = (h + 1) / 2, ow = (w + 1) / 2;
+  const long long img_bytes = tdeed_conv3_weight_image_elems(c) * 2;
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      C3TOut og{h, w, 2, 2, py, px};
+      int rc = conv3x3g_tc_run(dy, n, oh, ow, c, 1, (const uint8_t*)wimgs + (py * 2 + px) * img_bytes, nullptr, 0, dx, stream, &og);
+      if (rc) return rc;
+    }
+  return TDEED_OK;
 }

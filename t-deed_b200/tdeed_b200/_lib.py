@@ -93,6 +93,7 @@ SIGNATURES.update({
     'tdeed_conv3_weight_image_elems': (c_ll, [c_int]),
     'tdeed_conv3_weight_image': (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp]),
     'tdeed_conv3x3g_tc_raw_fwd': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
+    'tdeed_conv3x3g_tc_bwd_data_s2': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     'tdeed_conv3x3g_bwd_data': (c_int, [c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     'tdeed_conv3x3g_bwd_weight_workspace_floats': (c_ll, [c_int, c_int, c_int, c_int, c_int, c_int]),
     'tdeed_conv3x3g_bwd_weight': (c_int, [c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),

@@ -309,6 +309,8 @@ class TrainEngine:
         T.conv3x3g_bwd_weight(z1, dy2, self.gw, stride, out=G[p + '.conv2.conv.weight'])
         if self.adt == torch.bfloat16 and stride == 1:   # data gradient = the same tcgen05 conv with the transposed, flipped kernel
             dz1 = T.conv3x3g_tc_raw(dy2, T.conv3_weight_image(P[p + '.conv2.conv.weight'], self.gw, transpose_flip=True), 1)
+        elif self.adt == torch.bfloat16 and stride == 2:  # four parity convolutions over the dy grid, scattered into dx
+            dz1 = T.conv3x3g_tc_bwd_data_s2(dy2, (n, h, w, cout), P[p + '.conv2.conv.weight'], self.gw)
         else:
             dz1 = T.conv3x3g_bwd_data(dy2, (n, h, w, cout), P[p + '.conv2.conv.weight'], self.gw, stride)
         # conv1 (+BN+ReLU)

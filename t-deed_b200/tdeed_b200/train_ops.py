@@ -133,6 +133,19 @@ def conv3x3g_tc_raw(x, wimg, stride):
     return out
 
 
+def conv3x3g_tc_bwd_data_s2(dy, in_shape, weight, group_width):
+    """bf16 data gradient of the stride-2 grouped conv on tcgen05 (four parity convolutions over the dy grid)."""
+    n, h, w, c = in_shape
+    elems = int(L.load().tdeed_conv3_weight_image_elems(c))
+    imgs = torch.empty(4 * elems, dtype=torch.bfloat16, device=dy.device)
+    for q in range(4):
+        L.check(L.load().tdeed_conv3_weight_image(L.ptr(weight), c, group_width, 2 + q, imgs.data_ptr() + 2 * q * elems, L.stream()),
+                'conv3_weight_image')
+    dx = torch.empty(in_shape, dtype=dy.dtype, device=dy.device)
+    L.check(L.load().tdeed_conv3x3g_tc_bwd_data_s2(L.ptr(dy), n, h, w, c, L.ptr(imgs), L.ptr(dx), L.stream()), 'conv3x3g_tc_bwd_data_s2')
+    return dx
+
+
 def conv3x3g_bwd_data(dy, in_shape, weight, group_width, stride):
     n, h, w, c = in_shape
     dx = torch.empty(in_shape, dtype=dy.dtype, device=dy.device)

@@ -179,7 +179,8 @@ def test_stem_raw_and_weight_grad(unit):
     assert rel(dw, wr.grad) < 1e-4
 
 
-@pytest.mark.parametrize('c,gw,stride,h,w', [(24, 8, 2, 32, 32), (56, 8, 1, 17, 23), (64, 16, 2, 30, 45), (320, 16, 1, 7, 7), (368, 8, 1, 7, 7)])
+@pytest.mark.parametrize('c,gw,stride,h,w', [(24, 8, 2, 32, 32), (56, 8, 1, 17, 23), (64, 16, 2, 30, 45), (320, 16, 1, 7, 7), (368, 8, 1, 7, 7),
+                                              (128, 16, 2, 13, 9)])
 def test_conv3x3g_train(c, gw, stride, h, w):
     g = torch.Generator(device=DEV).manual_seed(c + h)
     n = 6
@@ -213,6 +214,11 @@ def test_conv3x3g_train(c, gw, stride, h, w):
         dq = dy.bfloat16().float()
         dxq = torch.nn.grad.conv2d_input(x.shape, wb, dq, stride=1, padding=1, groups=c // gw)
         dxt = T().conv3x3g_tc_raw(nhwc(dy).bfloat16(), T().conv3_weight_image(wgt, gw, transpose_flip=True), 1)
+        assert rel(nchw(dxt.float()), dxq) < 1e-2
+    else:
+        dq = dy.bfloat16().float()
+        dxq = torch.nn.grad.conv2d_input(x.shape, wb, dq, stride=2, padding=1, groups=c // gw)
+        dxt = T().conv3x3g_tc_bwd_data_s2(nhwc(dy).bfloat16(), (n, h, w, c), wgt, gw)
         assert rel(nchw(dxt.float()), dxq) < 1e-2
 
 
