@@ -325,36 +325,38 @@ class TDEEDModel(BaseRGBModel):
             ce_kwargs['weight'] = torch.FloatTensor([1] + [fg_weight] * (self._num_classes - 1)).to(self.device)
 
         epoch_loss = 0.
+        epoch_loss_dev = None
         with torch.no_grad() if optimizer is None else nullcontext():
             for batch_idx, batch in enumerate(tqdm(loader)):
-                frame = batch['frame'].to(self.device)          # kept uint8: the stem kernel normalises
-                label = batch['label'].to(self.device)
+                frame = batch['frame'].to(self.device, non_blocking=True)          # kept uint8: the stem kernel normalises
+                label = batch['label'].to(self.device, non_blocking=True)
 
                 if self._model._double_head:
                     batch_dataset = batch['dataset']
                     label = update_labels_2heads(label, batch_dataset, self._args.num_classes)
 
                 if 'labelD' in batch.keys():
-                    labelD = batch['labelD'].to(self.device).float()
+                    labelD = batch['labelD'].to(self.device, non_blocking=True).float()
 
                 if 'frame2' in batch.keys():
-                    frame = frame.float()
-                    frame2 = batch['frame2'].to(self.device).float()
-                    label2 = batch['label2'].to(self.device)
+                    # mixup (model/model.py:228-254 of the reference), same arithmetic — fl32(l)*frame + fl32(1-l)*frame2 and the
+                    # two label adds in the same order — but batched and free of host syncs (the reference's per-clip
+                    # `label_dist[i, range(T), label[i]] += l[i]` uploads an index tensor from pageable memory every clip,
+                    # which drains the stream)
+                    frame2 = batch['frame2'].to(self.device, non_blocking=True).float()
+                    label2 = batch['label2'].to(self.device, non_blocking=True)
+                    nb = frame2.shape[0]
+                    l = [random.betavariate(0.2, 0.2) for _ in range(nb)]
+                    lam = torch.tensor([[v, 1 - v] for v in l], dtype=torch.float64).float().pin_memory().to(self.device, non_blocking=True)
+                    la, lb = lam[:, 0], lam[:, 1]
+                    frame = la.view(nb, 1, 1, 1, 1) * frame.float() + lb.view(nb, 1, 1, 1, 1) * frame2
+                    label_dist = torch.zeros((label.shape[0], label.shape[1], self._num_classes), device=self.device)
+                    label_dist.scatter_add_(2, label.unsqueeze(2), la.view(nb, 1, 1).expand(-1, label.shape[1], 1).contiguous())
+                    label_dist.scatter_add_(2, label2.unsqueeze(2), lb.view(nb, 1, 1).expand(-1, label.shape[1], 1).contiguous())
                     if 'labelD2' in batch.keys():
-                        labelD2 = batch['labelD2'].to(self.device).float()
-                        labelD_dist = torch.zeros((labelD.shape[0], label.shape[1])).to(self.device)
-                    l = [random.betavariate(0.2, 0.2) for _ in range(frame2.shape[0])]
-                    label_dist = torch.zeros((label.shape[0], label.shape[1], self._num_classes)).to(self.device)
-                    for i in range(frame2.shape[0]):
-                        frame[i] = l[i] * frame[i] + (1 - l[i]) * frame2[i]
-                        label_dist[i, range(label.shape[1]), label[i]] += l[i]
-                        label_dist[i, range(label2.shape[1]), label2[i]] += 1 - l[i]
-                        if 'labelD2' in batch.keys():
-                            labelD_dist[i] = l[i] * labelD[i] + (1 - l[i]) * labelD2[i]
+                        labelD2 = batch['labelD2'].to(self.device, non_blocking=True).float()
+                        labelD = la.view(nb, 1) * labelD + lb.view(nb, 1) * labelD2
                     label = label_dist
-                    if 'labelD2' in batch.keys():
-                        labelD = labelD_dist
 
                 if valMAP:
                     labels_aux = process_labels(label, labelD if 'labelD' in batch.keys() else None,
@@ -387,7 +389,8 @@ class TDEEDModel(BaseRGBModel):
                         if lr_scheduler is not None:
                             lr_scheduler.step()
                         optimizer.zero_grad()
-                    epoch_loss += float(loss_dev[0])
+                    # no host sync per step: the loss stays on the device until the end of the epoch
+                    epoch_loss_dev = loss_dev[0].clone() if epoch_loss_dev is None else epoch_loss_dev + loss_dev[0]
                     continue
 
                 with torch.autocast('cuda', dtype=torch.bfloat16):
@@ -429,6 +432,8 @@ class TDEEDModel(BaseRGBModel):
 
                 epoch_loss += loss.detach().item()
 
+        if epoch_loss_dev is not None:
+            epoch_loss += float(epoch_loss_dev)
         if valMAP:
             return epoch_loss / len(loader), torch.cat(map_labels, 0), torch.cat(map_preds, 0)
         return epoch_loss / len(loader)
