@@ -140,6 +140,13 @@ int tdeed_linear_bwd_data(const float* dout, int ldd, int M, int C, const float*
 int tdeed_ce_mse_loss(const float* logits, int M, int K, int ld_logits, const long long* target_hard,
                       const float* target_soft, const float* class_weight, const float* displ, const float* labelD,
                       float* loss_out, float* dlogits, float* ddispl, void* stream);
+/* joint-dataset double head (model/model.py:278-306): dataset int32 [B] in {1, 2} selects head 1 (columns [0, n1)) or head 2
+ * ([n1, n1+n2)) per sample; per-sample cross entropy (class_weight[:k]) over its T rows, summed / B; int64 targets of dataset-2
+ * samples are shifted by n1 as update_labels_2heads leaves them; soft targets are [B*T, n1+n2].  dlogits: [B*T, n1+n2]. */
+int tdeed_ce_mse_loss_2heads(const float* logits, int B, int T, int n1, int n2, int ld_logits, const int* dataset,
+                             const long long* target_hard, const float* target_soft, const float* class_weight,
+                             const float* displ, const float* labelD, float* loss_out, float* dlogits, float* ddispl,
+                             void* stream);
 /* torch.optim.AdamW single step on a flat fp32 buffer; g is multiplied by grad_scale first; shadow_bf16 (nullable)
  * receives the bf16 copy of the updated weights. */
 int tdeed_adamw_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1, double beta2,

@@ -137,6 +137,87 @@ ce_mse_loss_kernel(const float* __restrict__ logits, int M, int K, int ld, const
   }
 }
 
+// Joint-dataset ("double head") loss of model/model.py:278-306: sample b uses head 1 (columns [0, n1)) when dataset[b] == 1 and
+// head 2 (columns [n1, n1+n2)) when dataset[b] == 2; per sample F.cross_entropy(weight = cw[:k]) over its T rows (weighted mean
+// for int64 targets — already shifted by n1 for dataset 2, as update_labels_2heads does — mean over rows for soft targets),
+// summed over samples and divided by B; + MSE on the displacement over all rows.  Single CTA.
+__global__ void __launch_bounds__(256)
+ce_mse_loss_2h_kernel(const float* __restrict__ logits, int B, int T, int n1, int n2, int ld, const int* __restrict__ dataset,
+                      const long long* __restrict__ hard, const float* __restrict__ soft, const float* __restrict__ cw,
+                      const float* __restrict__ displ, const float* __restrict__ labelD, float* __restrict__ out,
+                      float* __restrict__ dlogits, float* __restrict__ ddispl) {
+  __shared__ float s_red[32];
+  const int K = n1 + n2, M = B * T;
+  float total = 0.f;
+  for (int b = 0; b < B; ++b) {
+    const int ds = dataset[b];
+    const int c0 = ds == 2 ? n1 : 0, k = ds == 2 ? n2 : n1;
+    float lsum = 0.f, wsum = 0.f;
+    if (ds == 1 || ds == 2) {
+      for (int t = threadIdx.x; t < T; t += 256) {
+        const int m = b * T + t;
+        const float* z = logits + (size_t)m * ld + c0;
+        float mx = z[0];
+        for (int j = 1; j < k; ++j) mx = fmaxf(mx, z[j]);
+        float se = 0.f;
+        for (int j = 0; j < k; ++j) se += expf(z[j] - mx);
+        const float lse = mx + logf(se);
+        if (hard) {
+          const int y = (int)hard[m] - c0;
+          const float w = cw ? cw[y] : 1.f;
+          lsum += w * (lse - z[y]);
+          wsum += w;
+        } else {
+          float a = 0.f;
+          for (int j = 0; j < k; ++j) a = fmaf((cw ? cw[j] : 1.f) * soft[(size_t)m * K + c0 + j], lse - z[j], a);
+          lsum += a;
+        }
+      }
+    }
+    lsum = block_sum(lsum, s_red);
+    wsum = block_sum(wsum, s_red);
+    const float denom = (hard ? wsum : (float)T) * (float)B;
+    if (ds == 1 || ds == 2) total += lsum / denom;
+    for (int t = threadIdx.x; t < T; t += 256) {
+      const int m = b * T + t;
+      float* dz = dlogits + (size_t)m * K;
+      for (int j = 0; j < K; ++j) dz[j] = 0.f;
+      if (ds != 1 && ds != 2) continue;
+      const float* z = logits + (size_t)m * ld + c0;
+      float mx = z[0];
+      for (int j = 1; j < k; ++j) mx = fmaxf(mx, z[j]);
+      float se = 0.f;
+      for (int j = 0; j < k; ++j) se += expf(z[j] - mx);
+      const float inv = 1.f / se;
+      if (hard) {
+        const int y = (int)hard[m] - c0;
+        const float w = (cw ? cw[y] : 1.f) / denom;
+        for (int j = 0; j < k; ++j) dz[c0 + j] = w * (expf(z[j] - mx) * inv - (j == y ? 1.f : 0.f));
+      } else {
+        float tw = 0.f;
+        for (int j = 0; j < k; ++j) tw = fmaf(cw ? cw[j] : 1.f, soft[(size_t)m * K + c0 + j], tw);
+        for (int j = 0; j < k; ++j)
+          dz[c0 + j] = (expf(z[j] - mx) * inv * tw - (cw ? cw[j] : 1.f) * soft[(size_t)m * K + c0 + j]) / denom;
+      }
+    }
+  }
+  float msum = 0.f;
+  if (displ) {
+    for (int m = threadIdx.x; m < M; m += 256) {
+      const float d = displ[m] - labelD[m];
+      msum = fmaf(d, d, msum);
+      ddispl[m] = 2.f * d / (float)M;
+    }
+  }
+  msum = block_sum(msum, s_red);
+  if (threadIdx.x == 0) {
+    const float mse = displ ? msum / (float)M : 0.f;
+    out[0] = total + mse;
+    out[1] = total;
+    out[2] = mse;
+  }
+}
+
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                              long long n, float lr, float beta1, float beta2, float eps, float wd, float bc1, float bc2_sqrt,
                              float grad_scale, __nv_bfloat16* __restrict__ shadow) {
@@ -208,6 +289,19 @@ extern "C" int tdeed_ce_mse_loss(const float* logits, int M, int K, int ld_logit
   ce_mse_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, M, K, ld_logits, target_hard, target_soft, class_weight, displ,
                                                           labelD, loss_out, dlogits, ddispl);
   return check_launch("tdeed_ce_mse_loss");
+}
+
+extern "C" int tdeed_ce_mse_loss_2heads(const float* logits, int B, int T, int n1, int n2, int ld_logits, const int* dataset,
+                                        const long long* target_hard, const float* target_soft, const float* class_weight,
+                                        const float* displ, const float* labelD, float* loss_out, float* dlogits, float* ddispl,
+                                        void* stream) {
+  TDEED_REQUIRE(logits && dataset && loss_out && dlogits && B > 0 && T > 0 && n1 > 0 && n2 > 0 && ld_logits >= n1 + n2, TDEED_ERR_SHAPE,
+                "tdeed_ce_mse_loss_2heads: bad arguments");
+  TDEED_REQUIRE((target_hard != nullptr) != (target_soft != nullptr), TDEED_ERR_SHAPE, "tdeed_ce_mse_loss_2heads: exactly one of hard / soft targets");
+  TDEED_REQUIRE(!displ || (labelD && ddispl), TDEED_ERR_SHAPE, "tdeed_ce_mse_loss_2heads: displacement needs labelD and ddispl");
+  ce_mse_loss_2h_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, B, T, n1, n2, ld_logits, dataset, target_hard, target_soft,
+                                                             class_weight, displ, labelD, loss_out, dlogits, ddispl);
+  return check_launch("tdeed_ce_mse_loss_2heads");
 }
 
 extern "C" int tdeed_adamw_step(float* p, const float* g, float* m, float* v, long long n, double lr, double beta1, double beta2,

@@ -132,7 +132,7 @@ class TDEEDModel(BaseRGBModel):
             return eng
 
         def train_step(self, frame, label, labelD=None, fg_weight=5, grad_scale=1.0, accumulate=False, precision='bf16',
-                       dropout_p=None, use_graph=None):
+                       dropout_p=None, use_graph=None, dataset=None):
             """Forward (train mode) + loss + backward on the sm_100a kernels (model/model.py:262-324 of the reference).
             frame: (B,T,3,H,W) uint8 | float valued 0..255, already mixed up.  label: int64 (B*T) | float (B*T, K).
             Gradients of grad_scale * loss land in p.grad (added to the existing ones when accumulate).  Returns the
@@ -164,22 +164,29 @@ class TDEEDModel(BaseRGBModel):
             frame = frame.contiguous()
             self._train_calls += 1
             if dropout_p is None:            # nn.Dropout() of the FC heads (model/modules.py:366-376): p = 0.5 in train mode
-                dropout_p = float(self._pred_fine.dropout.p) if self.training else 0.0
+                head = self._pred_fine._fc1 if self._double_head else self._pred_fine
+                dropout_p = float(head.dropout.p) if self.training else 0.0
             hard = label.reshape(-1).contiguous() if not label.dtype.is_floating_point else None
             soft = label.float().contiguous() if label.dtype.is_floating_point else None
             use_d = labelD is not None and self._radi_displacement > 0
             labD = labelD.reshape(-1).float().contiguous() if use_d else None
 
+            ds_dev = None
+            if self._double_head:
+                if dataset is None:
+                    raise ValueError("double-head training needs batch['dataset'] (1 | 2 per clip)")
+                ds_dev = torch.as_tensor(dataset, dtype=torch.int32).reshape(-1).to(frame.device)
+
             def run(fr, hd, sf, ld, grads):
                 eng.G = grads
                 logits, displ = eng.forward(fr, (cy, cx, ch, cw), unit_input=unit, dropout_p=dropout_p)
-                loss = eng.loss(logits, displ, hd, sf, ld, fg_weight=fg_weight)
+                loss = eng.loss(logits, displ, hd, sf, ld, fg_weight=fg_weight, dataset=ds_dev)
                 eng.backward()
                 return loss, logits, displ
 
             direct = not accumulate and grad_scale == 1.0
             if use_graph is None:
-                use_graph = self.use_train_graph
+                use_graph = self.use_train_graph and not self._double_head     # (dataset ids are not a static graph input yet)
             if use_graph:
                 # CUDA graph of forward + loss + backward for this (shapes, crop, dtypes) signature: ~3500 launches replayed
                 # with one host call.  Inputs are copied into static buffers; gradients land in a static buffer.
@@ -273,6 +280,9 @@ class TDEEDModel(BaseRGBModel):
             self._double_head = True
             self._engines.clear()
             self.__dict__.pop('_tracked', None)
+            self._flat = None                  # the parameter set changed: re-home on the next training step
+            self._train_engines.clear()
+            self._train_graphs.clear()
 
         def print_stats(self):
             print('Model params:', sum(p.numel() for p in self.parameters()))
@@ -369,12 +379,11 @@ class TDEEDModel(BaseRGBModel):
                     # training: forward (train mode) + loss + backward are sm_100a kernels (tdeed_b200/train_engine.py);
                     # the reference's `step(optimizer, scaler, loss / acc_grad_iter, ...)` (model/modules.py:388-401)
                     # becomes gradient accumulation into p.grad + optimizer.step()
-                    if self._model._double_head:
-                        raise NotImplementedError('tdeed_b200: joint-dataset (double head) training is not built yet')
                     first = batch_idx % acc_grad_iter == 0
                     loss_dev = self._model.train_step(frame, label, labelD if 'labelD' in batch.keys() else None,
                                                       fg_weight=fg_weight, grad_scale=1.0 / acc_grad_iter,
-                                                      accumulate=not first, precision=self.train_precision)
+                                                      accumulate=not first, precision=self.train_precision,
+                                                      dataset=batch_dataset if self._model._double_head else None)
                     if valMAP:
                         logits, displ = self._model._last_train
                         map_preds.append((process_prediction(logits, displ) if displ is not None

@@ -123,6 +123,8 @@ SIGNATURES.update({
     'tdeed_linear_fwd': (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_int, c_vp]),
     'tdeed_linear_bwd_data': (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp]),
     'tdeed_ce_mse_loss': (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'tdeed_ce_mse_loss_2heads': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp,
+                                         c_vp]),
     'tdeed_adamw_step': (c_int, [c_vp, c_vp, c_vp, c_vp, c_ll, c_double, c_double, c_double, c_double, c_double, c_int,
                                  c_float, c_vp, c_vp]),
     'tdeed_axpy': (c_int, [c_vp, c_float, c_ll, c_vp, c_vp]),

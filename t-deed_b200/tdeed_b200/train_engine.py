@@ -24,8 +24,6 @@ class TrainEngine:
         if not torch.cuda.is_available():
             raise RuntimeError('tdeed_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
         L.load()
-        if cfg.double_head:
-            raise NotImplementedError('training with the joint-dataset double head (model/model.py:278-306) is not built yet')
         if cfg.shift_mode not in ('gsf', 'gsm'):
             raise NotImplementedError('training needs a gate-shift backbone (rny00X_gsf / _gsm)')
         self.cfg = cfg
@@ -87,7 +85,18 @@ class TrainEngine:
         else:
             xin = o2
         hd['x_c'] = xin
-        logits = T.linear_fwd(xin, P['_pred_fine._fc_out.weight'], P['_pred_fine._fc_out.bias'])
+        if cfg.double_head:              # FC2Layers: cat(fc1(drop(x)), fc2(drop(x))), one Dropout per head (model/modules.py:378-387)
+            n1, n2 = cfg.double_head
+            if dropout_p > 0:
+                x2, hd['mask_c2'] = T.dropout_fwd_devseed(o2, dropout_p, self.seed_dev, 2)
+            else:
+                x2 = o2
+            hd['x_c2'] = x2
+            logits = torch.empty((n, n1 + n2), dtype=torch.float32, device=o2.device)
+            T.linear_fwd(xin, P['_pred_fine._fc1._fc_out.weight'], P['_pred_fine._fc1._fc_out.bias'], out=logits, col0=0)
+            T.linear_fwd(x2, P['_pred_fine._fc2._fc_out.weight'], P['_pred_fine._fc2._fc_out.bias'], out=logits, col0=n1)
+        else:
+            logits = T.linear_fwd(xin, P['_pred_fine._fc_out.weight'], P['_pred_fine._fc_out.bias'])
         displ = None
         if cfg.radi_displacement > 0:
             if dropout_p > 0:
@@ -226,7 +235,8 @@ class TrainEngine:
         return x
 
     # ------------------------------------------------------------------ loss
-    def loss(self, logits, displ, target_hard=None, target_soft=None, labelD=None, fg_weight=5):
+    def loss(self, logits, displ, target_hard=None, target_soft=None, labelD=None, fg_weight=5, dataset=None):
+        """dataset: int32 device tensor [B] in {1, 2} — required for the joint-dataset double head (model/model.py:278-306)."""
         k = logits.shape[1]
         cw = None
         if fg_weight != 1:
@@ -234,7 +244,14 @@ class TrainEngine:
             if cw is None:
                 cw = torch.tensor([1.0] + [float(fg_weight)] * (k - 1), dtype=torch.float32).to(logits.device)
                 self._class_weights[(k, fg_weight)] = cw
-        loss, dlogits, ddispl = T.ce_mse_loss(logits, target_hard, target_soft, cw, displ, labelD if displ is not None else None)
+        if self.cfg.double_head:
+            if dataset is None:
+                raise ValueError("double-head training needs batch['dataset'] (1 | 2 per clip)")
+            n1, n2 = self.cfg.double_head
+            loss, dlogits, ddispl = T.ce_mse_loss_2heads(logits, self.tape['b'], self.tape['t'], n1, n2, dataset, target_hard,
+                                                          target_soft, cw, displ, labelD if displ is not None else None)
+        else:
+            loss, dlogits, ddispl = T.ce_mse_loss(logits, target_hard, target_soft, cw, displ, labelD if displ is not None else None)
         self.tape['dlogits'], self.tape['ddispl'] = dlogits, ddispl
         return loss
 
@@ -247,11 +264,24 @@ class TrainEngine:
         hd = tape['heads']
         dlogits, ddispl = tape['dlogits'], tape['ddispl']
         k = dlogits.shape[1]
-        T.gemm_tn(dlogits, hd['x_c'], k, d, n, out=G['_pred_fine._fc_out.weight'])
-        T.colsum(dlogits, out=G['_pred_fine._fc_out.bias'])
-        dx = T.linear_bwd_data(dlogits, P['_pred_fine._fc_out.weight'])
-        if hd['p'] > 0:
-            dx = T.dropout_bwd(dx, hd['mask_c'], hd['p'])
+        if cfg.double_head:
+            n1, n2 = cfg.double_head
+            dx = None
+            for j, (c0, nj, xk, mk) in enumerate(((0, n1, 'x_c', 'mask_c'), (n1, n2, 'x_c2', 'mask_c2'))):
+                pj = '_pred_fine._fc%d._fc_out' % (j + 1)
+                dl = dlogits[:, c0:c0 + nj]
+                T.gemm_tn(dl, hd[xk], nj, d, n, out=G[pj + '.weight'])
+                T.colsum(dl, out=G[pj + '.bias'])
+                if hd['p'] > 0:
+                    dx = T.dropout_bwd(T.linear_bwd_data(dlogits, P[pj + '.weight'], col0=c0, n=nj), hd[mk], hd['p'], add=dx)
+                else:
+                    dx = T.linear_bwd_data(dlogits, P[pj + '.weight'], add=dx, col0=c0, n=nj)
+        else:
+            T.gemm_tn(dlogits, hd['x_c'], k, d, n, out=G['_pred_fine._fc_out.weight'])
+            T.colsum(dlogits, out=G['_pred_fine._fc_out.bias'])
+            dx = T.linear_bwd_data(dlogits, P['_pred_fine._fc_out.weight'])
+            if hd['p'] > 0:
+                dx = T.dropout_bwd(dx, hd['mask_c'], hd['p'])
         if ddispl is not None:
             dd2 = ddispl.view(n, 1)
             T.gemm_tn(dd2, hd['x_d'], 1, d, n, out=G['_pred_displ._fc_out.weight'])

@@ -378,6 +378,18 @@ def ce_mse_loss(logits, target_hard, target_soft, class_weight, displ, labelD):
     return loss, dlogits, ddispl
 
 
+def ce_mse_loss_2heads(logits, B, T, n1, n2, dataset, target_hard, target_soft, class_weight, displ, labelD):
+    """logits [B*T, n1+n2] fp32; dataset int32 [B].  -> (loss[3], dlogits [B*T, n1+n2], ddispl | None)."""
+    dev = logits.device
+    loss = torch.empty(3, dtype=torch.float32, device=dev)
+    dlogits = torch.empty((B * T, n1 + n2), dtype=torch.float32, device=dev)
+    ddispl = torch.empty(B * T, dtype=torch.float32, device=dev) if displ is not None else None
+    L.check(L.load().tdeed_ce_mse_loss_2heads(L.ptr(logits), B, T, n1, n2, logits.stride(0), L.ptr(dataset), L.ptr(target_hard),
+                                              L.ptr(target_soft), L.ptr(class_weight), L.ptr(displ), L.ptr(labelD), L.ptr(loss),
+                                              L.ptr(dlogits), L.ptr(ddispl), L.stream()), 'ce_mse_loss_2heads')
+    return loss, dlogits, ddispl
+
+
 def adamw_step_(p, g, m, v, lr, betas, eps, weight_decay, step, grad_scale=1.0, shadow=None):
     L.check(L.load().tdeed_adamw_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), lr, betas[0], betas[1], eps, weight_decay,
                                       step, grad_scale, L.ptr(shadow), L.stream()), 'adamw_step')

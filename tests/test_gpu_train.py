@@ -204,3 +204,107 @@ def test_train_step_cuda_graph_equals_eager(golden_dir):
     assert len(ent) == 1 and 'graph' in ent[0]
     # running statistics advanced exactly once since the last reset
     assert int(m.state_dict()['_features.stem.bn.num_batches_tracked']) == int(buffers0['_features.stem.bn.num_batches_tracked']) + 1
+
+
+@pytest.mark.parametrize('soft', [False, True])
+def test_double_head_joint_training_step(soft):
+    """Joint-dataset training with the double head (model/model.py:278-306, train_tdeed.py:145-148): per-sample head selection
+    by batch['dataset'], update_labels_2heads label shift, FC2Layers with one dropout per head.  Checked against autograd of the
+    oracle network + the reference's loss loop restated in torch, in float64."""
+    import torch.nn.functional as F
+    n1, n2 = 5, 7
+    cfg = O.Config(feature_arch='rny002_gsf', clip_len=8, n_layers=2, sgp_ks=5, sgp_r=4, num_classes=n1 - 1, radi_displacement=2,
+                   crop_dim=None, double_head=[n1, n2])
+    sd = O.random_state(cfg, 9)
+    import contextlib
+    import io
+    from model.model import TDEEDModel, update_labels_2heads
+    args = _args(cfg)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = TDEEDModel(device='cuda', args=args)
+    m._model.update_pred_head([n1, n2])
+    m._num_classes = n1 + n2
+    m.load(sd)
+    m._model.augmentation = torch.nn.Identity()
+    for mod in m._model.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    m._model.train()
+    gen = torch.Generator().manual_seed(3)
+    B, T_ = 3, 8
+    frames = torch.randint(0, 256, (B, T_, 3, 64, 64), generator=gen, dtype=torch.uint8)
+    dataset = [1, 2, 2]
+    label = torch.stack([torch.randint(0, n1 if d == 1 else n2, (T_,), generator=gen) for d in dataset])
+    labelD = torch.randint(-2, 3, (B, T_), generator=gen).float()
+    label = update_labels_2heads(label.clone(), dataset, n1 - 1)
+    K = n1 + n2
+    if soft:
+        onehot = F.one_hot(label, K).float()
+        other = F.one_hot(update_labels_2heads(torch.stack([torch.randint(0, n1 if d == 1 else n2, (T_,), generator=gen)
+                                                             for d in dataset]), dataset, n1 - 1), K).float()
+        target = 0.7 * onehot + 0.3 * other
+        lab_in = target.reshape(-1, K).cuda()
+    else:
+        target = label
+        lab_in = label.reshape(-1).cuda()
+    loss = m._model.train_step(frames.cuda(), lab_in, labelD.cuda(), fg_weight=5, precision='fp32', dataset=dataset)
+    # float64 reference: oracle network + the reference's per-sample loss loop
+    s64 = {k: (v.cuda().double().requires_grad_(True) if v.dtype.is_floating_point and 'running' not in k else v.cuda())
+           for k, v in sd.items()}
+    logits, displ = O.forward(s64, cfg, frames.cuda().double(), train=True)
+    w = torch.tensor([1.] + [5.] * (K - 1), dtype=torch.float64, device='cuda')
+    ref = 0.
+    for i in range(B):
+        if dataset[i] == 1:
+            tgt = target[i][:, :n1] if soft else target[i]
+            ref = ref + F.cross_entropy(logits[i][:, :n1], tgt.cuda().double() if soft else tgt.cuda(), weight=w[:n1]) / B
+        else:
+            tgt = target[i][:, n1:] if soft else target[i] - n1
+            ref = ref + F.cross_entropy(logits[i][:, n1:], tgt.cuda().double() if soft else tgt.cuda(), weight=w[:n2]) / B
+    ref = ref + F.mse_loss(displ, labelD.cuda().double(), reduction='none').mean()
+    ref.backward()
+    assert abs(float(loss[0]) - float(ref)) < 1e-4 * max(1.0, abs(float(ref)))
+    for name in ('_pred_fine._fc1._fc_out.weight', '_pred_fine._fc2._fc_out.weight', '_pred_fine._fc2._fc_out.bias',
+                 '_pred_displ._fc_out.weight', '_temp_fine._sgp.4.mlp.2.weight', '_temp_fine._sgpMixer.0.concat_fc.weight'):
+        got = dict(m._model.named_parameters())[name].grad
+        assert rel_err(got.double().cpu().numpy(), s64[name].grad.cpu().numpy()) < 2e-3, name
+    # and through epoch() with the reference's batch schema
+    batch = {'frame': frames, 'label': update_labels_2heads(label.clone(), dataset, -1 - n1) if False else
+             torch.stack([label[i] - (n1 if dataset[i] == 2 else 0) for i in range(B)]), 'labelD': labelD.long(), 'dataset': dataset}
+    m.train_precision = 'fp32'
+    m._args.num_classes = n1 - 1
+
+    class Recording:
+        def zero_grad(self):
+            pass
+
+        def step(self):
+            pass
+
+    if not soft:
+        l2 = m.epoch([batch], optimizer=Recording(), scaler=None, fg_weight=5)
+        assert abs(l2 - float(ref)) < 2e-3 * max(1.0, abs(float(ref)))      # (BN running stats moved once in between: loss identical)
+
+
+def test_train_step_gsm_backbone_vs_f64_oracle():
+    """GSM variant (model/impl/gsm.py) end to end: no golden (the reference's _GSM needs CUDA tensors to even run), so the
+    check is against autograd of the float64 oracle with the same noise-floor rule as the GSF cases."""
+    cfg = O.Config(feature_arch='rny002_gsm', clip_len=10, n_layers=2, sgp_ks=5, sgp_r=2, num_classes=3, radi_displacement=0,
+                   crop_dim=None)
+    sd = O.random_state(cfg, 11)
+    gen = torch.Generator().manual_seed(5)
+    frames = torch.randint(0, 256, (2, 10, 3, 64, 64), generator=gen, dtype=torch.uint8).float()
+    label = torch.randint(0, 4, (2, 10), generator=gen)
+    m = _model(cfg, sd)
+    m._model.train()
+    loss = m._model.train_step(frames.cuda(), label.cuda().reshape(-1), None, fg_weight=5, precision='fp32')
+    l64, logits64, g64, _ = _oracle_grads(sd, cfg, frames, label, None, torch.float64)
+    _, _, g32, _ = _oracle_grads(sd, cfg, frames, label, None, torch.float32)
+    assert abs(float(loss[0]) - l64) < 1e-4 * max(1.0, abs(l64))
+    mine = {n: p.grad for n, p in m._model.named_parameters()}
+    e_ref = {n: rel_err(g32[n].double().cpu().numpy(), g64[n].cpu().numpy()) for n in g64 if g64[n].numel() >= 16}
+    e_mine = {n: rel_err(mine[n].double().cpu().numpy(), g64[n].cpu().numpy()) for n in g64 if g64[n].numel() >= 16}
+    worst = max(e_mine, key=e_mine.get)
+    print('gsm: floor %.2e, kernels worst %.2e (%s), median %.2e' % (max(e_ref.values()), e_mine[worst], worst,
+                                                                     float(np.median(list(e_mine.values())))))
+    assert e_mine[worst] <= 4 * max(e_ref.values()) + 1e-4
