@@ -240,7 +240,8 @@ def test_gate_shift(dev, mode, fold, c, hw):
     assert rel_err(got, ref) < 2e-5
 
 
-@pytest.mark.parametrize('c,t_in,t_out,ks,r', [(368, 25, 25, 7, 4), (368, 25, 13, 5, 4), (768, 100, 50, 9, 4), (368, 13, 7, 11, 2)])
+@pytest.mark.parametrize('c,t_in,t_out,ks,r', [(368, 25, 25, 7, 4), (368, 25, 13, 5, 4), (768, 100, 50, 9, 4), (368, 13, 7, 11, 2),
+                                              (768, 800, 800, 11, 4), (768, 800, 400, 3, 2)])   # last two: long-sequence (one-tile) mode
 def test_sgp_block_fp32(dev, c, t_in, t_out, ks, r):
     from model.modules import SGPBlock
     torch.manual_seed(5)
@@ -256,7 +257,7 @@ def test_sgp_block_fp32(dev, c, t_in, t_out, ks, r):
     assert rel_err(got, ref) < 2e-5
 
 
-@pytest.mark.parametrize('c,tc,t,ks,r', [(368, 13, 25, 7, 4), (768, 50, 100, 9, 4), (368, 7, 13, 5, 4)])
+@pytest.mark.parametrize('c,tc,t,ks,r', [(368, 13, 25, 7, 4), (768, 50, 100, 9, 4), (368, 7, 13, 5, 4), (768, 400, 800, 9, 4)])
 def test_sgp_mixer_fp32(dev, c, tc, t, ks, r):
     from model.modules import SGPMixer
     torch.manual_seed(6)
