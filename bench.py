@@ -319,6 +319,14 @@ def main():
             roofline = {'kernel': top, 'bound': 'tensor', 'achieved': f['flops'] / sec / 1e12, 'peak': pk['tf'], 'unit': 'TFLOP/s'}
         roofline['frac'] = roofline['achieved'] / roofline['peak']
         roofline['traffic'] = None
+        roofline['alg_bytes_per_launch'] = f['bytes'] / f['launches']
+        try:    # measured DRAM bytes per launch of this family (ncu dram__bytes_read.sum + dram__bytes_write.sum, committed profile)
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r1g_traffic.json')))
+            if B == 39 and top in tr['families']:
+                roofline['traffic'] = tr['families'][top]['dram_bytes_per_launch']
+                roofline['traffic_source'] = 'profiles/r1g_traffic.json (ncu, one 39-clip batch)'
+        except Exception:
+            pass
         roofline['peak_source'] = pk['src']
         roofline['ms_per_launch'] = f['ms'] / f['launches']
         roofline['share_of_step'] = f['ms'] / sum(v['ms'] for v in families.values())
