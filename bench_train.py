@@ -268,7 +268,7 @@ def run_train(args, quiet=False):
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dev_s / args.steps * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
             'config': {'workload': TRAIN_CONFIG['name'] + ' training step', 'clips_per_gpu': CLIPS_PER_GPU,
-                       'frame_shape': [100, 3, 224, 224], 'mixup': True, 'augmentation': not args.no_aug, 'optimizer': 'fused AdamW',
+                       'frame_shape': [100, 3, 224, 224], 'mixup': True, 'augmentation': (not args.no_aug) and 'fused kernels (train_aug.cu), reference distributions', 'optimizer': 'fused AdamW',
                        'l2_policy': 'activations of one step (>10 GB) larger than L2', 'parallelism': 'dp%d' % world},
             'e2e': {'value': total / e2e_s, 'unit': 'clips/s', 'h2d_bytes_per_step': int(2 * frame_bytes + 2 * CLIPS_PER_GPU * 100 * 8),
                     'd2h_bytes_per_step': 4},

@@ -124,6 +124,19 @@ int tdeed_gelu_bwd(const float* h, const float* da, long long n, void* dh, int o
 int tdeed_upsample_bwd(const float* dxu, int B, int t_coarse, int T, int C, float* dx, void* stream);
 int tdeed_cast_f32(const float* in, long long n, void* out, int out_dtype, void* stream);
 
+/* ---- per-clip training augmentation (model/model.py:77-84,154-157: torchvision ColorJitter / GaussianBlur(5) / hflip) -----------
+ * tdeed_aug_color: frames planar [n, 3, in_h, in_w] u8 | f32, cropped to [crop_y, +h) x [crop_x, +w), scaled by in_scale (1/255),
+ * then hue shift -> saturation -> brightness (each if *_on), out fp32 planar [n, 3, h, w] in [0, 1].
+ * tdeed_aug_gray_mean: mean[n] of the grayscale image (the pivot of adjust_contrast).
+ * tdeed_aug_contrast_blur_flip: contrast (pivot mean[frame]) -> 5x5 Gaussian (kernel1d_host: 5 host floats, reflect padding) ->
+ * horizontal flip; x and out must not alias. */
+int tdeed_aug_color(const void* frames, int frames_dtype, float in_scale, int n_frames, int in_h, int in_w, int crop_y,
+                    int crop_x, int h, int w, int hue_on, float hue, int sat_on, float sat, int bri_on, float bri,
+                    float* out, void* stream);
+int tdeed_aug_gray_mean(const float* x, int n_frames, int hw, float* mean, void* stream);
+int tdeed_aug_contrast_blur_flip(const float* x, int n_frames, int h, int w, int con_on, float con, const float* mean,
+                                 int blur_on, const float* kernel1d_host, int flip, float* out, void* stream);
+
 /* ---- heads, loss, optimizer ---------------------------------------------------------------------------------------- */
 int tdeed_dropout_fwd(const float* x, long long n, float p, unsigned long long seed, float* out, unsigned char* mask,
                       void* stream);

@@ -88,6 +88,7 @@ class TDEEDModel(BaseRGBModel):
             self._flat = None
             self._train_engines = {}
             self._train_graphs = {}
+            self.fused_augmentation = True   # False: run self.augmentation (torchvision ops) instead of train_aug.cu
             self.use_train_graph = True      # replay forward+loss+backward as a CUDA graph from the 3rd step of a signature on
             self._train_calls = 0
 
@@ -152,9 +153,14 @@ class TDEEDModel(BaseRGBModel):
                 cy, cx, ch, cw = 0, 0, H, W
             unit = False
             if not isinstance(self.augmentation, nn.Identity):
-                x = frame[..., cy:cy + ch, cx:cx + cw].float() / 255.
-                for i in range(b):
-                    x[i] = self.augmentation(x[i])
+                if self.fused_augmentation and frame.dtype in (torch.uint8, torch.float32):
+                    # same transforms / distributions as self.augmentation, three fused kernel passes per clip (train_aug.cu)
+                    from tdeed_b200.augment import ClipAugment
+                    x = ClipAugment.apply(frame.contiguous(), (cy, cx, ch, cw), [ClipAugment.sample() for _ in range(b)])
+                else:                  # the reference's torchvision pipeline, verbatim
+                    x = frame[..., cy:cy + ch, cx:cx + cw].float() / 255.
+                    for i in range(b):
+                        x[i] = self.augmentation(x[i])
                 frame, unit, cy, cx = x.contiguous(), True, 0, 0
             elif frame.dtype not in (torch.uint8, torch.float32):
                 frame = frame.float()

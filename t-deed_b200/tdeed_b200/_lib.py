@@ -117,6 +117,11 @@ SIGNATURES.update({
     'tdeed_gelu_bwd': (c_int, [c_vp, c_vp, c_ll, c_vp, c_int, c_vp]),
     'tdeed_upsample_bwd': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     'tdeed_cast_f32': (c_int, [c_vp, c_ll, c_vp, c_int, c_vp]),
+    'tdeed_aug_color': (c_int, [c_vp, c_int, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_float,
+                                c_int, c_float, c_vp, c_vp]),
+    'tdeed_aug_gray_mean': (c_int, [c_vp, c_int, c_int, c_vp, c_vp]),
+    'tdeed_aug_contrast_blur_flip': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_float, c_vp, c_int, ctypes.POINTER(c_float), c_int,
+                                             c_vp, c_vp]),
     'tdeed_dropout_fwd': (c_int, [c_vp, c_ll, c_float, c_ull, c_vp, c_vp, c_vp]),
     'tdeed_dropout_fwd_devseed': (c_int, [c_vp, c_ll, c_float, c_vp, c_ull, c_vp, c_vp, c_vp]),
     'tdeed_dropout_bwd': (c_int, [c_vp, c_vp, c_ll, c_float, c_vp, c_vp, c_vp]),

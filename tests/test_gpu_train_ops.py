@@ -465,3 +465,54 @@ def test_dropout_and_adamw():
     y = torch.ones(100, device=DEV)
     T().axpy_(torch.full((100,), 2.0, device=DEV), 0.5, y)
     assert torch.equal(y, torch.full((100,), 2.0, device=DEV))
+
+
+@pytest.mark.parametrize('in_dtype', [torch.uint8, torch.float32])
+def test_fused_augmentation_matches_torchvision(in_dtype):
+    """train_aug.cu against torchvision's own tensor ops with the same parameters (model/model.py:77-84 pipeline order)."""
+    import torchvision.transforms.functional as TF
+    from tdeed_b200.augment import ClipAugment
+    g = torch.Generator(device=DEV).manual_seed(3)
+    B, Tn, H, W = 6, 4, 40, 52
+    crop = (3, 5, 32, 40)
+    frames = torch.randint(0, 256, (B, Tn, 3, H, W), device=DEV, generator=g, dtype=torch.uint8)
+    # smooth images too (blur / hue behave differently on noise and on gradients)
+    yy, xx = torch.meshgrid(torch.arange(H, device=DEV), torch.arange(W, device=DEV), indexing='ij')
+    frames[1] = ((yy * 3 + xx * 2) % 256).to(torch.uint8)[None, None].expand(Tn, 3, H, W).clone()
+    frames[1, :, 1] = ((yy * 5) % 256).to(torch.uint8)
+    if in_dtype == torch.float32:
+        frames = frames.float()
+    params = [dict(hue=0.13, sat=None, bri=None, con=None, sigma=None, flip=False),
+              dict(hue=-0.2, sat=0.8, bri=1.15, con=0.75, sigma=1.3, flip=True),
+              dict(hue=None, sat=1.2, bri=None, con=None, sigma=None, flip=True),
+              dict(hue=None, sat=None, bri=0.7, con=1.2, sigma=None, flip=False),
+              dict(hue=None, sat=None, bri=None, con=None, sigma=0.4, flip=False),
+              dict(hue=None, sat=None, bri=None, con=None, sigma=None, flip=False)]
+    out = ClipAugment.apply(frames, crop, params)
+    cy, cx, h, w = crop
+    for i, p in enumerate(params):
+        x = frames[i][..., cy:cy + h, cx:cx + w].float() / 255.
+        if p['hue'] is not None:
+            x = TF.adjust_hue(x, p['hue'])
+        if p['sat'] is not None:
+            x = TF.adjust_saturation(x, p['sat'])
+        if p['bri'] is not None:
+            x = TF.adjust_brightness(x, p['bri'])
+        if p['con'] is not None:
+            x = TF.adjust_contrast(x, p['con'])
+        if p['sigma'] is not None:
+            x = TF.gaussian_blur(x, [5, 5], [p['sigma'], p['sigma']])
+        if p['flip']:
+            x = TF.hflip(x)
+        d = (out[i] - x).abs()
+        # hue: floor(h*6) may land on the other side of a sector boundary for a handful of pixels -> allow 1e-5 of them
+        frac_bad = float((d > 2e-5).float().mean())
+        assert frac_bad <= (1e-4 if p['hue'] is not None else 0.0), (i, frac_bad, float(d.max()))
+    # sampling: frequencies of the decisions
+    torch.manual_seed(0)
+    s = [ClipAugment.sample() for _ in range(4000)]
+    for k in ('hue', 'sat', 'bri', 'con', 'sigma'):
+        assert 0.21 < sum(v[k] is not None for v in s) / 4000 < 0.29
+    assert 0.45 < sum(v['flip'] for v in s) / 4000 < 0.55
+    hs = [v['hue'] for v in s if v['hue'] is not None]
+    assert -0.2 <= min(hs) and max(hs) <= 0.2 and 0.7 <= min(v['con'] for v in s if v['con'] is not None)
