@@ -343,7 +343,7 @@ class TDEEDModel(BaseRGBModel):
         epoch_loss = 0.
         epoch_loss_dev = None
         with torch.no_grad() if optimizer is None else nullcontext():
-            for batch_idx, batch in enumerate(tqdm(loader)):
+            for batch_idx, batch in enumerate(tqdm(_DevicePrefetch(loader, self.device) if optimizer is not None else loader)):
                 frame = batch['frame'].to(self.device, non_blocking=True)          # kept uint8: the stem kernel normalises
                 label = batch['label'].to(self.device, non_blocking=True)
 
@@ -473,6 +473,49 @@ class TDEEDModel(BaseRGBModel):
             # softmax (+ displacement scatter-max over the first head) is fused into the heads kernel
             pred = self._model._last_probs.cpu().numpy()
         return np.argmax(pred, axis=2), pred
+
+
+class _DevicePrefetch:
+    """Iterates a loader one batch ahead and uploads the tensors of the NEXT batch on a side stream (pinned host memory ->
+    non-blocking H2D), so that the copy overlaps the kernels of the current training step.  Non-tensor entries (e.g. the
+    'dataset' list) pass through.  The reference blocks on `.to(device)` at the top of every iteration (model/model.py:216-234)."""
+
+    def __init__(self, loader, device):
+        self.loader, self.device = loader, device
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _upload(self, batch, stream):
+        if not torch.cuda.is_available() or torch.device(self.device).type != 'cuda':
+            return batch, None
+        out = {}
+        with torch.cuda.stream(stream):
+            for k, v in batch.items():
+                out[k] = v.to(self.device, non_blocking=True) if isinstance(v, torch.Tensor) else v
+            ev = torch.cuda.Event()
+            ev.record(stream)
+        return out, ev
+
+    def __iter__(self):
+        stream = torch.cuda.Stream(device=self.device) if torch.cuda.is_available() else None
+        it = iter(self.loader)
+        try:
+            nxt = self._upload(next(it), stream)
+        except StopIteration:
+            return
+        while nxt is not None:
+            cur, ev = nxt
+            try:
+                nxt = self._upload(next(it), stream)
+            except StopIteration:
+                nxt = None
+            if ev is not None:
+                torch.cuda.current_stream().wait_event(ev)
+                for v in cur.values():
+                    if isinstance(v, torch.Tensor) and v.is_cuda:
+                        v.record_stream(torch.cuda.current_stream())
+            yield cur
 
 
 def update_labels_2heads(labels, datasets, num_classes1=1):

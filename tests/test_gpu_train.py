@@ -286,25 +286,35 @@ def test_double_head_joint_training_step(soft):
         assert abs(l2 - float(ref)) < 2e-3 * max(1.0, abs(float(ref)))      # (BN running stats moved once in between: loss identical)
 
 
-def test_train_step_gsm_backbone_vs_f64_oracle():
-    """GSM variant (model/impl/gsm.py) end to end: no golden (the reference's _GSM needs CUDA tensors to even run), so the
-    check is against autograd of the float64 oracle with the same noise-floor rule as the GSF cases."""
-    cfg = O.Config(feature_arch='rny002_gsm', clip_len=10, n_layers=2, sgp_ks=5, sgp_r=2, num_classes=3, radi_displacement=0,
-                   crop_dim=None)
-    sd = O.random_state(cfg, 11)
-    gen = torch.Generator().manual_seed(5)
-    frames = torch.randint(0, 256, (2, 10, 3, 64, 64), generator=gen, dtype=torch.uint8).float()
-    label = torch.randint(0, 4, (2, 10), generator=gen)
+@pytest.mark.parametrize('arch,shape,radi,seed', [('rny002_gsm', (2, 10, 64, 64), 0, 11), ('rny002_gsf', (2, 6, 52, 76), 2, 12),
+                                                  ('rny008_gsf', (1, 7, 45, 33), 1, 13)])
+def test_train_step_variants_vs_f64_oracle(arch, shape, radi, seed):
+    """Variants without a reference golden — GSM (the reference's _GSM needs CUDA tensors to even run), odd frame sizes (every
+    stride-2 stage sees odd extents: parity views / reflect-free padding paths), 800MF with odd sizes — against autograd of the
+    float64 oracle with the same noise-floor rule as the golden cases."""
+    b, t, h, w = shape
+    cfg = O.Config(feature_arch=arch, clip_len=t, n_layers=2, sgp_ks=5, sgp_r=2, num_classes=3, radi_displacement=radi, crop_dim=None)
+    sd = O.random_state(cfg, seed)
+    gen = torch.Generator().manual_seed(seed)
+    frames = torch.randint(0, 256, (b, t, 3, h, w), generator=gen, dtype=torch.uint8).float()
+    label = torch.randint(0, 4, (b, t), generator=gen)
+    labelD = torch.randint(-radi, radi + 1, (b, t), generator=gen).float() if radi else None
     m = _model(cfg, sd)
     m._model.train()
-    loss = m._model.train_step(frames.cuda(), label.cuda().reshape(-1), None, fg_weight=5, precision='fp32')
-    l64, logits64, g64, _ = _oracle_grads(sd, cfg, frames, label, None, torch.float64)
-    _, _, g32, _ = _oracle_grads(sd, cfg, frames, label, None, torch.float32)
+    loss = m._model.train_step(frames.cuda(), label.cuda().reshape(-1), labelD.cuda() if radi else None, fg_weight=5, precision='fp32')
+    l64, logits64, g64, _ = _oracle_grads(sd, cfg, frames, label, labelD, torch.float64)
+    _, _, g32, _ = _oracle_grads(sd, cfg, frames, label, labelD, torch.float32)
     assert abs(float(loss[0]) - l64) < 1e-4 * max(1.0, abs(l64))
     mine = {n: p.grad for n, p in m._model.named_parameters()}
     e_ref = {n: rel_err(g32[n].double().cpu().numpy(), g64[n].cpu().numpy()) for n in g64 if g64[n].numel() >= 16}
     e_mine = {n: rel_err(mine[n].double().cpu().numpy(), g64[n].cpu().numpy()) for n in g64 if g64[n].numel() >= 16}
     worst = max(e_mine, key=e_mine.get)
-    print('gsm: floor %.2e, kernels worst %.2e (%s), median %.2e' % (max(e_ref.values()), e_mine[worst], worst,
-                                                                     float(np.median(list(e_mine.values())))))
+    print('%s %s: floor %.2e, kernels worst %.2e (%s), median %.2e' % (arch, shape, max(e_ref.values()), e_mine[worst], worst,
+                                                                       float(np.median(list(e_mine.values())))))
     assert e_mine[worst] <= 4 * max(e_ref.values()) + 1e-4
+    # bf16 path on the same (odd) geometry: runs, finite, loss close
+    m2 = _model(cfg, sd)
+    m2._model.train()
+    lb = m2._model.train_step(frames.cuda(), label.cuda().reshape(-1), labelD.cuda() if radi else None, fg_weight=5, precision='bf16')
+    assert abs(float(lb[0]) - l64) < 0.1 * abs(l64)
+    assert all(torch.isfinite(p.grad).all() for p in m2._model.parameters())
