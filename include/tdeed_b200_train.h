@@ -39,6 +39,9 @@ int tdeed_gemm_tn(int a_dtype, const void* A, long long lda, int b_dtype, const 
                   float* workspace, void* stream);
 long long tdeed_colsum_workspace_floats(long long M, int C);
 int tdeed_colsum(int dtype, const void* x, long long M, int C, long long ld, float* out, float* workspace, void* stream);
+/* dst[f, oy, ox, :] = src[f, s*oy, s*ox, :]: compact copy of the pixels a stride-s 1x1 conv reads (its dW then runs on the dense
+ * tcgen05 GEMM) */
+int tdeed_strided_gather(int dtype, const void* src, void* dst, int n, int h, int w, int c, int stride, void* stream);
 /* dst[f, s*oy, s*ox, :] += src[f, oy, ox, :]: data gradient of a stride-s 1x1 conv added into the block-input gradient */
 int tdeed_strided_add(int dtype, void* dst, const void* src, int n, int h, int w, int c, int stride, void* stream);
 
@@ -51,6 +54,10 @@ long long tdeed_stem_bwd_weight_workspace_floats(void);
 int tdeed_stem_bwd_weight(const void* frames, int frames_dtype, int unit_input, int n_frames, int in_h, int in_w,
                           int crop_y, int crop_x, int h, int w, int flip, const void* dy, int dy_dtype, float* dw,
                           float* workspace, void* stream);
+/* im2col of the normalised stem input as bf16 rows [n*oh*ow][32] (k = ci*9 + ky*3 + kx, columns 27..31 zero): the stem weight
+ * gradient is then tdeed_gemm_tn(dY [P, 32], patches [P, 32]) on tcgen05 */
+int tdeed_stem_im2col(const void* frames, int frames_dtype, int unit_input, int n_frames, int in_h, int in_w, int crop_y,
+                      int crop_x, int h, int w, int flip, void* patches_bf16, void* stream);
 int tdeed_conv3x3g_raw_fwd(int dtype, const void* in, int n, int h, int w, int c, int group_width, int stride,
                            const float* weight, void* out, void* stream);
 int tdeed_conv3x3g_bwd_data(int dtype, const void* dy, int n, int h, int w, int c, int group_width, int stride,

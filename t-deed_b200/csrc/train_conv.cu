@@ -261,7 +261,63 @@ stem_bwd_weight_kernel(const TIn* __restrict__ frames, int unit_input, int in_h,
   }
 }
 
+// im2col of the normalised stem input: patches[p][k] (k = ci*9 + ky*3 + kx, 27 padded to 32 with zeros) as bf16, one row per
+// output pixel — the B operand of the tcgen05 dW GEMM for the stem weight gradient (dW = dY^T patches).
+template <typename TIn>
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const TIn* __restrict__ frames, int unit_input, int in_h, int in_w, int crop_y, int crop_x, int h, int w, int flip,
+                   int oh, int ow, long long total, __nv_bfloat16* __restrict__ patches) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (idx >= total) return;
+  const int ox = (int)(idx % ow), oy = (int)((idx / ow) % oh);
+  const long long f = idx / ((long long)ow * oh);
+  const float mean[3] = {0.485f, 0.456f, 0.406f};
+  const float stdv[3] = {0.229f, 0.224f, 0.225f};
+  const TIn* fbase = frames + (size_t)f * 3 * in_h * in_w;
+  float v[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) {
+    float val = 0.f;
+    if (k < 27) {
+      const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
+      const int y = 2 * oy + ky - 1, x = 2 * ox + kx - 1;
+      if (y >= 0 && y < h && x >= 0 && x < w) {
+        const int sx = flip ? (w - 1 - x) : x;
+        const float raw = (float)fbase[((size_t)ci * in_h + (crop_y + y)) * in_w + (crop_x + sx)];
+        val = ((unit_input ? raw : raw / 255.f) - mean[ci]) / stdv[ci];
+      }
+    }
+    v[k] = val;
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = v[8 * q + j];
+    store8(patches + idx * 32 + 8 * q, t);
+  }
+}
+
 }  // namespace tdeed
+
+extern "C" int tdeed_stem_im2col(const void* frames, int frames_dtype, int unit_input, int n_frames, int in_h, int in_w, int crop_y,
+                                 int crop_x, int h, int w, int flip, void* patches_bf16, void* stream) {
+  using namespace tdeed;
+  TDEED_REQUIRE(frames && patches_bf16 && n_frames > 0 && h > 0 && w > 0 && crop_y >= 0 && crop_x >= 0 && crop_y + h <= in_h &&
+                crop_x + w <= in_w, TDEED_ERR_SHAPE, "tdeed_stem_im2col: bad geometry");
+  const int oh = (h + 1) / 2, ow = (w + 1) / 2;
+  const long long total = (long long)n_frames * oh * ow;
+  const unsigned grid = (unsigned)ceil_div_ll(total, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (frames_dtype == TDEED_U8)
+    stem_im2col_kernel<uint8_t><<<grid, 256, 0, st>>>((const uint8_t*)frames, unit_input, in_h, in_w, crop_y, crop_x, h, w, flip, oh, ow, total,
+                                                       (__nv_bfloat16*)patches_bf16);
+  else if (frames_dtype == TDEED_F32)
+    stem_im2col_kernel<float><<<grid, 256, 0, st>>>((const float*)frames, unit_input, in_h, in_w, crop_y, crop_x, h, w, flip, oh, ow, total,
+                                                     (__nv_bfloat16*)patches_bf16);
+  else { set_error("tdeed_stem_im2col: dtype %d", frames_dtype); return TDEED_ERR_UNSUPPORTED; }
+  return check_launch("tdeed_stem_im2col");
+}
 
 extern "C" int tdeed_conv3x3g_bwd_data(int dtype, const void* dy, int n, int h, int w, int c, int group_width, int stride,
                                        const float* weight, void* dx, void* stream) {

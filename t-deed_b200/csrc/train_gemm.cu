@@ -122,6 +122,22 @@ strided_add_kernel(T* __restrict__ dst, const T* __restrict__ src, int h, int w,
   store8(d, a);
 }
 
+// dst[f, oy, ox, :] = src[f, s*oy, s*ox, :]  (compact copy of the pixels a stride-s 1x1 conv reads: its weight gradient then
+// runs on the dense tcgen05 dW GEMM)
+template <typename T>
+__global__ void __launch_bounds__(256)
+strided_gather_kernel(const T* __restrict__ src, T* __restrict__ dst, int h, int w, int c8n, int stride, int oh, int ow, long long total8) {
+  const long long q = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (q >= total8) return;
+  const int c8 = (int)(q % c8n);
+  const long long p = q / c8n;
+  const int ox = (int)(p % ow), oy = (int)((p / ow) % oh);
+  const long long f = p / ((long long)ow * oh);
+  const T* s_ = src + (((f * h + (long long)oy * stride) * w + (long long)ox * stride) * c8n + c8) * 8;
+  *reinterpret_cast<uint4*>(dst + q * 8) = *reinterpret_cast<const uint4*>(s_);
+  if (sizeof(T) == 4) *reinterpret_cast<uint4*>(reinterpret_cast<char*>(dst + q * 8) + 16) = *reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(s_) + 16);
+}
+
 static int tn_splits(long long R, int m, int n) {
   const int tiles = ceil_div(m, TN_TILE) * ceil_div(n, TN_TILE);
   long long s = ceil_div_ll(2 * kNumSMs, tiles);                  // ~2 CTAs per SM
@@ -229,4 +245,19 @@ extern "C" int tdeed_strided_add(int dtype, void* dst, const void* src, int n, i
     strided_add_kernel<float><<<grid, 256, 0, st>>>((float*)dst, (const float*)src, h, w, c / 8, stride, oh, ow, total8);
   else { set_error("tdeed_strided_add: dtype %d", dtype); return TDEED_ERR_UNSUPPORTED; }
   return check_launch("tdeed_strided_add");
+}
+
+extern "C" int tdeed_strided_gather(int dtype, const void* src, void* dst, int n, int h, int w, int c, int stride, void* stream) {
+  using namespace tdeed;
+  TDEED_REQUIRE(dst && src && n > 0 && h > 0 && w > 0 && c > 0 && c % 8 == 0 && stride >= 1, TDEED_ERR_SHAPE, "tdeed_strided_gather: bad arguments");
+  const int oh = (h + stride - 1) / stride, ow = (w + stride - 1) / stride;
+  const long long total8 = (long long)n * oh * ow * (c / 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)ceil_div_ll(total8, 256);
+  if (dtype == TDEED_BF16)
+    strided_gather_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, h, w, c / 8, stride, oh, ow, total8);
+  else if (dtype == TDEED_F32)
+    strided_gather_kernel<float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, h, w, c / 8, stride, oh, ow, total8);
+  else { set_error("tdeed_strided_gather: dtype %d", dtype); return TDEED_ERR_UNSUPPORTED; }
+  return check_launch("tdeed_strided_gather");
 }

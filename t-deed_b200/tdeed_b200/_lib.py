@@ -83,6 +83,8 @@ SIGNATURES.update({
                               c_ll, c_vp, c_vp]),
     'tdeed_colsum_workspace_floats': (c_ll, [c_ll, c_int]),
     'tdeed_colsum': (c_int, [c_int, c_vp, c_ll, c_int, c_ll, c_vp, c_vp, c_vp]),
+    'tdeed_strided_gather': (c_int, [c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    'tdeed_stem_im2col': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     'tdeed_strided_add': (c_int, [c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     'tdeed_stem_raw_fwd': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp,
                                    c_int, c_vp]),

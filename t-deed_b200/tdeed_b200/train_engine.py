@@ -303,7 +303,10 @@ class TrainEngine:
         dy0, dg, db, _ = T.bn_act_bwd(dz, y0, y0, st0)
         G['_features.stem.bn.weight'].copy_(dg)
         G['_features.stem.bn.bias'].copy_(db)
-        T.stem_bwd_weight(tape['frames'], tape['unit'], tape['crop'], tape['flip'], dy0, out=G['_features.stem.conv.weight'])
+        if self.adt == torch.bfloat16:
+            T.stem_bwd_weight_tc(tape['frames'], tape['unit'], tape['crop'], tape['flip'], dy0, G['_features.stem.conv.weight'])
+        else:
+            T.stem_bwd_weight(tape['frames'], tape['unit'], tape['crop'], tape['flip'], dy0, out=G['_features.stem.conv.weight'])
         self.tape = None
 
     def _dw(self, dy2d, x2d, name, cout, cin, rows, gather=None):
@@ -355,7 +358,10 @@ class TrainEngine:
             dysc, dg, db, _ = T.bn_act_bwd(g_sc, None, r['ysc'], r['std'])
             G[p + '.downsample.bn.weight'].copy_(dg)
             G[p + '.downsample.bn.bias'].copy_(db)
-            self._dw(dysc, x.view(M, cin), p + '.downsample.conv.weight', cout, cin, M2, gather=(stride, h, w) if stride > 1 else None)
+            if stride > 1 and self.adt == torch.bfloat16:      # compact the strided pixels once, then the dense tcgen05 dW GEMM
+                self._dw(dysc, T.strided_gather(x, stride).view(M2, cin), p + '.downsample.conv.weight', cout, cin, M2)
+            else:
+                self._dw(dysc, x.view(M, cin), p + '.downsample.conv.weight', cout, cin, M2, gather=(stride, h, w) if stride > 1 else None)
             dsc = self._gemm(dysc, r['wdt'], M2)                 # [M2, cin] gradient at the (strided) shortcut pixels
             add = None
         else:

@@ -78,6 +78,26 @@ def colsum(x2d, C=None, out=None):
     return out
 
 
+def strided_gather(src, stride):
+    n, h, w, c = src.shape
+    dst = torch.empty((n, (h + stride - 1) // stride, (w + stride - 1) // stride, c), dtype=src.dtype, device=src.device)
+    L.check(L.load().tdeed_strided_gather(L.dtype_code(src.dtype), L.ptr(src), L.ptr(dst), n, h, w, c, stride, L.stream()), 'strided_gather')
+    return dst
+
+
+def stem_bwd_weight_tc(frames, unit_input, crop, flip, dy, out):
+    """bf16 path: im2col of the normalised input (bf16 [P, 32]) + the tcgen05 dW GEMM; out fp32 [32, 3, 3, 3]."""
+    n, _, in_h, in_w = frames.shape
+    cy, cx, h, w = crop
+    P_ = n * ((h + 1) // 2) * ((w + 1) // 2)
+    patches = torch.empty((P_, 32), dtype=torch.bfloat16, device=frames.device)
+    L.check(L.load().tdeed_stem_im2col(L.ptr(frames), L.dtype_code(frames.dtype), int(unit_input), n, in_h, in_w, cy, cx, h, w,
+                                       int(bool(flip)), L.ptr(patches), L.stream()), 'stem_im2col')
+    dw = gemm_tn(dy.view(P_, 32), patches, 32, 32, P_)
+    out.view(32, 27).copy_(dw[:, :27])
+    return out
+
+
 def strided_add_(dst, src, stride):
     n, h, w, c = dst.shape
     L.check(L.load().tdeed_strided_add(L.dtype_code(dst.dtype), L.ptr(dst), L.ptr(src), n, h, w, c, stride, L.stream()),

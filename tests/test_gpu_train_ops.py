@@ -153,6 +153,8 @@ def test_gemm_tn_gather_colsum_strided_add():
     ref[:, ::2, ::2] += src
     T().strided_add_(dst, src, 2)
     assert torch.equal(dst, ref)
+    assert torch.equal(T().strided_gather(x, 2), x[:, ::2, ::2].contiguous())
+    assert torch.equal(T().strided_gather(x.bfloat16(), 2), x.bfloat16()[:, ::2, ::2].contiguous())
 
 
 @pytest.mark.parametrize('unit', [False, True])
@@ -177,6 +179,9 @@ def test_stem_raw_and_weight_grad(unit):
     assert rel(nchw(y), yr) < 1e-5
     dw = T().stem_bwd_weight(frames, unit, crop, False, nhwc(dy))
     assert rel(dw, wr.grad) < 1e-4
+    # bf16 training path: im2col (bf16 patches) + tcgen05 dW GEMM
+    dwt = T().stem_bwd_weight_tc(frames, unit, crop, False, nhwc(dy).bfloat16(), torch.empty((32, 3, 3, 3), device=DEV))
+    assert rel(dwt, wr.grad) < 1e-2
 
 
 @pytest.mark.parametrize('c,gw,stride,h,w', [(24, 8, 2, 32, 32), (56, 8, 1, 17, 23), (64, 16, 2, 30, 45), (320, 16, 1, 7, 7), (368, 8, 1, 7, 7),
