@@ -64,6 +64,17 @@ int tdeed_stem_tc_fwd(const void* frames, int frames_dtype, int n_frames, int in
                       const void* w0_bf16, const float* b0, const void* w1_bf16, const float* b1, int n1,
                       void* out_stem, int stem_sub, void* out_c1, void* stream);
 
+/* (1c) second-generation fused stem for uint8 frames (stem_tc2.cu): shifted-descriptor implicit GEMM on RAW pixel values — the
+ * normalisation is folded into the weights, zero padding becomes padding with the raw value 255*mean (pad_rgb_host, 3 floats),
+ * two taps share one K=16 MMA.  wimg: tdeed_stem_tc2_wimg_bytes() bytes = 5 B tiles [32 out][16 k] (canonical K-major
+ * no-swizzle; k 0..2 = channels of the pair's first tap, k 8..10 = second tap; pairs (0,0)+(0,2), (2,0)+(2,2), (0,1)+(2,1),
+ * (1,0)+(1,2), (1,1)) of  w * bn_scale / (255 * std);  b0 = bn_shift - sum_k bf16(w') * 255 * mean.  w1 / b1 / n1 / out_stem /
+ * stem_sub / out_c1 as in (1b); the fused conv1 is mandatory here. */
+long long tdeed_stem_tc2_wimg_bytes(void);
+int tdeed_stem_tc2_fwd(const void* frames_u8, int n_frames, int in_h, int in_w, int crop_y, int crop_x, int h, int w,
+                       int flip, const void* wimg, const float* b0, const float* pad_rgb_host, const void* w1_bf16,
+                       const float* b1, int n1, void* out_stem, int stem_sub, void* out_c1, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (2) 1x1 convolution / linear layer as a GEMM with fused epilogue:
  *        out[m, n] = act( sum_k A[m, k] * W[n, k] + bias[n] + residual[m, n] )

@@ -45,6 +45,9 @@ SIGNATURES = {
                                c_vp, c_int, c_vp]),
     'tdeed_stem_tc_fwd': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp,
                                   c_vp, c_int, c_vp, c_int, c_vp, c_vp]),
+    'tdeed_stem_tc2_wimg_bytes': (c_ll, []),
+    'tdeed_stem_tc2_fwd': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, ctypes.POINTER(c_float), c_vp,
+                                   c_vp, c_int, c_vp, c_int, c_vp, c_vp]),
     'tdeed_gemm_fwd': (c_int, [c_int, c_ll, c_int, c_int, ctypes.POINTER(GemmSeg), c_int, c_int, c_int, c_vp, c_vp,
                                c_vp, c_ll, c_int, c_int, c_vp, c_ll, c_int, c_int, c_vp]),
     'tdeed_conv3x3g_fwd': (c_int, [c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),

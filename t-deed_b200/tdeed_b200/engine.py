@@ -92,6 +92,7 @@ class InferenceEngine:
         self.prof = None
         self.fuse_stem = True            # bf16: tcgen05 stem fused with s1.b1.conv1
         self.conv3_tc = True             # bf16: grouped 3x3 conv on tcgen05
+        self.stem_v2 = True              # bf16 + uint8 frames: raw-pixel shifted-descriptor stem (stem_tc2.cu)
         self._graphs = {}
         self.load_state(state)
 
@@ -107,6 +108,7 @@ class InferenceEngine:
         w0 = torch.zeros((32, 32), dtype=torch.float32, device=dev)
         w0[:, :27] = W['stem_w'].reshape(32, 27)
         W['stem_w_tc'] = w0.to(torch.bfloat16).contiguous()        # tcgen05 stem: K = 27 padded to 32
+        W['stem2_wimg'], W['stem2_b0'], W['stem2_pad'] = ops.stem_tc2_weights(W['stem_w'], W['stem_b'])   # raw-pixel stem (stem_tc2.cu)
         gw = REGNET[cfg.backbone]['group_width']
         blocks = []
         for p, cin, cout, stride, shifted in cfg.blocks():
@@ -251,10 +253,16 @@ class InferenceEngine:
             # tcgen05 stem + s1.b1.conv1 in one kernel; only the stride-2 subsample of the stem output (the
             # shortcut conv's input) and conv1's output reach HBM
             c1 = W['blocks'][0]['cout']
-            x_sub, a1_fused = self._op('stem', 2.0 * n * oh0 * ow0 * 32 * (27 + c1),
-                                       n * (3 * crop[2] * crop[3] * frames.element_size() + oh0 * ow0 * (c1 + 8) * es),
-                                       ops.stem_tc, frames.reshape(n, 3, in_h, in_w), crop, flip, W['stem_w_tc'], W['stem_b'],
-                                       W['blocks'][0]['w1_fused'], W['blocks'][0]['b1'], c1, True, 2)
+            if frames.dtype == torch.uint8 and self.stem_v2:
+                x_sub, a1_fused = self._op('stem', 2.0 * n * oh0 * ow0 * 32 * (27 + c1),
+                                           n * (3 * crop[2] * crop[3] * frames.element_size() + oh0 * ow0 * (c1 + 8) * es),
+                                           ops.stem_tc2, frames.reshape(n, 3, in_h, in_w), crop, flip, W['stem2_wimg'], W['stem2_b0'],
+                                           W['stem2_pad'], W['blocks'][0]['w1_fused'], W['blocks'][0]['b1'], c1, 2)
+            else:
+                x_sub, a1_fused = self._op('stem', 2.0 * n * oh0 * ow0 * 32 * (27 + c1),
+                                           n * (3 * crop[2] * crop[3] * frames.element_size() + oh0 * ow0 * (c1 + 8) * es),
+                                           ops.stem_tc, frames.reshape(n, 3, in_h, in_w), crop, flip, W['stem_w_tc'], W['stem_b'],
+                                           W['blocks'][0]['w1_fused'], W['blocks'][0]['b1'], c1, True, 2)
             x = None
         elif adt == torch.bfloat16 and self.fuse_stem:
             x, _ = self._op('stem', 2.0 * n * oh0 * ow0 * 32 * 27, n * (3 * crop[2] * crop[3] * frames.element_size() + oh0 * ow0 * 32 * es),

@@ -36,6 +36,43 @@ def stem_tc(frames, crop, flip, w0, b0, w1=None, b1=None, n1=0, want_stem=True, 
     return out_stem, out_c1
 
 
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+STEM2_PAIRS = ((0, 2), (6, 8), (1, 7), (3, 5), (4, None))     # taps (ky*3+kx) sharing one K=16 MMA
+
+
+def stem_tc2_weights(stem_w, stem_b):
+    """Folded stem conv weights fp32 [32,3,3,3] / bias [32] (BN folded, for NORMALISED input) -> (wimg bf16, b0 fp32, pad_rgb) for
+    tdeed_stem_tc2_fwd: weights for raw 0..255 input, bias absorbing the -mean/std term, raw padding pixel 255*mean."""
+    dev = stem_w.device
+    std = torch.tensor(IMAGENET_STD, dtype=torch.float32, device=dev)
+    mean = torch.tensor(IMAGENET_MEAN, dtype=torch.float32, device=dev)
+    w = (stem_w.float().reshape(32, 3, 9) / (255.0 * std.view(1, 3, 1))).to(torch.bfloat16)          # [co][ci][tap]
+    pad = (255.0 * mean)
+    b0 = stem_b.float() - (w.float() * pad.view(1, 3, 1)).sum(dim=(1, 2))
+    tiles = torch.zeros((len(STEM2_PAIRS), 32, 16), dtype=torch.bfloat16, device=dev)
+    for q, (ta, tb) in enumerate(STEM2_PAIRS):
+        tiles[q, :, 0:3] = w[:, :, ta]
+        if tb is not None:
+            tiles[q, :, 8:11] = w[:, :, tb]
+    img = tiles.reshape(len(STEM2_PAIRS), 4, 8, 2, 8).permute(0, 1, 3, 2, 4).contiguous()           # [q][n/8][k/8][n%8][k%8]
+    return img.reshape(-1), b0.contiguous(), [float(v) for v in pad]
+
+
+def stem_tc2(frames, crop, flip, wimg, b0, pad_rgb, w1, b1, n1, stem_sub=2):
+    """uint8 frames (N,3,H,W) -> (stem_out subsample (N, ceil(oh/sub), ceil(ow/sub), 32), conv1_out (N, oh, ow, n1)), bf16."""
+    n, _, in_h, in_w = frames.shape
+    cy, cx, h, w = crop
+    oh, ow = (h + 1) // 2, (w + 1) // 2
+    dev = frames.device
+    out_stem = torch.empty((n, (oh + stem_sub - 1) // stem_sub, (ow + stem_sub - 1) // stem_sub, 32), dtype=torch.bfloat16, device=dev)
+    out_c1 = torch.empty((n, oh, ow, n1), dtype=torch.bfloat16, device=dev)
+    pad = (ctypes.c_float * 3)(*pad_rgb)
+    L.check(L.load().tdeed_stem_tc2_fwd(L.ptr(frames), n, in_h, in_w, cy, cx, h, w, int(bool(flip)), L.ptr(wimg), L.ptr(b0), pad,
+                                        L.ptr(w1), L.ptr(b1), n1, L.ptr(out_stem), stem_sub, L.ptr(out_c1), L.stream()), 'stem_tc2')
+    return out_stem, out_c1
+
+
 def gemm(segs, weight, bias=None, residual=None, act=L.ACT_NONE, out=None, out_dtype=None, gather=None,
          backend=L.GEMM_AUTO, rows=None):
     """out[M,N] = act(concat_k(segs) @ weight.T + bias + residual).

@@ -161,6 +161,31 @@ def test_stem_tcgen05_fused_conv1(dev, in_dtype, flip, n1):
     assert rel_err(_nchw(c1), c1_ref) < 8e-3
 
 
+@pytest.mark.parametrize('flip,n1,geom', [(False, 24, (3, 70, 90, (2, 5, 67, 83))), (True, 64, (3, 70, 90, (2, 5, 67, 83))),
+                                          (False, 24, (2, 224, 398, (0, 87, 224, 224))), (True, 24, (1, 96, 140, (0, 0, 96, 140)))])
+def test_stem_raw_pixel_shifted_descriptor(dev, flip, n1, geom):
+    """stem_tc2.cu (raw-pixel implicit GEMM, normalisation folded into the weights, tap pairs per MMA) vs the fp32 oracle."""
+    from tdeed_b200 import ops
+    nfr, H, W, crop = geom
+    g = torch.Generator().manual_seed(8)
+    frames = torch.randint(0, 256, (nfr, 3, H, W), generator=g, dtype=torch.uint8)
+    w = torch.randn(32, 3, 3, 3, generator=g) * 0.2
+    b = torch.randn(32, generator=g) * 0.1
+    cy, cx, h, wd = crop
+    x = frames[None, :, :, cy:cy + h, cx:cx + wd]
+    xn = O.preprocess(x, O.Config(crop_dim=None), flip=flip)
+    stem_ref = torch.relu(torch.nn.functional.conv2d(xn, w, b, stride=2, padding=1))
+    w1 = (torch.randn(n1, 32, generator=g) / math.sqrt(32)).to(torch.bfloat16).float()
+    b1 = torch.randn(n1, generator=g) * 0.1
+    c1_ref = torch.relu(torch.nn.functional.conv2d(stem_ref, w1[:, :, None, None], b1))
+    w1p = torch.zeros((n1 + 15) // 16 * 16, 32)
+    w1p[:n1] = w1
+    wimg, b0, pad = ops.stem_tc2_weights(w.to(dev), b.to(dev))
+    sub, c1 = ops.stem_tc2(frames.to(dev), crop, flip, wimg, b0, pad, w1p.to(torch.bfloat16).to(dev), b1.to(dev), n1, 2)
+    assert rel_err(_nchw(sub), stem_ref[:, :, ::2, ::2]) < 1e-2
+    assert rel_err(_nchw(c1), c1_ref) < 1.5e-2
+
+
 @pytest.mark.parametrize('c,gw,stride,h,w', [(24, 8, 2, 20, 22), (152, 8, 1, 7, 9), (368, 8, 2, 14, 14),
                                               (64, 16, 2, 12, 10), (320, 16, 1, 5, 6)])
 def test_conv3x3g(dev, c, gw, stride, h, w):
