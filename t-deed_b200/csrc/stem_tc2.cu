@@ -75,9 +75,9 @@ __device__ __forceinline__ bool s2_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(s2_smem_u32(bar)), "r"(parity) : "memory");
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"     // suspend-time hint: sleep in hardware instead of
+      "selp.u32 %0, 1, 0, p;\n\t}"                                            // spinning (ncu r1h: half of all issued instructions
+      : "=r"(ok) : "r"(s2_smem_u32(bar)), "r"(parity), "r"(4000u) : "memory");   // were wait-loop branches stealing producer slots)
   return ok != 0;
 }
 __device__ __forceinline__ void s2_wait(uint64_t* bar, uint32_t parity) {
