@@ -92,6 +92,7 @@ class InferenceEngine:
         self.prof = None
         self.fuse_stem = True            # bf16: tcgen05 stem fused with s1.b1.conv1
         self.conv3_tc = True             # bf16: grouped 3x3 conv on tcgen05
+        self.fuse_ds0 = True             # bf16: s1.b1 shortcut conv as a second K-segment of conv3's GEMM
         self.stem_v2 = True              # bf16 + uint8 frames: raw-pixel shifted-descriptor stem (stem_tc2.cu)
         self._graphs = {}
         self.load_state(state)
@@ -162,6 +163,11 @@ class InferenceEngine:
                 wf = torch.zeros(((cout + 15) // 16 * 16, 32), dtype=torch.float32, device=dev)
                 wf[:cout] = w1
                 b['w1_fused'] = wf.to(torch.bfloat16).contiguous()
+                if 'wd' in b and adt == torch.bfloat16:
+                    # the stem kernel writes the stride-2 subsample of its output compactly, so the shortcut conv of s1.b1 is a
+                    # second K-segment of conv3's GEMM:  relu([a2 | x_sub] @ [W3 | Wd]^T + b3 + bd)  — one launch, no `res` tensor
+                    b['w3d'] = torch.cat([b['w3'].float(), b['wd'].float()], dim=1).to(adt).contiguous()
+                    b['b3d'] = (b['b3'] + b['bd']).contiguous()
             blocks.append(b)
         W['blocks'] = blocks
         W['temp_enc'] = f32(sd['temp_enc'])
@@ -306,6 +312,10 @@ class InferenceEngine:
                               ops.conv3x3g, a1, blk['w2'], blk['b2'], blk['gw'], stride)
             self._op('se', 4.0 * n * cout * blk['se_w1'].shape[0], 2 * mo * cout * es,
                      ops.se_, a2, blk['se_w1'], blk['se_b1'], blk['se_w2'], blk['se_b2'])
+            if bi == 0 and a1_fused is not None and 'w3d' in blk and self.fuse_ds0:
+                x = self._gemm([(a2.view(mo, cout), cout, 0, cout), (x_sub.view(mo, 32), 32, 0, 32)], blk['w3d'], blk['b3d'],
+                               label='conv1x1', act=L.ACT_RELU, rows=mo).view(n, oh, ow, cout)
+                continue
             if bi == 0 and a1_fused is not None:
                 # the stem kernel already wrote the stride-2 subsample: plain GEMM, no gather
                 res = self._gemm([(x_sub, 32, 0, 32)], blk['wd'], blk['bd'], label='conv1x1_ds', rows=mo)
