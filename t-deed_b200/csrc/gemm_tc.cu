@@ -41,6 +41,8 @@ struct TcParams {
   int m_tiles, n_tiles;
   // 4D gather geometry (strided 1x1 conv): an M tile is a bw x bh patch of output pixels of one frame
   int gather, Ho, Wo, bw, bh, tiles_x, tiles_y;
+  int w_res;      // 1: the whole weight matrix (one n-tile, all k-blocks) is loaded once per CTA and stays in shared memory
+  uint32_t w_kb_stride, w_res_bytes;
   int out_bufs;   // 1 or 2 output staging tiles
   int staged;     // 1: outputs go through the smem staging tile (coalesced stores); 0: row pieces straight from registers
   int debug;   // TDEED_GEMM_DEBUG (dev only): 1 = skip global stores, 2 = skip TMEM loads, 4 = skip the MMAs
@@ -142,8 +144,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t a_stage_bytes = TC_BM * TC_BK * 2;                 // 16 KB
   const uint32_t w_stage_bytes = (uint32_t)p.block_n * TC_BK * 2;   // block_n * 128 B
-  const uint32_t stage_bytes = a_stage_bytes + ((w_stage_bytes + 1023u) & ~1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.num_stages * stage_bytes);
+  // W-resident mode (s3-sized layers: W <= 72 KB, many M tiles per CTA): W occupies the head of the buffer and is fetched
+  // ONCE; the ring then carries only the 16 KB A blocks.  Re-fetching W per tile was 55 % of the TMA fill traffic of these
+  // layers, and the kernel runs close to the ~24 B/clk/SM shared-memory fill rate of TMA.
+  uint8_t* w_region = smem;
+  uint8_t* ring = smem + (p.w_res ? p.w_res_bytes : 0u);
+  const uint32_t stage_bytes = p.w_res ? a_stage_bytes : a_stage_bytes + ((w_stage_bytes + 1023u) & ~1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)p.num_stages * stage_bytes);
+  uint64_t* w_bar = bars + 2 * TC_MAX_STAGES + 5;
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + TC_MAX_STAGES;
   uint64_t* tmem_full_bar = bars + 2 * TC_MAX_STAGES;        // [2]
@@ -170,6 +178,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       mbar_init(&tmem_full_bar[a], 1);
       mbar_init(&tmem_empty_bar[a], 256);     // every epilogue thread arrives
     }
+    mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < p.n_tiles * p.block_n; i += TC_THREADS) s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
@@ -186,6 +195,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // ===== TMA producer (one lane) =====
     if (lane == 0) {
       uint32_t it = 0;
+      if (p.w_res) {
+        mbar_expect_tx(w_bar, (uint32_t)total_kb * w_stage_bytes);
+        int kbi = 0;
+        for (int s = 0; s < p.nseg; ++s)
+          for (int i = 0; i < p.nkb[s]; ++i, ++kbi) tma_load_2d(&map_w, w_bar, w_region + (size_t)kbi * p.w_kb_stride, p.w_col0[s] + i * TC_BK, 0);
+      }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
         const int n0 = nt * p.block_n;
@@ -202,12 +217,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
             const int stage = it % p.num_stages;
             const uint32_t round = it / p.num_stages;
             mbar_wait(&empty_bar[stage], (round & 1u) ^ 1u);
-            uint8_t* sa = smem + (size_t)stage * stage_bytes;
+            uint8_t* sa = ring + (size_t)stage * stage_bytes;
             uint8_t* sw = sa + a_stage_bytes;
-            mbar_expect_tx(&full_bar[stage], a_tx_bytes + w_stage_bytes);
+            mbar_expect_tx(&full_bar[stage], p.w_res ? a_tx_bytes : a_tx_bytes + w_stage_bytes);
             if (p.gather) tma_load_4d(map_a, &full_bar[stage], sa, p.a_col0[s] + i * TC_BK, c1, c2, c3);
             else tma_load_2d(map_a, &full_bar[stage], sa, p.a_col0[s] + i * TC_BK, c1);
-            tma_load_2d(&map_w, &full_bar[stage], sw, p.w_col0[s] + i * TC_BK, n0);
+            if (!p.w_res) tma_load_2d(&map_w, &full_bar[stage], sw, p.w_col0[s] + i * TC_BK, n0);
           }
         }
       }
@@ -217,6 +232,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     // instruction descriptor: D=f32, A=B=bf16, both K-major, N = block_n, M = 128
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     uint32_t it = 0, j = 0;
+    if (p.w_res && blockIdx.x < num_tiles) mbar_wait(w_bar, 0);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++j) {
       const uint32_t acc = j & 1u;
       mbar_wait(&tmem_empty_bar[acc], ((j >> 1) & 1u) ^ 1u);     // epilogue has drained this accumulator
@@ -228,8 +244,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         mbar_wait(&full_bar[stage], round & 1u);
         tcgen05_fence_after();
         if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t sw = sa + a_stage_bytes;
+          const uint32_t sa = smem_u32(ring + (size_t)stage * stage_bytes);
+          const uint32_t sw = p.w_res ? smem_u32(w_region) + (uint32_t)kb * p.w_kb_stride : sa + a_stage_bytes;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
             if (p.debug & 4) break;
@@ -499,8 +515,15 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
   int rc = make_map_2d(&maps[2], W, N, K, K, block_n);
   if (rc) return rc;
 
-  const size_t stage_bytes = (size_t)TC_BM * TC_BK * 2 + (((size_t)block_n * TC_BK * 2 + 1023) & ~(size_t)1023);
-  int stages = (int)((200 * 1024) / stage_bytes);
+  const size_t w_kb_stride = ((size_t)block_n * TC_BK * 2 + 1023) & ~(size_t)1023;
+  static int wres_env = -2;
+  if (wres_env == -2) { const char* e = getenv("TDEED_GEMM_WRES"); wres_env = e ? atoi(e) : -1; }
+  p.w_res = (p.n_tiles == 1 && (size_t)total_kb * w_kb_stride <= 72 * 1024 && p.m_tiles >= 4 * kNumSMs) ? 1 : 0;
+  if (wres_env >= 0) p.w_res = p.w_res && wres_env;
+  p.w_kb_stride = (uint32_t)w_kb_stride;
+  p.w_res_bytes = p.w_res ? (uint32_t)(total_kb * w_kb_stride) : 0u;
+  const size_t stage_bytes = p.w_res ? (size_t)TC_BM * TC_BK * 2 : (size_t)TC_BM * TC_BK * 2 + w_kb_stride;
+  int stages = (int)((200 * 1024 - p.w_res_bytes) / stage_bytes);
   if (stages > TC_MAX_STAGES) stages = TC_MAX_STAGES;
   if (stages < 2) stages = 2;
   p.num_stages = stages;
@@ -511,7 +534,7 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
   const char* force_staged = getenv("TDEED_GEMM_STAGED");
   p.staged = force_staged ? atoi(force_staged) : (residual == nullptr && N >= 96 ? 1 : 0);
   const size_t stage_out_bytes = p.staged ? (size_t)TC_BM * ((size_t)block_n * (out_dtype == TDEED_F32 ? 4 : 2) + 16) : 0;
-  const size_t fixed = 1024 + (2 * TC_MAX_STAGES + 6) * sizeof(uint64_t) + bias_bytes + 2 * TC_BM * sizeof(long long) + stage_out_bytes;
+  const size_t fixed = 1024 + p.w_res_bytes + (2 * TC_MAX_STAGES + 6) * sizeof(uint64_t) + bias_bytes + 2 * TC_BM * sizeof(long long) + stage_out_bytes;
   TDEED_REQUIRE(fixed + 2 * stage_bytes <= 227 * 1024, TDEED_ERR_UNSUPPORTED, "gemm_tc: N=%d too wide for the bias staging area", N);
   // a second output staging tile saves one CTA-wide barrier per tile; take it when >= 3 ring stages still fit
   p.out_bufs = (fixed + stage_out_bytes + 3 * stage_bytes <= 227 * 1024) ? 2 : 1;
