@@ -199,7 +199,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         mbar_expect_tx(w_bar, (uint32_t)total_kb * w_stage_bytes);
         int kbi = 0;
         for (int s = 0; s < p.nseg; ++s)
-          for (int i = 0; i < p.nkb[s]; ++i, ++kbi) tma_load_2d(&map_w, w_bar, w_region + (size_t)kbi * p.w_kb_stride, p.w_col0[s] + i * TC_BK, 0);
+          for (int i = 0; i < p.nkb[s]; ++i, ++kbi)
+            tma_load_2d(&map_w, w_bar, w_region + (size_t)kbi * p.w_kb_stride, p.w_col0[s] + i * TC_BK, (int)(blockIdx.x % p.n_tiles) * p.block_n);
       }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int nt = tile % p.n_tiles, mt = tile / p.n_tiles;
@@ -518,7 +519,12 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
   const size_t w_kb_stride = ((size_t)block_n * TC_BK * 2 + 1023) & ~(size_t)1023;
   static int wres_env = -2;
   if (wres_env == -2) { const char* e = getenv("TDEED_GEMM_WRES"); wres_env = e ? atoi(e) : -1; }
-  p.w_res = (p.n_tiles == 1 && (size_t)total_kb * w_kb_stride <= 72 * 1024 && p.m_tiles >= 4 * kNumSMs) ? 1 : 0;
+  // one n-tile: W <= 72 KB stays resident next to a deep ring.  Several n-tiles (s4-sized layers, W ~ 280 KB): every CTA keeps the
+  // SLICE of its own n-tile (tile index % n_tiles is constant per CTA when the grid is a multiple of n_tiles) — up to 150 KB,
+  // with a 3-stage A ring and direct (unstaged) stores; A is then read n_tiles times but W no longer once per M tile.
+  const size_t w_slice = (size_t)total_kb * w_kb_stride;
+  const bool big_slice = w_slice > 72 * 1024;
+  p.w_res = (w_slice <= 150 * 1024 && (p.n_tiles == 1 || kNumSMs / p.n_tiles >= 1) && p.m_tiles >= 4 * kNumSMs) ? 1 : 0;
   if (wres_env >= 0) p.w_res = p.w_res && wres_env;
   p.w_kb_stride = (uint32_t)w_kb_stride;
   p.w_res_bytes = p.w_res ? (uint32_t)(total_kb * w_kb_stride) : 0u;
@@ -533,6 +539,7 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
   // row's lines into L1.
   const char* force_staged = getenv("TDEED_GEMM_STAGED");
   p.staged = force_staged ? atoi(force_staged) : (residual == nullptr && N >= 96 ? 1 : 0);
+  if (p.w_res && big_slice) p.staged = 0;
   const size_t stage_out_bytes = p.staged ? (size_t)TC_BM * ((size_t)block_n * (out_dtype == TDEED_F32 ? 4 : 2) + 16) : 0;
   const size_t fixed = 1024 + p.w_res_bytes + (2 * TC_MAX_STAGES + 6) * sizeof(uint64_t) + bias_bytes + 2 * TC_BM * sizeof(long long) + stage_out_bytes;
   TDEED_REQUIRE(fixed + 2 * stage_bytes <= 227 * 1024, TDEED_ERR_UNSUPPORTED, "gemm_tc: N=%d too wide for the bias staging area", N);
@@ -552,7 +559,8 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
   if (dbg < 0) { const char* e = getenv("TDEED_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
   p.debug = dbg;
   const int num_tiles = p.m_tiles * p.n_tiles;
-  const int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+  int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
+  if (p.w_res) grid -= grid % p.n_tiles;             // every CTA then sees one fixed n-tile: its resident W slice
   gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], p);
   return check_launch("tdeed_gemm_fwd(tcgen05)");
 }
