@@ -158,12 +158,16 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours')
-    ap.add_argument('--clips-per-batch', type=int, default=39)
+    ap.add_argument('--clips-per-batch', type=int, default=57)
+    ap.add_argument('--cold-batch', type=int, default=13,
+                    help='e2e: size of the first batch of the first video, while nothing is in flight to hide its upload behind')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--workload', default='infer', choices=['infer', 'train'],
                     help="infer: BASELINE configs[1] (headline); train: configs[2] FineGym_big training step (bench_train.py)")
     ap.add_argument('--no-aug', action='store_true', help='train workload: disable the per-clip torchvision augmentation')
+    ap.add_argument('--ncu-step', action='store_true',
+                    help='train workload: after the warm-up run ONE eager step between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)')
     ap.add_argument('--no-train', action='store_true', help="infer workload: skip the short 'train_step' side measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
@@ -231,11 +235,16 @@ def main():
 
     pending = []
 
-    def step_e2e():
+    # cold start: the first upload of a stream of videos has no compute to hide behind, so it is kept short (a small first
+    # batch, then full batches); every later video starts while the previous one is still computing and uses even batches
+    cb = max(1, min(args.cold_batch, B))
+    cold_batches = [(0, cb)] + [(i, min(i + B, n_clips)) for i in range(cb, n_clips, B)]
+
+    def step_e2e(cold=False):
         """One video through the host-facing path.  Nothing here blocks the host: clip uploads run on a side
         stream, the event lists come back through async D2H copies that are collected one video later."""
         vs = VideoScores(VIDEO_FRAMES, K, dev)
-        for lo, hi in batches:
+        for lo, hi in (cold_batches if cold else batches):
             x = uploader.upload(host_batch[:hi - lo])                     # H2D of this batch's clips (side stream)
             _, _, probs = eng.forward_graphed(x, crop=(0, 0, crop_win[2], crop_win[3]))
             uploader.release()
@@ -283,11 +292,12 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     step_e2e()
+    step_e2e(cold=True)                  # captures the graphs of the cold-start batch sizes outside the timed region
     drain_e2e()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
+    for i in range(args.steps):
+        step_e2e(cold=(i == 0))
     drain_e2e()
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
@@ -321,10 +331,10 @@ def main():
         roofline['traffic'] = None
         roofline['alg_bytes_per_launch'] = f['bytes'] / f['launches']
         try:    # measured DRAM bytes per launch of this family (ncu dram__bytes_read.sum + dram__bytes_write.sum, committed profile)
-            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r1g_traffic.json')))
-            if B == 39 and top in tr['families']:
+            tr = json.load(open(os.path.join(ROOT, 'profiles', 'r1h_traffic.json')))
+            if B == tr.get('clips_per_batch', 39) and top in tr['families']:
                 roofline['traffic'] = tr['families'][top]['dram_bytes_per_launch']
-                roofline['traffic_source'] = 'profiles/r1g_traffic.json (ncu, one 39-clip batch)'
+                roofline['traffic_source'] = 'profiles/r1h_traffic.json (ncu, one %d-clip batch)' % B
         except Exception:
             pass
         roofline['peak_source'] = pk['src']
@@ -357,7 +367,7 @@ def main():
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dev_s / args.steps * 1e3, 'higher_is_better': True,
             'scaling': 'weak', 'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
             'config': {'workload': CONFIG['name'] + ' batched inference + NMS', 'clips_per_step': n_clips,
-                       'clips_per_batch': B, 'frame_shape': [100, 3, FRAME_H, FRAME_W], 'video_frames': VIDEO_FRAMES,
+                       'clips_per_batch': B, 'e2e_cold_batch': cb, 'frame_shape': [100, 3, FRAME_H, FRAME_W], 'video_frames': VIDEO_FRAMES,
                        'l2_policy': 'inputs (4.5 GB/video) larger than L2', 'parallelism': 'clip-sharded x%d' % world},
             'e2e': {'value': total_clips / e2e_s, 'unit': 'clips/s', 'h2d_bytes_per_step': int(n_clips * 100 * 3 * crop_win[2] * crop_win[3]),
                     'd2h_bytes_per_step': int(d2h[0])},

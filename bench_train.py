@@ -199,6 +199,15 @@ def run_train(args, quiet=False):
         del dummy
     loss = step(dev_batch, args.warmup)
     barrier()
+    if getattr(args, 'ncu_step', False):
+        model._model.use_train_graph = False
+        step(dev_batch)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step(dev_batch)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return None
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()

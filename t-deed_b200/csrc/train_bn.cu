@@ -17,15 +17,21 @@ struct StatsOp {
   long long ld;
   float piv[8];
   __device__ void begin(int ch0, int nch) { load_n(x + ch0, nch, piv); }
-  __device__ void row(long long r, int ch0, int nch, float (&a0)[8], float (&a1)[8]) {
-    float v[8];
-    load_n(x + r * ld + ch0, nch, v);
+  static constexpr int kBatch = 8;
+  struct Regs { float v[8]; };
+  __device__ void load(long long r, int ch0, Regs& g) const { load8(x + r * ld + ch0, g.v); }
+  __device__ void acc(const Regs& g, float (&a0)[8], float (&a1)[8]) const {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float d = v[j] - piv[j];
+      const float d = g.v[j] - piv[j];
       a0[j] += d;
       a1[j] = fmaf(d, d, a1[j]);
     }
+  }
+  __device__ void row(long long r, int ch0, int nch, float (&a0)[8], float (&a1)[8]) {
+    Regs g;
+    load_n(x + r * ld + ch0, nch, g.v);
+    acc(g, a0, a1);
   }
 };
 
@@ -88,15 +94,16 @@ bn_act_fwd_kernel(const T* __restrict__ y, long long M, int C, const float* __re
 }
 
 // ---- backward ----
-template <typename T>
+// MODE: 0 no activation, 1 ReLU mask recomputed from y as (y*scale + shift > 0) (the z == y sentinel: saves reading z),
+//       2 ReLU mask from the post-activation tensor z
+template <typename T, int MODE>
 struct BwdOp {
   const T* dz;
-  const T* z;      // post-activation output (mask), or nullptr when there is no ReLU
+  const T* z;
   const T* y;
   const float* mean;
   const float* invstd;
   int C;
-  int mask_from_y;       // z == y sentinel: ReLU mask recomputed as (y*scale + shift > 0) — saves reading z
   float mu[8], is[8], sc[8], sh[8];
   __device__ void begin(int ch0, int nch) {
 #pragma unroll
@@ -107,22 +114,28 @@ struct BwdOp {
       sh[j] = j < nch ? mean[3 * C + ch0 + j] : 0.f;
     }
   }
-  __device__ void row(long long r, int ch0, int nch, float (&a0)[8], float (&a1)[8]) {
-    float g[8], yv[8], zv[8];
-    load8(dz + r * C + ch0, g);
-    load8(y + r * C + ch0, yv);
-    if (mask_from_y) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) zv[j] = fmaf(yv[j], sc[j], sh[j]);
-    } else if (z) {
-      load8(z + r * C + ch0, zv);
-    }
+  static constexpr int kBatch = 4;
+  struct Regs { float g[8], yv[8], zv[MODE == 2 ? 8 : 1]; };
+  __device__ void load(long long r, int ch0, Regs& q) const {
+    load8(dz + r * C + ch0, q.g);
+    load8(y + r * C + ch0, q.yv);
+    if constexpr (MODE == 2) load8(z + r * C + ch0, q.zv);
+  }
+  __device__ void acc(const Regs& q, float (&a0)[8], float (&a1)[8]) const {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float gg = (z && !(zv[j] > 0.f)) ? 0.f : g[j];
+      bool keep = true;
+      if constexpr (MODE == 1) keep = fmaf(q.yv[j], sc[j], sh[j]) > 0.f;
+      if constexpr (MODE == 2) keep = q.zv[j] > 0.f;
+      const float gg = keep ? q.g[j] : 0.f;
       a0[j] += gg;
-      a1[j] = fmaf(gg, (yv[j] - mu[j]) * is[j], a1[j]);
+      a1[j] = fmaf(gg, (q.yv[j] - mu[j]) * is[j], a1[j]);
     }
+  }
+  __device__ void row(long long r, int ch0, int nch, float (&a0)[8], float (&a1)[8]) {
+    Regs q;
+    load(r, ch0, q);
+    acc(q, a0, a1);
   }
 };
 
@@ -140,7 +153,7 @@ __global__ void bn_bwd_final_kernel(const float* __restrict__ part, int nparts, 
   coef[C + ch] = (float)(q / (double)M);
 }
 
-template <typename T>
+template <typename T, int MODE>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_act_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T* __restrict__ y, long long M, int C,
                         const float* __restrict__ stats, const float* __restrict__ coef, T* __restrict__ dy,
@@ -159,26 +172,42 @@ bn_act_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ z, const
     k1[j] = coef[ch];
     k2[j] = coef[C + ch];
   }
-  const bool from_y = z == y;
-  for (long long r = (long long)blockIdx.x * l.rpi + lr; r < M; r += (long long)gridDim.x * l.rpi) {
-    const long long at = r * C + c8 * 8;
-    float g[8], yv[8], zv[8], o[8];
-    load8(dz + at, g);
-    load8(y + at, yv);
-    if (from_y) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) zv[j] = fmaf(yv[j], sc[j], sh[j]);
-    } else if (z) {
-      load8(z + at, zv);
-    }
+  constexpr int U = 2;                        // rows per trip, loads of both issued before the first store
+  const long long stride = (long long)gridDim.x * l.rpi;
+  auto one = [&](long long at, float (&g)[8], const float (&yv)[8], const float* zv) {
+    float o[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      if (z && !(zv[j] > 0.f)) g[j] = 0.f;
+      bool keep = true;
+      if constexpr (MODE == 1) keep = fmaf(yv[j], sc[j], sh[j]) > 0.f;
+      if constexpr (MODE == 2) keep = zv[j] > 0.f;
+      if (!keep) g[j] = 0.f;
       const float xhat = (yv[j] - mu[j]) * is[j];
       o[j] = sc[j] * (g[j] - k1[j] - xhat * k2[j]);
     }
     store8(dy + at, o);
     if (dres) store8(dres + at, g);
+  };
+  long long r = (long long)blockIdx.x * l.rpi + lr;
+  for (; r + (U - 1) * stride < M; r += U * stride) {
+    float g[U][8], yv[U][8], zv[U][MODE == 2 ? 8 : 1];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long at = (r + u * stride) * C + c8 * 8;
+      load8(dz + at, g[u]);
+      load8(y + at, yv[u]);
+      if constexpr (MODE == 2) load8(z + at, zv[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) one((r + u * stride) * C + c8 * 8, g[u], yv[u], zv[u]);
+  }
+  for (; r < M; r += stride) {
+    const long long at = r * C + c8 * 8;
+    float g[8], yv[8], zv[MODE == 2 ? 8 : 1];
+    load8(dz + at, g);
+    load8(y + at, yv);
+    if constexpr (MODE == 2) load8(z + at, zv);
+    one(at, g, yv, zv);
   }
 }
 
@@ -203,29 +232,36 @@ static int run_stats(const void* x, long long M, int C, long long ld, const floa
   return check_launch("tdeed_bn_stats(final)");
 }
 
-template <typename T>
-static int run_bwd(const void* dz, const void* z, const void* y, long long M, int C, const float* stats, float* dgamma,
-                   float* dbeta, void* dy, void* dres, float* ws, cudaStream_t st) {
-  BwdOp<T> op;
+template <typename T, int MODE>
+static int run_bwd_mode(const void* dz, const void* z, const void* y, long long M, int C, const float* stats, float* dgamma,
+                        float* dbeta, void* dy, void* dres, float* ws, cudaStream_t st) {
+  BwdOp<T, MODE> op;
   op.dz = (const T*)dz;
   op.z = (const T*)z;
   op.y = (const T*)y;
   op.mean = stats;
   op.invstd = stats + C;
   op.C = C;
-  op.mask_from_y = (z != nullptr && z == y) ? 1 : 0;
   const int grid = bn_grid(M, C);
   const int cpad = ((C + 7) / 8) * 8;
   float* coef = ws + (size_t)BN_MAX_GRID * 2 * cpad;
-  bn_reduce_kernel<T, BwdOp<T>><<<grid, BN_THREADS, 0, st>>>(op, M, C, ws);
+  bn_reduce_kernel<T, BwdOp<T, MODE>><<<grid, BN_THREADS, 0, st>>>(op, M, C, ws);
   int rc = check_launch("tdeed_bn_act_bwd(partial)");
   if (rc) return rc;
   bn_bwd_final_kernel<<<ceil_div(C, 8), 256, 0, st>>>(ws, grid, M, C, dgamma, dbeta, coef);
   rc = check_launch("tdeed_bn_act_bwd(final)");
   if (rc) return rc;
-  bn_act_bwd_apply_kernel<T><<<bn_apply_grid(M, C), BN_THREADS, 0, st>>>((const T*)dz, (const T*)z, (const T*)y, M, C, stats, coef,
-                                                                         (T*)dy, (T*)dres);
+  bn_act_bwd_apply_kernel<T, MODE><<<bn_apply_grid(M, C), BN_THREADS, 0, st>>>((const T*)dz, (const T*)z, (const T*)y, M, C, stats,
+                                                                               coef, (T*)dy, (T*)dres);
   return check_launch("tdeed_bn_act_bwd(apply)");
+}
+
+template <typename T>
+static int run_bwd(const void* dz, const void* z, const void* y, long long M, int C, const float* stats, float* dgamma,
+                   float* dbeta, void* dy, void* dres, float* ws, cudaStream_t st) {
+  if (!z) return run_bwd_mode<T, 0>(dz, z, y, M, C, stats, dgamma, dbeta, dy, dres, ws, st);
+  if (z == y) return run_bwd_mode<T, 1>(dz, z, y, M, C, stats, dgamma, dbeta, dy, dres, ws, st);
+  return run_bwd_mode<T, 2>(dz, z, y, M, C, stats, dgamma, dbeta, dy, dres, ws, st);
 }
 
 }  // namespace tdeed

@@ -196,7 +196,7 @@ static int launch_bwd_weight(const void* x, const void* dy, int n, int h, int w,
   int rc = check_launch("tdeed_conv3x3g_bwd_weight(partial)");
   if (rc) return rc;
   const long long count = (long long)c * gw * 9;
-  partial_sum_kernel<<<(unsigned)ceil_div_ll(count, 256), 256, 0, st>>>(ws, parts, count, dw);
+  launch_partial_sum(ws, parts, count, dw, st);
   return check_launch("tdeed_conv3x3g_bwd_weight(final)");
 }
 
@@ -410,6 +410,6 @@ extern "C" int tdeed_stem_bwd_weight(const void* frames, int frames_dtype, int u
 #undef SW_CASE
   int rc = check_launch("tdeed_stem_bwd_weight(partial)");
   if (rc) return rc;
-  partial_sum_kernel<<<ceil_div(864, 256), 256, 0, st>>>(workspace, grid, 864, dw);
+  launch_partial_sum(workspace, grid, 864, dw, st);
   return check_launch("tdeed_stem_bwd_weight(final)");
 }

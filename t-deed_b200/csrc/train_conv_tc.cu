@@ -314,7 +314,7 @@ int conv3x3g_bwd_weight_tc_launch(const void* x, const void* dy, int n, int h, i
   rc = check_launch("tdeed_conv3x3g_bwd_weight(tcgen05)");
   if (rc) return rc;
   const long long count = (long long)c * gw * 9;
-  partial_sum_kernel<<<(unsigned)ceil_div_ll(count, 256), 256, 0, st>>>(ws, pl.splits, count, dw);
+  launch_partial_sum(ws, pl.splits, count, dw, st);
   return check_launch("tdeed_conv3x3g_bwd_weight(tcgen05 final)");
 }
 

@@ -159,32 +159,64 @@ gsf_bwd_pix_kernel(const T* __restrict__ x, const T* __restrict__ dcat, int clip
 }
 
 // ---- 4. conv3d transpose + ReLU mask ----
+// Thread = one pixel: its 27 (x 2 gate groups) dpre neighbours are loaded ONCE into registers (bounds handled there), then the
+// channel loop is 27 FMAs against weights read as broadcast 16 B shared-memory vectors.  x and dbn pass through shared
+// memory in 32-channel chunks so that global accesses stay coalesced.  (One thread per (pixel, channel) re-did the 27 bounds
+// checks / address computations / global loads for every channel and was instruction-issue bound, ~8x off the HBM time.)
+constexpr int GZ_PIX = 128;      // pixels (threads) per CTA
+constexpr int GZ_CH = 32;        // channels per staging chunk
+constexpr int GZ_LD = GZ_CH + 1;
+static size_t gsf_bwd_z_smem(int fold) { return ((size_t)fold * 28 + 2 * fold + 2 * GZ_PIX * GZ_LD) * sizeof(float); }
+
+__device__ __forceinline__ float dot27(const float* __restrict__ wk, const float (&d)[27]) {
+  float acc = 0.f;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) {
+    const float4 wv = *reinterpret_cast<const float4*>(wk + 4 * q);
+    acc = fmaf(wv.x, d[4 * q], acc);
+    acc = fmaf(wv.y, d[4 * q + 1], acc);
+    acc = fmaf(wv.z, d[4 * q + 2], acc);
+    acc = fmaf(wv.w, d[4 * q + 3], acc);
+  }
+  const float4 wv = *reinterpret_cast<const float4*>(wk + 24);
+  acc = fmaf(wv.x, d[24], acc);
+  acc = fmaf(wv.y, d[25], acc);
+  acc = fmaf(wv.z, d[26], acc);
+  return acc;
+}
+
 template <typename T>
-__global__ void __launch_bounds__(GB_THREADS)
+__global__ void __launch_bounds__(GZ_PIX)
 gsf_bwd_z_kernel(const T* __restrict__ x, int clip_len, int h, int w, int c, int fold, const float* __restrict__ stats,
-                 const float* __restrict__ w3d, const float* __restrict__ dpre, long long total, float* __restrict__ dbn) {
-  extern __shared__ float s_w[];        // [fold][27]
-  for (int i = threadIdx.x; i < fold * 27; i += GB_THREADS) s_w[i] = w3d[i];
-  __syncthreads();
-  const long long idx = (long long)blockIdx.x * GB_THREADS + threadIdx.x;
-  if (idx >= total) return;
-  const int ch = (int)(idx % fold);
-  const long long fp = idx / fold;
+                 const float* __restrict__ w3d, const float* __restrict__ dpre, long long M, float* __restrict__ dbn) {
+  extern __shared__ __align__(16) float s_gz[];
+  float* s_w = s_gz;                        // [fold][28]
+  float* s_sc = s_w + (size_t)fold * 28;    // [fold] scale, [fold] shift
+  float* s_x = s_sc + 2 * fold;             // [GZ_PIX][GZ_LD]
+  float* s_o = s_x + GZ_PIX * GZ_LD;        // [GZ_PIX][GZ_LD]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < fold * 28; i += GZ_PIX) {
+    const int ch = i / 28, tap = i - ch * 28;
+    s_w[i] = tap < 27 ? w3d[ch * 27 + tap] : 0.f;
+  }
+  for (int i = tid; i < 2 * fold; i += GZ_PIX) s_sc[i] = stats[2 * fold + i];
   const int hw = h * w;
-  const int p = (int)(fp % hw);
-  const long long f = fp / hw;
-  const int t = (int)(f % clip_len);
-  const int py = p / w, px = p - py * w;
-  const int g = ch / (fold / 2);
-  const float xv = Elem<T>::ld(x + (size_t)fp * c + ch);
-  float dz = 0.f;
-  if (fmaf(xv, stats[2 * fold + ch], stats[3 * fold + ch]) > 0.f) {
-    const float* wk = s_w + ch * 27;
+  const long long base = (long long)blockIdx.x * GZ_PIX;
+  const long long fp = base + tid;
+  float d0[27], d1[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) d0[i] = d1[i] = 0.f;
+  if (fp < M) {
+    const int p = (int)(fp % hw);
+    const long long f = fp / hw;
+    const int t = (int)(f % clip_len);
+    const int py = p / w, px = p - py * w;
+    const float2* dp2 = reinterpret_cast<const float2*>(dpre);
 #pragma unroll
     for (int kt = 0; kt < 3; ++kt) {
       const int tt = t - (kt - 1);
       if (tt < 0 || tt >= clip_len) continue;
-      const float* dp = dpre + (size_t)(f - t + tt) * hw * 2;
+      const float2* dp = dp2 + (size_t)(f - t + tt) * hw;
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int yy = py - (ky - 1);
@@ -193,12 +225,36 @@ gsf_bwd_z_kernel(const T* __restrict__ x, int clip_len, int h, int w, int c, int
         for (int kx = 0; kx < 3; ++kx) {
           const int xx = px - (kx - 1);
           if (xx < 0 || xx >= w) continue;
-          dz = fmaf(wk[kt * 9 + ky * 3 + kx], dp[((size_t)yy * w + xx) * 2 + g], dz);
+          const float2 v = dp[yy * w + xx];
+          d0[kt * 9 + ky * 3 + kx] = v.x;
+          d1[kt * 9 + ky * 3 + kx] = v.y;
         }
       }
     }
   }
-  dbn[idx] = dz;
+  const int half = fold / 2;
+  const int npx = (int)((M - base) < GZ_PIX ? (M - base) : GZ_PIX);
+  for (int c0 = 0; c0 < fold; c0 += GZ_CH) {
+    const int nc = min(GZ_CH, fold - c0);
+    __syncthreads();                         // previous chunk's s_o readers are done (and s_w / s_sc are filled)
+    for (int i = tid; i < npx * nc; i += GZ_PIX) {
+      const int pi = i / nc, j = i - pi * nc;
+      s_x[pi * GZ_LD + j] = Elem<T>::ld(x + (size_t)(base + pi) * c + c0 + j);
+    }
+    __syncthreads();
+    for (int j = 0; j < nc; ++j) {
+      const int ch = c0 + j;                  // uniform over the CTA
+      const float xv = s_x[tid * GZ_LD + j];
+      const float* wk = s_w + ch * 28;
+      const float dz = ch < half ? dot27(wk, d0) : dot27(wk, d1);
+      s_o[tid * GZ_LD + j] = fmaf(xv, s_sc[ch], s_sc[fold + ch]) > 0.f ? dz : 0.f;
+    }
+    __syncthreads();
+    for (int i = tid; i < npx * nc; i += GZ_PIX) {
+      const int pi = i / nc, j = i - pi * nc;
+      dbn[(size_t)(base + pi) * fold + c0 + j] = s_o[pi * GZ_LD + j];
+    }
+  }
 }
 
 // ---- 5. BatchNorm backward over the fold slice ----
@@ -210,6 +266,7 @@ struct GsfBnOp {
   int fold;
   const float* stats;
   float mu[8], is[8];
+  static constexpr int kBatch = 1;
   __device__ void begin(int ch0, int nch) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -275,15 +332,20 @@ gsf_bwd_final_kernel(const T* __restrict__ x, const T* __restrict__ dcat, const 
 }
 
 // ---- 6. conv3D weight gradient partials.  grid (row blocks, frames) ----
+// Work item = (channel, kt) with the nine (ky, kx) taps in registers: per pixel one dpre value and a sliding 3x3 window of z
+// (3 new shared-memory reads per step) feed 9 FMAs — 2.25 FMA per LDS instead of 0.5 with one tap per thread.  When there are
+// fewer items than threads (small fold) the rows of the tile are dealt out to several thread slices per item and the slices are
+// added in slice order through shared memory.
 template <typename T>
 __global__ void __launch_bounds__(GB_THREADS)
 gsf_bwd_w3d_kernel(const T* __restrict__ x, int clip_len, int h, int w, int c, int fold, int rows_per_cta,
                    const float* __restrict__ stats, const float* __restrict__ dpre, float* __restrict__ part) {
   extern __shared__ float smem[];
   const int wp = w + 2, rp = rows_per_cta + 2;
-  const int plane = rp * wp + 1;
+  const int plane = (rp * wp) | 1;                 // odd channel stride: lanes on different channels hit different banks
   float* s_z = smem;                               // [fold][plane]   rows y0-1 .. y0+rows, cols -1 .. w
-  float* s_d = smem + (size_t)fold * plane;        // [3 kt][2 g][rows_per_cta * w]
+  float* s_d = smem + (size_t)fold * ((size_t)rp * wp + 1);        // [3 kt][2 g][rows_per_cta * w]
+  float* s_r = s_d + (size_t)6 * rows_per_cta * w;                 // [GB_THREADS][9] slice partials
   const int f = blockIdx.y, t = f % clip_len;
   const int y0 = blockIdx.x * rows_per_cta;
   const int rows = min(rows_per_cta, h - y0);
@@ -307,20 +369,55 @@ gsf_bwd_w3d_kernel(const T* __restrict__ x, int clip_len, int h, int w, int c, i
   }
   __syncthreads();
   const int half = fold / 2;
+  const int items = fold * 3;
+  const int nsl = items >= GB_THREADS ? 1 : GB_THREADS / items;
   float* o = part + ((size_t)f * gridDim.x + blockIdx.x) * fold * 27;
-  for (int item = threadIdx.x; item < fold * 27; item += GB_THREADS) {
-    const int ch = item / 27, tap = item - ch * 27;
-    const int kt = tap / 9, ky = (tap % 9) / 3, kx = tap % 3;
-    const int g = ch / half;
-    const float* d = s_d + (kt * 2 + g) * npx;
-    const float* z = s_z + ch * plane;
-    float s = 0.f;
-    for (int py = 0; py < rows; ++py) {
-      const float* zr = z + (py + ky) * wp + kx;     // z at (y0 + py + ky - 1, px + kx - 1)
-      const float* dr = d + py * w;
-      for (int px = 0; px < w; ++px) s = fmaf(dr[px], zr[px], s);
+  for (int it0 = 0; it0 < items; it0 += GB_THREADS) {
+    const int item = nsl == 1 ? it0 + (int)threadIdx.x : (int)threadIdx.x % items;
+    const int sl = nsl == 1 ? 0 : (int)threadIdx.x / items;
+    const bool active = item < items && sl < nsl;
+    const int ch = item / 3, kt = item - ch * 3;
+    float acc[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+    if (active) {
+      const float* d = s_d + (kt * 2 + ch / half) * npx;
+      const float* z = s_z + ch * plane;
+      for (int py = sl; py < rows; py += nsl) {
+        const float* z0 = z + py * wp;               // z rows y0+py-1, y0+py, y0+py+1 (ky = 0, 1, 2), starting at column -1
+        const float* z1 = z0 + wp;
+        const float* z2 = z1 + wp;
+        const float* dr = d + py * w;
+        float a0 = z0[0], a1 = z0[1], b0 = z1[0], b1 = z1[1], c0 = z2[0], c1 = z2[1];
+        for (int px = 0; px < w; ++px) {
+          const float a2 = z0[px + 2], b2 = z1[px + 2], c2 = z2[px + 2];
+          const float dv = dr[px];
+          acc[0] = fmaf(dv, a0, acc[0]);
+          acc[1] = fmaf(dv, a1, acc[1]);
+          acc[2] = fmaf(dv, a2, acc[2]);
+          acc[3] = fmaf(dv, b0, acc[3]);
+          acc[4] = fmaf(dv, b1, acc[4]);
+          acc[5] = fmaf(dv, b2, acc[5]);
+          acc[6] = fmaf(dv, c0, acc[6]);
+          acc[7] = fmaf(dv, c1, acc[7]);
+          acc[8] = fmaf(dv, c2, acc[8]);
+          a0 = a1; a1 = a2; b0 = b1; b1 = b2; c0 = c1; c1 = c2;
+        }
+      }
     }
-    o[item] = s;
+    if (nsl > 1) {                                  // single pass in this case (items < GB_THREADS)
+#pragma unroll
+      for (int k = 0; k < 9; ++k) s_r[threadIdx.x * 9 + k] = acc[k];
+      __syncthreads();
+      if (active && sl == 0)
+        for (int q = 1; q < nsl; ++q)
+#pragma unroll
+          for (int k = 0; k < 9; ++k) acc[k] += s_r[(q * items + item) * 9 + k];
+    }
+    if (active && sl == 0) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) o[ch * 27 + kt * 9 + k] = acc[k];
+    }
   }
 }
 
@@ -335,8 +432,10 @@ static GsfBwdPlan gsf_bwd_plan(int clips, int clip_len, int h, int w, int fold) 
   GsfBwdPlan p;
   const size_t n = (size_t)clips * clip_len, hw = (size_t)h * w;
   int rows = h;
-  auto need = [&](int r) { return ((size_t)fold * ((size_t)(r + 2) * (w + 2) + 1) + (size_t)6 * r * w) * sizeof(float); };
-  while (rows > 1 && need(rows) > 160 * 1024) rows = (rows + 1) / 2;
+  auto need = [&](int r) { return ((size_t)fold * ((size_t)(r + 2) * (w + 2) + 1) + (size_t)6 * r * w + GB_THREADS * 9) * sizeof(float); };
+  // small tiles: 3+ CTAs per SM hide the staging phase of one behind the FMA phase of the others; the price is the halo rows
+  while (rows > 4 && need(rows) > 76 * 1024) rows = (rows + 1) / 2;
+  while (rows > 1 && need(rows) > 200 * 1024) rows = (rows + 1) / 2;
   p.rows = rows;
   p.rblocks = ceil_div(h, rows);
   p.smem_w3d = need(rows);
@@ -377,14 +476,24 @@ static int run_gsf_bwd(int mode, const void* x, const void* dcat, const void* ad
     if ((rc = check_launch("tdeed_gsf_bwd(dwgt)"))) return rc;
     gsf_bwd_plane_kernel<<<n, GB_THREADS, 0, st>>>(dA, sums, clip_len, hw, fold, cc_w, dP0, dP1, ccpart);
     if ((rc = check_launch("tdeed_gsf_bwd(plane)"))) return rc;
-    partial_sum_kernel<<<1, 64, 0, st>>>(ccpart, n, 38, dcc);
+    launch_partial_sum(ccpart, n, 38, dcc, st);
     if ((rc = check_launch("tdeed_gsf_bwd(cc)"))) return rc;
   }
   gsf_bwd_pix_kernel<T><<<(unsigned)ceil_div_ll(M * 2, GB_THREADS), GB_THREADS, 0, st>>>(
       (const T*)x, (const T*)dcat, clip_len, hw, c, fold, mode, gate, wgt, dP0, dP1, M * 2, dxa, dpre);
   if ((rc = check_launch("tdeed_gsf_bwd(pix)"))) return rc;
-  gsf_bwd_z_kernel<T><<<(unsigned)ceil_div_ll(M * fold, GB_THREADS), GB_THREADS, (size_t)fold * 27 * sizeof(float), st>>>(
-      (const T*)x, clip_len, h, w, c, fold, stats, w3d, dpre, M * fold, dbn);
+  {
+    auto kz = gsf_bwd_z_kernel<T>;
+    const size_t smem_z = gsf_bwd_z_smem(fold);
+    static size_t z_set = 48 * 1024;
+    if (smem_z > z_set) {
+      cudaError_t e = cudaFuncSetAttribute(kz, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      TDEED_REQUIRE(e == cudaSuccess, TDEED_ERR_CUDA, "tdeed_gsf_bwd: cudaFuncSetAttribute(z): %s", cudaGetErrorString(e));
+      z_set = 200 * 1024;
+    }
+    TDEED_REQUIRE(smem_z <= 200 * 1024, TDEED_ERR_UNSUPPORTED, "tdeed_gsf_bwd: fold %d too large for the conv3d^T kernel", fold);
+    kz<<<(unsigned)ceil_div_ll(M, GZ_PIX), GZ_PIX, smem_z, st>>>((const T*)x, clip_len, h, w, c, fold, stats, w3d, dpre, M, dbn);
+  }
   if ((rc = check_launch("tdeed_gsf_bwd(z)"))) return rc;
   GsfBnOp<T> op;
   op.dbn = dbn;
@@ -411,7 +520,7 @@ static int run_gsf_bwd(int mode, const void* x, const void* dcat, const void* ad
   TDEED_REQUIRE(p.smem_w3d <= 200 * 1024, TDEED_ERR_UNSUPPORTED, "tdeed_gsf_bwd: a row of %d px x %d ch does not fit shared memory", w, fold);
   kw<<<dim3(p.rblocks, n), GB_THREADS, p.smem_w3d, st>>>((const T*)x, clip_len, h, w, c, fold, p.rows, stats, dpre, w3dpart);
   if ((rc = check_launch("tdeed_gsf_bwd(w3d)"))) return rc;
-  partial_sum_kernel<<<ceil_div(fold * 27, 256), 256, 0, st>>>(w3dpart, n * p.rblocks, (long long)fold * 27, dw3d);
+  launch_partial_sum(w3dpart, n * p.rblocks, (long long)fold * 27, dw3d, st);
   if ((rc = check_launch("tdeed_gsf_bwd(w3d final)"))) return rc;
   return tdeed_colsum(TDEED_F32, dpre, M, 2, 2, db3d, cs, st);
 }

@@ -23,6 +23,7 @@ __host__ __device__ inline BnLayout bn_layout(int C) {
 __device__ inline void warp_partial_sums(const float* __restrict__ part, int nparts, int cpad, int ch, double& s, double& q) {
   const int lane = threadIdx.x & 31;
   double a = 0.0, b = 0.0;
+#pragma unroll 4
   for (int p = lane; p < nparts; p += 32) {
     a += (double)part[((size_t)p * 2) * cpad + ch];
     b += (double)part[((size_t)p * 2 + 1) * cpad + ch];
@@ -49,7 +50,22 @@ __global__ void __launch_bounds__(BN_THREADS) bn_reduce_kernel(OP op, long long 
   if (active) {
     const int nch = min(8, C - c8 * 8);
     op.begin(c8 * 8, nch);
-    for (long long r = (long long)blockIdx.x * l.rpi + lr; r < M; r += (long long)gridDim.x * l.rpi) op.row(r, c8 * 8, nch, a0, a1);
+    const long long stride = (long long)gridDim.x * l.rpi;
+    long long r = (long long)blockIdx.x * l.rpi + lr;
+    if constexpr (OP::kBatch > 1) {
+      // kBatch rows per trip: all their loads are issued before the first accumulate, so a thread keeps kBatch x 16-32 B in
+      // flight (one row at a time left these reductions at 0.4-0.5 of the HBM rate the elementwise passes reach)
+      if (nch == 8) {
+        for (; r + (OP::kBatch - 1) * stride < M; r += OP::kBatch * stride) {
+          typename OP::Regs rg[OP::kBatch];
+#pragma unroll
+          for (int u = 0; u < OP::kBatch; ++u) op.load(r + u * stride, c8 * 8, rg[u]);
+#pragma unroll
+          for (int u = 0; u < OP::kBatch; ++u) op.acc(rg[u], a0, a1);
+        }
+      }
+    }
+    for (; r < M; r += stride) op.row(r, c8 * 8, nch, a0, a1);
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -77,13 +93,29 @@ __device__ inline void load_n(const T* p, int nch, float (&v)[8]) {
 }
 
 
-// out[i] = sum_p part[p][i], summed in double in a fixed order
-static __global__ void partial_sum_kernel(const float* __restrict__ part, int nparts, long long count, float* __restrict__ out) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
+// out[i] = sum_p part[p][i], summed in double in a fixed order.  CTA = 32 outputs x 8 slices of the partials (lane = output, so
+// every load is a coalesced 128 B row segment); the slices meet in shared memory and are added in slice order.  One thread per
+// output walking all partials serially left ~10 CTAs on the machine for the gate-shift / conv weight gradients.
+constexpr int PS_SLICES = 8;
+static __global__ void __launch_bounds__(32 * PS_SLICES)
+partial_sum_kernel(const float* __restrict__ part, int nparts, long long count, float* __restrict__ out) {
+  __shared__ double s_p[PS_SLICES][33];
+  const int lane = threadIdx.x & 31, slice = threadIdx.x >> 5;
+  const long long i = (long long)blockIdx.x * 32 + lane;
   double s = 0.0;
-  for (int p = 0; p < nparts; ++p) s += (double)part[(size_t)p * count + i];
-  out[i] = (float)s;
+  if (i < count)
+    for (int p = slice; p < nparts; p += PS_SLICES) s += (double)part[(size_t)p * count + i];
+  s_p[slice][lane] = s;
+  __syncthreads();
+  if (slice == 0 && i < count) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < PS_SLICES; ++q) t += s_p[q][lane];
+    out[i] = (float)t;
+  }
+}
+static inline void launch_partial_sum(const float* part, int nparts, long long count, float* out, cudaStream_t st) {
+  partial_sum_kernel<<<(unsigned)ceil_div_ll(count, 32), 32 * PS_SLICES, 0, st>>>(part, nparts, count, out);
 }
 
 inline int bn_grid(long long M, int C) {

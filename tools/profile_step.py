@@ -41,9 +41,16 @@ def main():
         step()
     torch.cuda.synchronize()
     torch.cuda.profiler.start()
+    eng.prof = []
     step()
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()
+    # launch-ordered family labels of the GEMM launches, so tools/traffic_from_ncu.py can attribute the ncu rows
+    import json
+    labels = [(lab, nb) for lab, _, nb, _, _ in eng.prof if lab in ('conv1x1', 'conv1x1_ds', 'sgp_gemm')]
+    os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+    json.dump(dict(clips_per_batch=B, precision=precision, gemm_launches=labels),
+              open(os.path.join(ROOT, 'gpurun_out', 'profile_step_labels.json'), 'w'))
 
 
 if __name__ == '__main__':
