@@ -1,0 +1,50 @@
+// Straight-line bf16 epilogue pieces shared by the tcgen05 GEMM kernels (gemm_tc.cu, gemm_thin.cu).
+#pragma once
+#include "common.cuh"
+
+namespace tdeed {
+
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
+// One 16-column accumulator piece of one row -> + bias (+ bf16 residual), clamp at `lo` (0 = ReLU, -inf = none), bf16, store.
+// Straight-line code (no runtime dtype / activation switches), so the 8-column groups interleave in the schedule.
+template <bool STAGED>
+__device__ __forceinline__ void epi_fast_chunk(const uint32_t (&acc)[16], const uint4& r0, const uint4& r1, const float* __restrict__ bias,
+                                               int c0, int ncols, float lo, uint32_t srow_addr, __nv_bfloat16* grow) {
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int cl = c0 + 8 * h;
+    if (cl < ncols) {
+      const float4 b0 = *reinterpret_cast<const float4*>(bias + cl);
+      const float4 b1 = *reinterpret_cast<const float4*>(bias + cl + 4);
+      const uint4 rv = h ? r1 : r0;
+      const uint32_t w4[4] = {rv.x, rv.y, rv.z, rv.w};
+      float v[8];
+      v[0] = __uint_as_float(acc[8 * h + 0]) + b0.x; v[1] = __uint_as_float(acc[8 * h + 1]) + b0.y;
+      v[2] = __uint_as_float(acc[8 * h + 2]) + b0.z; v[3] = __uint_as_float(acc[8 * h + 3]) + b0.w;
+      v[4] = __uint_as_float(acc[8 * h + 4]) + b1.x; v[5] = __uint_as_float(acc[8 * h + 5]) + b1.y;
+      v[6] = __uint_as_float(acc[8 * h + 6]) + b1.z; v[7] = __uint_as_float(acc[8 * h + 7]) + b1.w;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {           // residual words are zero when there is no residual
+        v[2 * q] += __uint_as_float(w4[q] << 16);
+        v[2 * q + 1] += __uint_as_float(w4[q] & 0xffff0000u);
+      }
+      uint4 o;
+      o.x = pack_bf16x2(fmaxf(v[0], lo), fmaxf(v[1], lo));
+      o.y = pack_bf16x2(fmaxf(v[2], lo), fmaxf(v[3], lo));
+      o.z = pack_bf16x2(fmaxf(v[4], lo), fmaxf(v[5], lo));
+      o.w = pack_bf16x2(fmaxf(v[6], lo), fmaxf(v[7], lo));
+      if (STAGED) sts128(srow_addr + (uint32_t)cl * 2u, o);
+      else if (grow) *reinterpret_cast<uint4*>(grow + cl) = o;
+    }
+  }
+}
+
+}  // namespace tdeed

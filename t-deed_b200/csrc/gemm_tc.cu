@@ -15,8 +15,10 @@
 // strided view of an NHWC tensor (every `stride`-th pixel): the stride-2 1x1 shortcut conv as implicit GEMM.
 // K tails and M / N tails rely on TMA out-of-bounds zero fill and masked stores.
 #include "common.cuh"
+#include "gemm_epilogue.cuh"
 #include <cuda.h>
 #include <cstdlib>
+#include <cstdio>
 
 namespace tdeed {
 
@@ -45,6 +47,7 @@ struct TcParams {
   uint32_t w_kb_stride, w_res_bytes;
   int out_bufs;   // 1 or 2 output staging tiles
   int staged;     // 1: outputs go through the smem staging tile (coalesced stores); 0: row pieces straight from registers
+  int fast;       // 1: specialised epilogue (bf16 out / bf16 residual, act none|relu): whole-row residual prefetch, pipelined TMEM loads
   int debug;   // TDEED_GEMM_DEBUG (dev only): 1 = skip global stores, 2 = skip TMEM loads, 4 = skip the MMAs
 };
 
@@ -132,6 +135,52 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+
+template <bool STAGED>
+__device__ __forceinline__ void epi_fast_tile(const TcParams& p, uint64_t* full_bar, uint32_t parity, uint32_t tmem_row, int half,
+                                              int ncols, int n0, long long m, bool row_ok, const float* s_bias, uint32_t srow_addr) {
+  // the residual row pieces of the thread's first TWO chunks are requested before the accumulator wait (their latency hides
+  // behind the MMA of this tile), the piece of chunk k+2 when chunk k has been consumed.  (One chunk at a time, requested
+  // right before its use, exposed ~1 us of global latency per chunk: 24 % of the epilogue's stall samples.)
+  uint4 rres[2][4];
+  const bool has_res = p.residual != nullptr && row_ok;
+  const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + m * p.ldr + n0;
+  auto load_res = [&](uint4 (&dst)[4], int c0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      dst[q] = make_uint4(0u, 0u, 0u, 0u);
+      if (has_res && c0 + 8 * q < ncols) dst[q] = *reinterpret_cast<const uint4*>(rp + c0 + 8 * q);
+    }
+  };
+  load_res(rres[0], half * 32);
+  load_res(rres[1], half * 32 + 64);
+  mbar_wait(full_bar, parity);
+  tcgen05_fence_after();
+  const float lo = p.act == TDEED_ACT_RELU ? 0.f : -INFINITY;
+  __nv_bfloat16* grow = (!STAGED && row_ok) ? reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo + n0 : nullptr;
+  const float* bias = s_bias + n0;
+  uint32_t va[16], vb[16];
+  // TMEM loads (16 columns each) run one piece ahead of the arithmetic; piece s covers columns c(s) = half*32 + 64*(s/2) + 16*(s%2)
+  if (half * 32 < ncols) tmem_ld16(tmem_row + (uint32_t)(half * 32), va);
+#pragma unroll
+  for (int s = 0; s < 8; ++s) {
+    const int k = s >> 1, sub = s & 1;
+    const int c0 = half * 32 + 64 * k + 16 * sub;
+    const int cn = half * 32 + 64 * ((s + 1) >> 1) + 16 * ((s + 1) & 1);      // next piece
+    if (c0 < ncols) {                          // uniform over the warp
+      tmem_ld_wait();
+      if (s & 1) {
+        if (s < 7 && cn < ncols) tmem_ld16(tmem_row + (uint32_t)cn, va);
+        epi_fast_chunk<STAGED>(vb, rres[k & 1][2], rres[k & 1][3], bias, c0, ncols, lo, srow_addr, grow);
+        if (k < 2) load_res(rres[k & 1], c0 - 16 + 128);
+      } else {
+        if (cn < ncols) tmem_ld16(tmem_row + (uint32_t)cn, vb);
+        epi_fast_chunk<STAGED>(va, rres[k & 1][0], rres[k & 1][1], bias, c0, ncols, lo, srow_addr, grow);
+      }
+    }
+  }
+}
 
 // ---------------------------------------------------------------- kernel
 struct TileCoord { int mt, nt; };
@@ -296,6 +345,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const int ncols = min(p.block_n, p.N - n0);           // multiple of 8
       const uint32_t tmem_row = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * (uint32_t)p.block_n;
       uint8_t* srow = s_out + r * pitch;
+      if (p.fast) {
+        if (p.staged && p.out_bufs == 1 && j > 0) epi_bar_sync();   // single staging tile: previous phase 2 must have drained
+        if (p.staged) epi_fast_tile<true>(p, &tmem_full_bar[acc], (j >> 1) & 1u, tmem_row, half, ncols, n0, m, row_ok, s_bias, smem_u32(srow));
+        else epi_fast_tile<false>(p, &tmem_full_bar[acc], (j >> 1) & 1u, tmem_row, half, ncols, n0, m, row_ok, s_bias, 0u);
+        tcgen05_fence_before();
+        mbar_arrive(&tmem_empty_bar[acc]);
+        if (!p.staged) continue;
+        epi_bar_sync();
+        // phase 2: a warp copies 16 rows; lanes cover the 16-byte chunks of one row (or of several rows when rows are short)
+        const int cpr = ncols >> 3;                           // <= 32
+        const int rpp = 32 / cpr;
+        const int sub = lane / cpr, ch = lane - sub * cpr;
+        const int ew = warp - 2;
+        if (sub < rpp) {
+          const uint32_t s_out_addr = smem_u32(s_out);
+          for (int rr = sub; rr < 16; rr += rpp) {
+            const int row = ew * 16 + rr;
+            const long long mm = s_rowm[row];
+            if (mm >= 0)
+              *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(p.out) + ((size_t)mm * p.ldo + n0) * 2 + (size_t)ch * 16) =
+                  lds128(s_out_addr + (uint32_t)(row * pitch + ch * 16));
+          }
+        }
+        continue;
+      }
       bool waited = false;
       if (p.staged && p.out_bufs == 1 && j > 0) epi_bar_sync();   // single staging tile: previous phase 2 must have drained
       for (int c0 = half * 32; c0 < ncols; c0 += 64) {
@@ -537,8 +611,19 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
   // Staging pays one CTA-wide barrier per tile: measured (tools/gemm_micro.py) to win for wide rows without a
   // residual (s3/s4 conv1: -10..-25 %) and to lose for thin rows or when the residual read already pulled the
   // row's lines into L1.
+  static int dbg = -1;
+  if (dbg < 0) { const char* e = getenv("TDEED_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+  p.debug = dbg;
+  static int fast_env = -1;
+  if (fast_env < 0) { const char* e = getenv("TDEED_GEMM_FAST_EPI"); fast_env = e ? atoi(e) : 1; }
+  p.fast = (fast_env && dbg == 0 && out_dtype == TDEED_BF16 && (act == TDEED_ACT_NONE || act == TDEED_ACT_RELU) && block_n <= 256) ? 1 : 0;
+  // With the specialised epilogue the direct row-piece stores win for one-n-tile and short-K layers (ncu per-launch times,
+  // 57-clip batch: N = 152 conv1 198 vs 281 us, K 152 -> N 368 454 vs 571 us, strided shortcut convs 252 vs 370 us): no
+  // CTA-wide barrier, no second pass over the tile.  The wide long-K layers without a residual (s4 conv1, K = N = 368) still
+  // prefer the staged, coalesced stores (171 vs 245 us).
   const char* force_staged = getenv("TDEED_GEMM_STAGED");
-  p.staged = force_staged ? atoi(force_staged) : (residual == nullptr && N >= 96 ? 1 : 0);
+  const bool direct_wins = p.fast && (N <= 256 || K <= 192);
+  p.staged = force_staged ? atoi(force_staged) : (!direct_wins && residual == nullptr && N >= 96 ? 1 : 0);
   if (p.w_res && big_slice) p.staged = 0;
   const size_t stage_out_bytes = p.staged ? (size_t)TC_BM * ((size_t)block_n * (out_dtype == TDEED_F32 ? 4 : 2) + 16) : 0;
   const size_t fixed = 1024 + p.w_res_bytes + (2 * TC_MAX_STAGES + 6) * sizeof(uint64_t) + bias_bytes + 2 * TC_BM * sizeof(long long) + stage_out_bytes;
@@ -555,12 +640,14 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
     TDEED_REQUIRE(e == cudaSuccess, TDEED_ERR_CUDA, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
-  static int dbg = -1;
-  if (dbg < 0) { const char* e = getenv("TDEED_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
-  p.debug = dbg;
   const int num_tiles = p.m_tiles * p.n_tiles;
   int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
   if (p.w_res) grid -= grid % p.n_tiles;             // every CTA then sees one fixed n-tile: its resident W slice
+  static int trace = -1;
+  if (trace < 0) { const char* e = getenv("TDEED_GEMM_TRACE"); trace = e ? atoi(e) : 0; }
+  if (trace)
+    fprintf(stderr, "gemm_tc M=%lld N=%d K=%d nseg=%d gather=%d res=%d act=%d | block_n=%d n_tiles=%d w_res=%d stages=%d staged=%d out_bufs=%d fast=%d grid=%d smem=%zu\n",
+            M, N, K, nseg, p.gather, residual != nullptr, act, block_n, p.n_tiles, p.w_res, stages, p.staged, p.out_bufs, p.fast, grid, smem);
   gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], p);
   return check_launch("tdeed_gemm_fwd(tcgen05)");
 }

@@ -11,6 +11,8 @@
 //   * 8 epilogue warps drain TMEM (tcgen05.ld.x32) -> bias / residual / activation -> 16-byte stores.
 // A 16-stage ring of 8..16 KB stages keeps > 64 KB of loads in flight per SM.
 #include "common.cuh"
+#include "gemm_epilogue.cuh"
+#include <cstdlib>
 
 namespace tdeed {
 
@@ -40,6 +42,8 @@ struct ThinParams {
   long long ldo;
   int out_dtype;
   uint32_t tmem_cols;
+  int fast;    // specialised bf16 epilogue (act none|relu): pipelined TMEM loads, cross-tile residual prefetch
+  int split;   // fast && N <= 32: the two epilogue warp halves take alternate tiles (otherwise half of them would idle)
 };
 
 __device__ __forceinline__ uint32_t th_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -97,6 +101,14 @@ __device__ __forceinline__ void th_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void th_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void th_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __global__ void __launch_bounds__(TH_THREADS, 1)
 gemm_thin_kernel(const ThinParams p) {
@@ -135,7 +147,7 @@ gemm_thin_kernel(const ThinParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       th_mbar_init(&tmem_full_bar[a], 1);
-      th_mbar_init(&tmem_empty_bar[a], 256);
+      th_mbar_init(&tmem_empty_bar[a], p.split ? 128 : 256);   // arrivals per accumulator drain
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -150,30 +162,62 @@ gemm_thin_kernel(const ThinParams p) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp < TH_PROD_WARPS) {
-    // ===== cp.async producers: 128 threads, chunk q = t + 128*i of the tile's 128 x kc_total 16-byte chunks =====
+    // ===== cp.async producers: 128 threads, chunk q = t + 128*i (i < kc_total) of the tile's 128 x kc_total 16-byte chunks =====
+    // The (row, chunk) of a thread's i-th copy does not depend on the tile, so the shared-memory offset, the global element
+    // offset and the segment are computed ONCE; per tile a copy is then an add and a cp.async.  (Recomputing them per chunk cost
+    // ~66 instructions per 16 bytes and made these four warps the bottleneck of the whole kernel: ncu r1h, 464 producer
+    // instructions per warp and tile while MMA and epilogue warps sat in their barrier waits.)
     const int t = threadIdx.x;
-    const uint32_t kc_magic = ((1u << 24) + (uint32_t)p.kc_total - 1u) / (uint32_t)p.kc_total;
     const uint32_t sA_u32 = th_smem_u32(sA);
-    uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
-      const int stage = it % p.num_stages;
-      const uint32_t round = it / p.num_stages;
+    uint32_t soff[8], goff[8], rowi[8];
+    uint32_t seg1 = 0u;                       // bit i: the i-th copy reads segment 1
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int q = t + 32 * TH_PROD_WARPS * i;
+      const int row = q / p.kc_total, c = q - row * p.kc_total;
+      rowi[i] = (uint32_t)row;
+      soff[i] = (uint32_t)c * p.a_plane_bytes + (uint32_t)row * 16u;
+      if (c < p.kc[0]) {
+        goff[i] = (uint32_t)(row * p.lda[0] + p.col0[0] + c * 8);
+      } else {
+        goff[i] = (uint32_t)(row * p.lda[1] + p.col0[1] + (c - p.kc[0]) * 8);
+        seg1 |= 1u << i;
+      }
+    }
+    const int n_it = p.kc_total;              // 128 * kc_total chunks over 128 threads
+    const long long lda0 = p.lda[0], lda1 = p.lda[1];
+    const __nv_bfloat16* a0 = p.a[0];
+    const __nv_bfloat16* a1 = p.a[1];
+    const int num_stages = p.num_stages, m_tiles = p.m_tiles;
+    const uint32_t stage_bytes = p.stage_bytes;
+    const long long M = p.M;
+    int stage = 0;
+    uint32_t round = 0;
+    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x) {
       th_wait(&empty_bar[stage], (round & 1u) ^ 1u);
       const long long m0 = (long long)tile * TH_BM;
-      const uint32_t sbase = sA_u32 + (uint32_t)stage * p.stage_bytes;
-      for (int q = t; q < TH_BM * p.kc_total; q += 32 * TH_PROD_WARPS) {
-        const int row = (int)(((unsigned long long)q * kc_magic) >> 24);
-        const int c = q - row * p.kc_total;
-        const long long m = m0 + row;
-        const bool valid = m < p.M;
-        const __nv_bfloat16* src;
-        if (c < p.kc[0]) src = p.a[0] + (valid ? m : 0) * p.lda[0] + p.col0[0] + c * 8;
-        else src = p.a[1] + (valid ? m : 0) * p.lda[1] + p.col0[1] + (c - p.kc[0]) * 8;
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + (uint32_t)c * p.a_plane_bytes + (uint32_t)row * 16u),
-                     "l"(src), "r"(valid ? 16 : 0) : "memory");
+      const uint32_t sbase = sA_u32 + (uint32_t)stage * stage_bytes;
+      const __nv_bfloat16* b0 = a0 + m0 * lda0;
+      const __nv_bfloat16* b1 = a1 + m0 * lda1;
+      if (m0 + TH_BM <= M) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i < n_it) {
+            const __nv_bfloat16* src = ((seg1 >> i) & 1u ? b1 : b0) + goff[i];
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + soff[i]), "l"(src) : "memory");
+          }
+      } else {                                 // last tile: rows past M are zero-filled (src-size 0), never dereferenced
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i < n_it) {
+            const bool valid = m0 + rowi[i] < M;
+            const __nv_bfloat16* src = valid ? ((seg1 >> i) & 1u ? b1 : b0) + goff[i] : a0;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sbase + soff[i]), "l"(src), "r"(valid ? 16 : 0) : "memory");
+          }
       }
       // the mbarrier receives this thread's arrival once all of its cp.async above have landed
       asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(th_smem_u32(&full_bar[stage])) : "memory");
+      if (++stage == num_stages) { stage = 0; ++round; }
     }
   } else if (warp == TH_PROD_WARPS) {
     // ===== MMA issuer =====
@@ -207,6 +251,61 @@ gemm_thin_kernel(const ThinParams p) {
     const int half = ew >> 2;
     const int r = lg * 32 + lane;
     const int esz = (p.out_dtype == TDEED_F32) ? 4 : 2;
+    if (p.fast) {
+      // Specialised bf16 epilogue.  The residual piece of a thread's FIRST chunk of the NEXT tile is requested before the current
+      // tile is processed, so its global latency overlaps a whole tile of work (with one tile in flight per warp it was fully
+      // exposed: the accumulators are ready long before the epilogue gets to them); TMEM loads run one 16-column piece ahead.
+      const float lo = p.act == TDEED_ACT_RELU ? 0.f : -INFINITY;
+      const uint32_t it_step = p.split ? 2u : 1u;
+      const int cbase = p.split ? 0 : half * 32;
+      const __nv_bfloat16* res = reinterpret_cast<const __nv_bfloat16*>(p.residual);
+      uint4 rres[2][4];
+      auto load_res = [&](uint4 (&dst)[4], long long m, int c0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          dst[q] = make_uint4(0u, 0u, 0u, 0u);
+          if (res != nullptr && m < p.M && c0 + 8 * q < p.N) dst[q] = *reinterpret_cast<const uint4*>(res + m * p.ldr + c0 + 8 * q);
+        }
+      };
+      uint32_t it = p.split ? (uint32_t)half : 0u;
+      long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
+      if (tile < p.m_tiles) load_res(rres[0], tile * TH_BM + r, cbase);
+      for (; tile < p.m_tiles; tile += (long long)it_step * gridDim.x, it += it_step) {
+        const uint32_t acc = it & 1u;
+        const long long m = tile * TH_BM + r;
+        const bool row_ok = m < p.M;
+        const uint32_t tmem_row = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * (uint32_t)p.block_n;
+        __nv_bfloat16* grow = row_ok ? reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo : nullptr;
+        load_res(rres[1], m, cbase + 64);
+        th_wait(&tmem_full_bar[acc], (it >> 1) & 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t va[16], vb[16];
+        if (cbase < p.N) th_ld16_nowait(tmem_row + (uint32_t)cbase, va);
+#pragma unroll
+        for (int s = 0; s < 8; ++s) {
+          const int k = s >> 1;
+          const int c0 = cbase + 64 * k + 16 * (s & 1);
+          const int cn = cbase + 64 * ((s + 1) >> 1) + 16 * ((s + 1) & 1);
+          if (c0 < p.N) {
+            th_ld_wait();
+            if (s & 1) {
+              if (s < 7 && cn < p.N) th_ld16_nowait(tmem_row + (uint32_t)cn, va);
+              epi_fast_chunk<false>(vb, rres[k & 1][2], rres[k & 1][3], s_bias, c0, p.N, lo, 0u, grow);
+              if (k >= 1 && k < 2) load_res(rres[k & 1], m, c0 - 16 + 128);       // chunk 3 (rres[1]); chunk 2 is loaded below
+            } else {
+              if (cn < p.N) th_ld16_nowait(tmem_row + (uint32_t)cn, vb);
+              epi_fast_chunk<false>(va, rres[k & 1][0], rres[k & 1][1], s_bias, c0, p.N, lo, 0u, grow);
+            }
+          }
+          if (s == 1 && cbase + 128 < p.N) load_res(rres[0], m, cbase + 128);    // chunk 2 of this tile
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        th_arrive(&tmem_empty_bar[acc]);
+        // first chunk of the next tile (after the last use of rres[0] in this one)
+        const long long tnext = tile + (long long)it_step * gridDim.x;
+        if (tnext < p.m_tiles) load_res(rres[0], tnext * TH_BM + r, cbase);
+      }
+    } else {
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
       const uint32_t acc = it & 1u;
@@ -274,6 +373,7 @@ gemm_thin_kernel(const ThinParams p) {
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       th_arrive(&tmem_empty_bar[acc]);
     }
+    }
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -331,6 +431,10 @@ int gemm_thin_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* 
     TDEED_REQUIRE(e == cudaSuccess, TDEED_ERR_CUDA, "gemm_thin: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
+  static int fast_env = -1;
+  if (fast_env < 0) { const char* e = getenv("TDEED_GEMM_FAST_EPI"); fast_env = e ? atoi(e) : 1; }
+  p.fast = (fast_env && out_dtype == TDEED_BF16 && (act == TDEED_ACT_NONE || act == TDEED_ACT_RELU)) ? 1 : 0;
+  p.split = (p.fast && N <= 32) ? 1 : 0;
   const int grid = p.m_tiles < kNumSMs ? p.m_tiles : kNumSMs;
   gemm_thin_kernel<<<grid, TH_THREADS, smem, st>>>(p);
   return check_launch("tdeed_gemm_fwd(tcgen05 thin-K)");
