@@ -31,7 +31,7 @@ constexpr int GS_Q_SMEM_BUDGET = 96 * 1024;
 // ---- kernel 1: Q maps.  grid (row_blocks, frames) ----
 template <typename T>
 __global__ void __launch_bounds__(GS_THREADS)
-gsf_q_kernel(const T* __restrict__ x, int h, int w, int c, int fold, int rows_per_cta,
+gsf_q_kernel(const T* __restrict__ x, int h, int w, int c, int fold, int rows_per_cta, int nsl,
              const float* __restrict__ bn_scale, const float* __restrict__ bn_shift,
              const float* __restrict__ w3d, float* __restrict__ Q) {
   extern __shared__ __align__(16) float smem[];
@@ -75,11 +75,21 @@ gsf_q_kernel(const T* __restrict__ x, int h, int w, int c, int fold, int rows_pe
   __syncthreads();
 
   // compute: a thread owns a strip of 4 horizontally adjacent pixels, so every z value feeds up to 3 taps x 3 temporal
-  // slices and every weight fetch feeds 4 pixels (the one-pixel-per-thread version ran at 85 % L1TEX: shared-memory bound)
+  // slices and every weight fetch feeds 4 pixels (the one-pixel-per-thread version ran at 85 % L1TEX: shared-memory bound).
+  // Small frames have few strips (14 at 7x7, 56 at 14x14): the channels of each group are then dealt out to `nsl` thread
+  // slices per strip and the slices are added through shared memory in slice order (with one slice only 14 of the 256
+  // threads worked at 7x7: 232 us per launch for an 81 MB problem).
   const int hw = h * w;
   const int strips = (w + 3) / 4;
-  for (int it = threadIdx.x; it < rows * strips; it += GS_THREADS) {
-    const int py = it / strips, x0 = (it - py * strips) * 4;
+  const int nstr = rows * strips;
+  const int cps = (half + nsl - 1) / nsl;           // channels of a group per slice
+  float* s_red = s_z;                               // reused after the barrier below (host checks that it fits)
+  for (int it0 = 0; it0 < nstr * nsl; it0 += GS_THREADS) {
+    const int it = it0 + threadIdx.x;
+    const bool active = it < nstr * nsl;
+    const int sl = active ? it / nstr : 0;
+    const int st = active ? it - sl * nstr : 0;
+    const int py = st / strips, x0 = (st - py * strips) * 4;
     float acc[2][3][4];
 #pragma unroll
     for (int g = 0; g < 2; ++g)
@@ -87,38 +97,71 @@ gsf_q_kernel(const T* __restrict__ x, int h, int w, int c, int fold, int rows_pe
       for (int k = 0; k < 3; ++k)
 #pragma unroll
         for (int q = 0; q < 4; ++q) acc[g][k][q] = 0.f;
+    if (active) {
+      const int ci0 = sl * cps, ci1 = min(half, ci0 + cps);
 #pragma unroll
-    for (int g = 0; g < 2; ++g) {
-      for (int ci = 0; ci < half; ++ci) {
-        const int ch = g * half + ci;
-        const float* zp = s_z + ch * plane + py * wp + x0;   // top-left of the strip's 3 x 6 window
-        float zr[3][6];
+      for (int g = 0; g < 2; ++g) {
+        for (int ci = ci0; ci < ci1; ++ci) {
+          const int ch = g * half + ci;
+          const float* zp = s_z + ch * plane + py * wp + x0;   // top-left of the strip's 3 x 6 window
+          float zr[3][6];
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
+          for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-          for (int j = 0; j < 6; ++j) zr[dy][j] = zp[dy * wp + j];   // columns past the row end are only used by masked pixels
+            for (int j = 0; j < 6; ++j) zr[dy][j] = zp[dy * wp + j];   // columns past the row end are only used by masked pixels
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
+          for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            const float4 w4 = s_w[(dy * 3 + dx) * fold + ch];
+            for (int dx = 0; dx < 3; ++dx) {
+              const float4 w4 = s_w[(dy * 3 + dx) * fold + ch];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float zv = zr[dy][q + dx];
-              acc[g][0][q] = fmaf(zv, w4.x, acc[g][0][q]);
-              acc[g][1][q] = fmaf(zv, w4.y, acc[g][1][q]);
-              acc[g][2][q] = fmaf(zv, w4.z, acc[g][2][q]);
+              for (int q = 0; q < 4; ++q) {
+                const float zv = zr[dy][q + dx];
+                acc[g][0][q] = fmaf(zv, w4.x, acc[g][0][q]);
+                acc[g][1][q] = fmaf(zv, w4.y, acc[g][1][q]);
+                acc[g][2][q] = fmaf(zv, w4.z, acc[g][2][q]);
+              }
             }
-          }
+        }
       }
     }
+    if (nsl == 1) {
+      if (!active) continue;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (x0 + q >= w) break;
-      float2* qo = reinterpret_cast<float2*>(Q + ((size_t)f * hw + (size_t)(y0 + py) * w + x0 + q) * 6);
-      qo[0] = make_float2(acc[0][0][q], acc[0][1][q]);
-      qo[1] = make_float2(acc[0][2][q], acc[1][0][q]);
-      qo[2] = make_float2(acc[1][1][q], acc[1][2][q]);
+      for (int q = 0; q < 4; ++q) {
+        if (x0 + q >= w) break;
+        float2* qo = reinterpret_cast<float2*>(Q + ((size_t)f * hw + (size_t)(y0 + py) * w + x0 + q) * 6);
+        qo[0] = make_float2(acc[0][0][q], acc[0][1][q]);
+        qo[1] = make_float2(acc[0][2][q], acc[1][0][q]);
+        qo[2] = make_float2(acc[1][1][q], acc[1][2][q]);
+      }
+    } else {
+      // nsl > 1 only when nstr * nsl <= GS_THREADS: a single pass, so the barriers below are reached by every thread
+      __syncthreads();                              // all z reads are done: the tile becomes the slice-partials buffer
+      if (active) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g)
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s_red[(sl * nstr + st) * 24 + (g * 3 + k) * 4 + q] = acc[g][k][q];
+      }
+      __syncthreads();
+      for (int o = threadIdx.x; o < nstr * 4; o += GS_THREADS) {
+        const int st2 = o >> 2, q = o & 3;
+        const int py2 = st2 / strips, x2 = (st2 - py2 * strips) * 4 + q;
+        if (x2 >= w) continue;
+        float v[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) v[j] = 0.f;
+        for (int s2 = 0; s2 < nsl; ++s2)
+#pragma unroll
+          for (int j = 0; j < 6; ++j) v[j] += s_red[(s2 * nstr + st2) * 24 + j * 4 + q];
+        float2* qo = reinterpret_cast<float2*>(Q + ((size_t)f * hw + (size_t)(y0 + py2) * w + x2) * 6);
+        qo[0] = make_float2(v[0], v[1]);
+        qo[1] = make_float2(v[2], v[3]);
+        qo[2] = make_float2(v[4], v[5]);
+      }
     }
   }
 }
@@ -278,7 +321,15 @@ static int launch_gsf(int mode, const void* x, int clips, int clip_len, int h, i
     TDEED_REQUIRE(e == cudaSuccess, TDEED_ERR_CUDA, "tdeed_gsf_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     q_set = 200 * 1024;
   }
-  kq<<<dim3(ceil_div(h, rows), n), GS_THREADS, smem_q, st>>>((const T*)x, h, w, c, fold, rows, bn_scale, bn_shift, w3d, Q);
+  // channel slices per strip for small frames (single compute pass, partials must fit the z tile they replace)
+  int nsl = 1;
+  {
+    const int nstr = (rows < h ? rows : h) * ((w + 3) / 4);
+    while (nsl < 16 && nstr * (nsl * 2) <= GS_THREADS && nsl * 2 <= fold / 2 &&
+           (size_t)nstr * (nsl * 2) * 24 <= (size_t)fold * ((size_t)(rows + 2) * (w + 2) + 5))
+      nsl *= 2;
+  }
+  kq<<<dim3(ceil_div(h, rows), n), GS_THREADS, smem_q, st>>>((const T*)x, h, w, c, fold, rows, nsl, bn_scale, bn_shift, w3d, Q);
   int rc = check_launch("tdeed_gsf_fwd(q)");
   if (rc) return rc;
 

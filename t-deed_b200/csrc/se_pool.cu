@@ -70,7 +70,8 @@ se_fc_kernel(const float* __restrict__ mean, int n, int c, int rd, const float* 
     float acc[SE_FR];
 #pragma unroll
     for (int f = 0; f < SE_FR; ++f) acc[f] = 0.f;
-    for (int ch = lane; ch < c; ch += 32) {
+#pragma unroll 4
+    for (int ch = lane; ch < c; ch += 32) {        // unrolled: 4 weight loads in flight (the loop was one L2 latency per step)
       const float wv = w1[(size_t)r * c + ch];
 #pragma unroll
       for (int f = 0; f < SE_FR; ++f) acc[f] = fmaf(wv, s_mean[f * c + ch], acc[f]);
@@ -88,6 +89,7 @@ se_fc_kernel(const float* __restrict__ mean, int n, int c, int rd, const float* 
     const float bb = b2[ch];
 #pragma unroll
     for (int f = 0; f < SE_FR; ++f) acc[f] = bb;
+#pragma unroll 8
     for (int r = 0; r < rd; ++r) {
       const float wv = w2t[(size_t)r * c + ch];      // coalesced over ch
 #pragma unroll
