@@ -13,6 +13,7 @@
 // Weights of the CTA's channel block stay resident in shared memory; CTAs are persistent over position tiles,
 // several per SM so that staging, MMA and epilogue of different tiles overlap.
 #include "common.cuh"
+#include "gemm_epilogue.cuh"
 
 namespace tdeed {
 
@@ -61,6 +62,14 @@ __device__ __forceinline__ void c3_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr) : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void c3_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void c3_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ bool c3_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -222,6 +231,7 @@ conv3x3g_tc_kernel(const C3TParams p) {
     // ===== epilogue (4 warps): row = position; bias + ReLU -> bf16 NHWC =====
     const int lg = warp & 3;
     const int r = lg * 32 + lane;
+    const float lo = p.relu ? 0.f : -INFINITY;
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
       const uint32_t buf = it & 1u;
@@ -240,20 +250,21 @@ conv3x3g_tc_kernel(const C3TParams p) {
       c3_wait(&tfull_bar[buf], (it >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_lane = tmem_base + ((uint32_t)(lg * 32) << 16) + buf * acc_cols;
-      for (int pp = 0; pp < np; ++pp) {
-        uint32_t v32[16];
-        c3_ld16(tmem_lane + (uint32_t)pp * 16u, v32);
-        if (!ok) continue;
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          if (pair0 * 16 + pp * 16 + 8 * hh >= p.C) continue;
-          float v[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float t = __uint_as_float(v32[8 * hh + q]) + s_bias[pp * 16 + 8 * hh + q];
-            v[q] = p.relu ? fmaxf(t, 0.f) : t;
-          }
-          store8(p.out + obase + pp * 16 + 8 * hh, v);
+      // TMEM loads run one channel pair ahead of the arithmetic; bias as 16-byte shared-memory reads, straight-line
+      // bias / ReLU / pack per 8 channels (after the producer rewrite these four warps were the busiest: ncu r1h)
+      __nv_bfloat16* grow = ok ? p.out + obase : nullptr;
+      const int ncols = min(np * 16, p.C - pair0 * 16);
+      const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+      uint32_t va[16], vb[16];
+      c3_ld16_nowait(tmem_lane, va);
+      for (int pp = 0; pp < np; pp += 2) {
+        c3_ld_wait();
+        if (pp + 1 < np) c3_ld16_nowait(tmem_lane + (uint32_t)(pp + 1) * 16u, vb);
+        epi_fast_chunk<false, false>(va, zero4, zero4, s_bias, pp * 16, ncols, lo, 0u, grow);
+        if (pp + 1 < np) {
+          c3_ld_wait();
+          if (pp + 2 < np) c3_ld16_nowait(tmem_lane + (uint32_t)(pp + 2) * 16u, va);
+          epi_fast_chunk<false, false>(vb, zero4, zero4, s_bias, (pp + 1) * 16, ncols, lo, 0u, grow);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

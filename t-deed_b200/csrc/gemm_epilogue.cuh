@@ -15,7 +15,7 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
 
 // One 16-column accumulator piece of one row -> + bias (+ bf16 residual), clamp at `lo` (0 = ReLU, -inf = none), bf16, store.
 // Straight-line code (no runtime dtype / activation switches), so the 8-column groups interleave in the schedule.
-template <bool STAGED>
+template <bool STAGED, bool HAS_RES = true>
 __device__ __forceinline__ void epi_fast_chunk(const uint32_t (&acc)[16], const uint4& r0, const uint4& r1, const float* __restrict__ bias,
                                                int c0, int ncols, float lo, uint32_t srow_addr, __nv_bfloat16* grow) {
 #pragma unroll
@@ -31,10 +31,12 @@ __device__ __forceinline__ void epi_fast_chunk(const uint32_t (&acc)[16], const 
       v[2] = __uint_as_float(acc[8 * h + 2]) + b0.z; v[3] = __uint_as_float(acc[8 * h + 3]) + b0.w;
       v[4] = __uint_as_float(acc[8 * h + 4]) + b1.x; v[5] = __uint_as_float(acc[8 * h + 5]) + b1.y;
       v[6] = __uint_as_float(acc[8 * h + 6]) + b1.z; v[7] = __uint_as_float(acc[8 * h + 7]) + b1.w;
+      if (HAS_RES) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {           // residual words are zero when there is no residual
-        v[2 * q] += __uint_as_float(w4[q] << 16);
-        v[2 * q + 1] += __uint_as_float(w4[q] & 0xffff0000u);
+        for (int q = 0; q < 4; ++q) {         // residual words are zero when there is no residual
+          v[2 * q] += __uint_as_float(w4[q] << 16);
+          v[2 * q + 1] += __uint_as_float(w4[q] & 0xffff0000u);
+        }
       }
       uint4 o;
       o.x = pack_bf16x2(fmaxf(v[0], lo), fmaxf(v[1], lo));

@@ -42,6 +42,7 @@ struct ThinParams {
   long long ldo;
   int out_dtype;
   uint32_t tmem_cols;
+  int nacc_log2;   // log2 of the number of TMEM accumulators (2..8): thin tiles are cheap, the MMA warp may run that far ahead
   int fast;    // specialised bf16 epilogue (act none|relu): pipelined TMEM loads, cross-tile residual prefetch
   int split;   // fast && N <= 32: the two epilogue warp halves take alternate tiles (otherwise half of them would idle)
 };
@@ -119,9 +120,9 @@ gemm_thin_kernel(const ThinParams p) {
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + TH_MAX_STAGES;
   uint64_t* tmem_full_bar = bars + 2 * TH_MAX_STAGES;
-  uint64_t* tmem_empty_bar = bars + 2 * TH_MAX_STAGES + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TH_MAX_STAGES + 4);
-  float* s_bias = reinterpret_cast<float*>(bars + 2 * TH_MAX_STAGES + 6);  // [block_n]
+  uint64_t* tmem_empty_bar = bars + 2 * TH_MAX_STAGES + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TH_MAX_STAGES + 16);
+  float* s_bias = reinterpret_cast<float*>(bars + 2 * TH_MAX_STAGES + 18);  // [block_n]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -145,7 +146,7 @@ gemm_thin_kernel(const ThinParams p) {
       th_mbar_init(&full_bar[s], 32 * TH_PROD_WARPS);       // one async arrival per producer thread
       th_mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < (1 << p.nacc_log2); ++a) {
       th_mbar_init(&tmem_full_bar[a], 1);
       th_mbar_init(&tmem_empty_bar[a], p.split ? 128 : 256);   // arrivals per accumulator drain
     }
@@ -224,11 +225,12 @@ gemm_thin_kernel(const ThinParams p) {
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(TH_BM >> 4) << 24);
     const uint32_t sA_u32 = th_smem_u32(sA), sW_u32 = th_smem_u32(sW);
     uint32_t it = 0;
-    for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
-      const uint32_t acc = it & 1u;
-      const int stage = it % p.num_stages;
-      const uint32_t round = it / p.num_stages;
-      th_wait(&tmem_empty_bar[acc], ((it >> 1) & 1u) ^ 1u);
+    int stage = 0;
+    uint32_t round = 0;
+    const int num_stages = p.num_stages, m_tiles = p.m_tiles, nacc_log2 = p.nacc_log2;
+    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
+      const uint32_t acc = it & ((1u << nacc_log2) - 1u);
+      th_wait(&tmem_empty_bar[acc], ((it >> nacc_log2) & 1u) ^ 1u);
       th_wait(&full_bar[stage], round & 1u);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) data -> visible to the MMA (async proxy)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -243,6 +245,7 @@ gemm_thin_kernel(const ThinParams p) {
         th_commit(&tmem_full_bar[acc]);
       }
       __syncwarp();
+      if (++stage == num_stages) { stage = 0; ++round; }
     }
   } else {
     // ===== epilogue (8 warps): TMEM -> bias / residual / activation -> global =====
@@ -271,13 +274,13 @@ gemm_thin_kernel(const ThinParams p) {
       long long tile = (long long)blockIdx.x + (long long)it * gridDim.x;
       if (tile < p.m_tiles) load_res(rres[0], tile * TH_BM + r, cbase);
       for (; tile < p.m_tiles; tile += (long long)it_step * gridDim.x, it += it_step) {
-        const uint32_t acc = it & 1u;
+        const uint32_t acc = it & ((1u << p.nacc_log2) - 1u);
         const long long m = tile * TH_BM + r;
         const bool row_ok = m < p.M;
         const uint32_t tmem_row = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * (uint32_t)p.block_n;
         __nv_bfloat16* grow = row_ok ? reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo : nullptr;
         load_res(rres[1], m, cbase + 64);
-        th_wait(&tmem_full_bar[acc], (it >> 1) & 1u);
+        th_wait(&tmem_full_bar[acc], (it >> p.nacc_log2) & 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         uint32_t va[16], vb[16];
         if (cbase < p.N) th_ld16_nowait(tmem_row + (uint32_t)cbase, va);
@@ -308,7 +311,7 @@ gemm_thin_kernel(const ThinParams p) {
     } else {
     uint32_t it = 0;
     for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, ++it) {
-      const uint32_t acc = it & 1u;
+      const uint32_t acc = it & ((1u << p.nacc_log2) - 1u);
       const long long m = (long long)tile * TH_BM + r;
       const bool row_ok = m < p.M;
       const uint32_t tmem_row = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * (uint32_t)p.block_n;
@@ -330,7 +333,7 @@ gemm_thin_kernel(const ThinParams p) {
           }
         }
         if (!waited) {
-          th_wait(&tmem_full_bar[acc], (it >> 1) & 1u);
+          th_wait(&tmem_full_bar[acc], (it >> p.nacc_log2) & 1u);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           waited = true;
         }
@@ -369,7 +372,7 @@ gemm_thin_kernel(const ThinParams p) {
           else store8(reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo + n, v);
         }
       }
-      if (!waited) th_wait(&tmem_full_bar[acc], (it >> 1) & 1u);
+      if (!waited) th_wait(&tmem_full_bar[acc], (it >> p.nacc_log2) & 1u);
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       th_arrive(&tmem_empty_bar[acc]);
     }
@@ -415,11 +418,14 @@ int gemm_thin_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* 
   p.m_tiles = (int)ceil_div_ll(M, TH_BM);
   p.W = (const __nv_bfloat16*)W; p.bias = bias; p.residual = residual; p.ldr = ldr; p.act = act;
   p.out = out; p.ldo = ldo; p.out_dtype = out_dtype;
+  int nacc_log2 = 1;
+  while (nacc_log2 < 3 && (2 << nacc_log2) * p.block_n + 16 <= 512) ++nacc_log2;
+  p.nacc_log2 = nacc_log2;
   uint32_t cols = 32;
-  while ((int)cols < 2 * p.block_n + 16) cols <<= 1;
+  while ((int)cols < (1 << nacc_log2) * p.block_n + 16) cols <<= 1;
   if (cols > 512) cols = 512;
   p.tmem_cols = cols;
-  const size_t fixed = (size_t)p.planes * p.w_plane_bytes + (2 * TH_MAX_STAGES + 6) * sizeof(uint64_t) + (size_t)p.block_n * sizeof(float) + 128;
+  const size_t fixed = (size_t)p.planes * p.w_plane_bytes + (2 * TH_MAX_STAGES + 18) * sizeof(uint64_t) + (size_t)p.block_n * sizeof(float) + 128;
   int stages = (int)((200 * 1024 - fixed) / p.stage_bytes);
   if (stages > TH_MAX_STAGES) stages = TH_MAX_STAGES;
   TDEED_REQUIRE(stages >= 2, TDEED_ERR_UNSUPPORTED, "gemm_thin: N=%d K=%d does not fit", N, K);
