@@ -204,13 +204,21 @@ stem_tc2_kernel(const Stem2Params p) {
           }
         }
         if (!fast) {
-          for (int jj = 0; jj < 4; ++jj) {
-            const int s = s0 + jj;
-            if (s >= p.npos) break;
-            const long long L = q_lo + s;
-            for (int px = 0; px < 2; ++px) {
-              uint32_t rg = p.pad_rg, bb = p.pad_b;
-              if (L >= 0 && L < p.total_pos) {
+          // byte-wise path (quads that straddle a grid row, touch the padding or the tensor's ends: ~8 % of the items, but
+          // almost every warp holds one).  Addresses first, then ALL loads of two positions (12 bytes) in flight at once from
+          // always-valid addresses, then pack + store: the former one-pixel-at-a-time loop exposed eight dependent global
+          // latencies per item and dominated the producers' time (ncu r1h: 3x the samples of the word path).
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const uint8_t* src[4];
+            bool okp[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int s = s0 + h2 * 2 + (u >> 1), px = u & 1;
+              const long long L = q_lo + s;
+              bool ok = false;
+              const uint8_t* sp = p.frames;
+              if (s < p.npos && L >= 0 && L < p.total_pos) {
                 const uint32_t Lu = (uint32_t)L;
                 const int ff = (int)(Lu / (uint32_t)p.G);
                 const uint32_t rem = Lu - (uint32_t)ff * (uint32_t)p.G;
@@ -218,11 +226,26 @@ stem_tc2_kernel(const Stem2Params p) {
                 const int iy = 2 * (UU - 1) + py, ix = 2 * (VV - 1) + px;
                 if (UU >= 1 && VV >= 1 && iy < p.H && ix < p.W) {
                   const int sx = p.flip ? (p.W - 1 - ix) : ix;
-                  const uint8_t* src = p.frames + (size_t)ff * 3 * plane_in + (size_t)(p.crop_y + iy) * p.in_w + p.crop_x + sx;
-                  rg = s2_u8_bf16(__ldg(src)) | (s2_u8_bf16(__ldg(src + plane_in)) << 16);
-                  bb = s2_u8_bf16(__ldg(src + 2 * plane_in));
+                  sp = p.frames + (size_t)ff * 3 * plane_in + (size_t)(p.crop_y + iy) * p.in_w + p.crop_x + sx;
+                  ok = true;
                 }
               }
+              src[u] = sp;
+              okp[u] = ok;
+            }
+            uint32_t cr[4], cg[4], cb[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {            // p.frames + {0, plane, 2 plane} is always inside the tensor
+              cr[u] = __ldg(src[u]);
+              cg[u] = __ldg(src[u] + plane_in);
+              cb[u] = __ldg(src[u] + 2 * plane_in);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int s = s0 + h2 * 2 + (u >> 1), px = u & 1;
+              if (s >= p.npos) continue;
+              const uint32_t rg = okp[u] ? (s2_u8_bf16(cr[u]) | (s2_u8_bf16(cg[u]) << 16)) : p.pad_rg;
+              const uint32_t bb = okp[u] ? s2_u8_bf16(cb[u]) : p.pad_b;
               *reinterpret_cast<uint4*>(dstb + ((size_t)(py * 2 + px) * p.npos_pad + s) * 16) = make_uint4(rg, bb, 0u, 0u);
             }
           }
