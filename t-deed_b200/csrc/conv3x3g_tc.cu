@@ -14,6 +14,7 @@
 // several per SM so that staging, MMA and epilogue of different tiles overlap.
 #include "common.cuh"
 #include "gemm_epilogue.cuh"
+#include <cstdlib>
 
 namespace tdeed {
 
@@ -323,6 +324,9 @@ static int conv3x3g_tc_run(const void* in, int n, int h, int w, int c, int strid
   const size_t per_pair = (size_t)9 * 512 + 2 * (size_t)p.nplanes * 2 * p.npos_pad * 16 + 64;     // two input buffers
   int max_pairs = (int)((200 * 1024 - 2 * (size_t)p.npos * p.nplanes * sizeof(int)) / per_pair);
   if (max_pairs > C3T_MAX_PAIRS) max_pairs = C3T_MAX_PAIRS;
+  static int pairs_env = -1;
+  if (pairs_env < 0) { const char* e = getenv("TDEED_C3_MAX_PAIRS"); pairs_env = e ? atoi(e) : 0; }
+  if (pairs_env > 0 && max_pairs > pairs_env) max_pairs = pairs_env;
   TDEED_REQUIRE(max_pairs >= 1, TDEED_ERR_UNSUPPORTED, "tdeed_conv3x3g_tc_fwd: frame width %d too large for the staged window", w);
   const int nblk = ceil_div(p.pairs_total, max_pairs);
   p.pairs_blk = ceil_div(p.pairs_total, nblk);

@@ -185,6 +185,9 @@ __device__ __forceinline__ void epi_fast_tile(const TcParams& p, uint64_t* full_
 // ---------------------------------------------------------------- kernel
 struct TileCoord { int mt, nt; };
 
+// FAST: the specialised bf16 epilogue is a separate instantiation, so the generic epilogue (fp32 outputs, GELU) keeps its own
+// register allocation.
+template <bool FAST>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const TcParams p) {
@@ -345,7 +348,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       const int ncols = min(p.block_n, p.N - n0);           // multiple of 8
       const uint32_t tmem_row = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * (uint32_t)p.block_n;
       uint8_t* srow = s_out + r * pitch;
-      if (p.fast) {
+      if constexpr (FAST) {
         if (p.staged && p.out_bufs == 1 && j > 0) epi_bar_sync();   // single staging tile: previous phase 2 must have drained
         if (p.staged) epi_fast_tile<true>(p, &tmem_full_bar[acc], (j >> 1) & 1u, tmem_row, half, ncols, n0, m, row_ok, s_bias, smem_u32(srow));
         else epi_fast_tile<false>(p, &tmem_full_bar[acc], (j >> 1) & 1u, tmem_row, half, ncols, n0, m, row_ok, s_bias, 0u);
@@ -369,7 +372,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           }
         }
         continue;
-      }
+      } else {
       bool waited = false;
       if (p.staged && p.out_bufs == 1 && j > 0) epi_bar_sync();   // single staging tile: previous phase 2 must have drained
       for (int c0 = half * 32; c0 < ncols; c0 += 64) {
@@ -456,6 +459,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
                 *reinterpret_cast<const uint4*>(s_out + row * pitch + ch * 16);
         }
       }
+      }   // generic epilogue
     }
   }
 
@@ -636,7 +640,8 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
   const size_t smem = fixed2 + stages * stage_bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     TDEED_REQUIRE(e == cudaSuccess, TDEED_ERR_CUDA, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -648,7 +653,8 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
   if (trace)
     fprintf(stderr, "gemm_tc M=%lld N=%d K=%d nseg=%d gather=%d res=%d act=%d | block_n=%d n_tiles=%d w_res=%d stages=%d staged=%d out_bufs=%d fast=%d grid=%d smem=%zu\n",
             M, N, K, nseg, p.gather, residual != nullptr, act, block_n, p.n_tiles, p.w_res, stages, p.staged, p.out_bufs, p.fast, grid, smem);
-  gemm_tc_kernel<<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], p);
+  if (p.fast) gemm_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], p);
+  else gemm_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], p);
   return check_launch("tdeed_gemm_fwd(tcgen05)");
 }
 
