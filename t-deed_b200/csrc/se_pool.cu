@@ -58,12 +58,16 @@ __global__ void __launch_bounds__(SE_THREADS)
 se_fc_kernel(const float* __restrict__ mean, int n, int c, int rd, const float* __restrict__ w1,
              const float* __restrict__ b1, const float* __restrict__ w2t, const float* __restrict__ b2,
              float* __restrict__ scale) {
-  extern __shared__ float smem[];
-  float* s_mean = smem;                         // [SE_FR][c]
-  float* s_hid = s_mean + (size_t)SE_FR * c;    // [SE_FR][rd]
+  extern __shared__ __align__(16) float smem[];
+  // frame-minor layouts: the 8 frame values of a channel / hidden unit are two 16-byte shared-memory reads per weight
+  float* s_mean = smem;                         // [c][SE_FR]
+  float* s_hid = s_mean + (size_t)SE_FR * c;    // [rd][SE_FR]
   const int f0 = blockIdx.x * SE_FR;
   const int nf = min(SE_FR, n - f0);
-  for (int i = threadIdx.x; i < SE_FR * c; i += SE_THREADS) s_mean[i] = (i < nf * c) ? mean[(size_t)f0 * c + i] : 0.f;
+  for (int i = threadIdx.x; i < SE_FR * c; i += SE_THREADS) {
+    const int f = i / c, ch = i - f * c;          // coalesced global read, transposed store
+    s_mean[ch * SE_FR + f] = (f < nf) ? mean[(size_t)(f0 + f) * c + ch] : 0.f;
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int r = warp; r < rd; r += SE_THREADS / 32) {
@@ -73,14 +77,16 @@ se_fc_kernel(const float* __restrict__ mean, int n, int c, int rd, const float* 
 #pragma unroll 4
     for (int ch = lane; ch < c; ch += 32) {        // unrolled: 4 weight loads in flight (the loop was one L2 latency per step)
       const float wv = w1[(size_t)r * c + ch];
-#pragma unroll
-      for (int f = 0; f < SE_FR; ++f) acc[f] = fmaf(wv, s_mean[f * c + ch], acc[f]);
+      const float4 m0 = *reinterpret_cast<const float4*>(s_mean + ch * SE_FR);
+      const float4 m1 = *reinterpret_cast<const float4*>(s_mean + ch * SE_FR + 4);
+      acc[0] = fmaf(wv, m0.x, acc[0]); acc[1] = fmaf(wv, m0.y, acc[1]); acc[2] = fmaf(wv, m0.z, acc[2]); acc[3] = fmaf(wv, m0.w, acc[3]);
+      acc[4] = fmaf(wv, m1.x, acc[4]); acc[5] = fmaf(wv, m1.y, acc[5]); acc[6] = fmaf(wv, m1.z, acc[6]); acc[7] = fmaf(wv, m1.w, acc[7]);
     }
     const float bb = b1[r];
 #pragma unroll
     for (int f = 0; f < SE_FR; ++f) {
       const float sres = warp_sum(acc[f]);
-      if (lane == 0) s_hid[f * rd + r] = fmaxf(sres + bb, 0.f);
+      if (lane == 0) s_hid[r * SE_FR + f] = fmaxf(sres + bb, 0.f);
     }
   }
   __syncthreads();
@@ -92,14 +98,17 @@ se_fc_kernel(const float* __restrict__ mean, int n, int c, int rd, const float* 
 #pragma unroll 8
     for (int r = 0; r < rd; ++r) {
       const float wv = w2t[(size_t)r * c + ch];      // coalesced over ch
-#pragma unroll
-      for (int f = 0; f < SE_FR; ++f) acc[f] = fmaf(wv, s_hid[f * rd + r], acc[f]);
+      const float4 h0 = *reinterpret_cast<const float4*>(s_hid + r * SE_FR);
+      const float4 h1 = *reinterpret_cast<const float4*>(s_hid + r * SE_FR + 4);
+      acc[0] = fmaf(wv, h0.x, acc[0]); acc[1] = fmaf(wv, h0.y, acc[1]); acc[2] = fmaf(wv, h0.z, acc[2]); acc[3] = fmaf(wv, h0.w, acc[3]);
+      acc[4] = fmaf(wv, h1.x, acc[4]); acc[5] = fmaf(wv, h1.y, acc[5]); acc[6] = fmaf(wv, h1.z, acc[6]); acc[7] = fmaf(wv, h1.w, acc[7]);
     }
 #pragma unroll
     for (int f = 0; f < SE_FR; ++f)
       if (f < nf) scale[(size_t)(f0 + f) * c + ch] = sigmoidf_(acc[f]);
   }
 }
+static_assert(SE_FR == 8, "se_fc_kernel reads the frame values as two float4");
 
 template <typename T>
 __global__ void __launch_bounds__(SE_THREADS)
