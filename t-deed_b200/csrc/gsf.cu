@@ -53,43 +53,24 @@ gsf_q_kernel(const T* __restrict__ x, int h, int w, int c, int fold, int rows_pe
   // stage z = relu(bn(x)) for rows [y0-1, y0+rows] x cols [-1, w], zero outside the image
   const T* xf = x + (size_t)f * h * w * c;
   const int c8n = fold / 8, ctail = fold - c8n * 8;
-  // four items per trip, all global loads issued before the first shared-memory store (one item per trip exposed one global
-  // latency per item: the staging, not the arithmetic, dominated the small-frame launches)
-  const int ngrp = c8n + (ctail ? 1 : 0);
-  const int n_items = (rows + 2) * wp * ngrp;
-  for (int i0 = threadIdx.x; i0 < n_items; i0 += 4 * GS_THREADS) {
-    float v[4][8];
-    int pixs[4], ch0s[4], nchs[4];
-    bool ins[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * GS_THREADS;
-      const int cg = i % ngrp;
-      const int pix = i / ngrp;
-      const int px = pix % wp - 1, py = pix / wp - 1 + y0;
-      pixs[u] = pix;
-      ch0s[u] = cg * 8;
-      nchs[u] = (cg < c8n) ? 8 : ctail;
-      ins[u] = i < n_items && py >= 0 && py < h && px >= 0 && px < w;
-      if (i >= n_items) nchs[u] = 0;
-      if (ins[u]) {
-        const T* src = xf + ((size_t)py * w + px) * c + ch0s[u];
-        if (nchs[u] == 8) {
-          load8(src, v[u]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (j < nchs[u]) v[u][j] = Elem<T>::ld(src + j);
-        }
+  for (int i = threadIdx.x; i < (rows + 2) * wp * (c8n + (ctail ? 1 : 0)); i += GS_THREADS) {
+    const int cg = i % (c8n + (ctail ? 1 : 0));
+    const int pix = i / (c8n + (ctail ? 1 : 0));
+    const int px = pix % wp - 1, py = pix / wp - 1 + y0;
+    const int ch0 = cg * 8;
+    const int nch = (cg < c8n) ? 8 : ctail;
+    float v[8];
+    const bool inside = py >= 0 && py < h && px >= 0 && px < w;
+    if (inside) {
+      const T* src = xf + ((size_t)py * w + px) * c + ch0;
+      if (nch == 8) {
+        load8(src, v);
+      } else {
+        for (int j = 0; j < nch; ++j) v[j] = Elem<T>::ld(src + j);
       }
     }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (j < nchs[u])
-          s_z[(ch0s[u] + j) * plane + pixs[u]] = ins[u] ? fmaxf(fmaf(v[u][j], bn_scale[ch0s[u] + j], bn_shift[ch0s[u] + j]), 0.f) : 0.f;
-    }
+    for (int j = 0; j < nch; ++j)
+      s_z[(ch0 + j) * plane + pix] = inside ? fmaxf(fmaf(v[j], bn_scale[ch0 + j], bn_shift[ch0 + j]), 0.f) : 0.f;
   }
   __syncthreads();
 
