@@ -255,15 +255,17 @@ __global__ void __launch_bounds__(GS_THREADS)
 gsf_blend_kernel(const T* __restrict__ x, int clip_len, int hw, int c, int fold, int mode,
                  const float* __restrict__ gate, const float* __restrict__ wgt, T* __restrict__ out, int ld_out,
                  long long total, int copy_tail) {
-  const long long idx = (long long)blockIdx.x * GS_THREADS + threadIdx.x;
-  if (idx >= total) return;
+  // grid (frames, pixel-octet blocks): the frame index is the block's, one 32-bit division per thread (the former flat index
+  // cost four 64-bit divisions per thread plus one division per output channel: more than half of the kernel's instructions)
   const int o8n = ld_out / 8;
+  const int local = blockIdx.y * GS_THREADS + threadIdx.x;   // pixel * o8n + octet inside the frame
+  if (local >= hw * o8n) return;
   const int half = fold / 2, quarter = fold / 4;
-  const int o8 = (int)(idx % o8n);
-  const long long fp = idx / o8n;                   // frame*hw + pixel
-  const int p = (int)(fp % hw);
-  const long long f = fp / hw;
-  const int t = (int)(f % clip_len);
+  const int p = local / o8n;
+  const int o8 = local - p * o8n;
+  const long long f = blockIdx.x;
+  const long long fp = f * hw + p;                  // frame*hw + pixel
+  const int t = (int)(blockIdx.x % (unsigned)clip_len);
   const T* xt = x + (size_t)fp * c;
   const float g0 = gate[(size_t)fp * 2], g1 = gate[(size_t)fp * 2 + 1];
   // shifted sources: group 0 <- t+1, group 1 <- t-1 (zero outside the clip)
@@ -278,7 +280,7 @@ gsf_blend_kernel(const T* __restrict__ x, int clip_len, int hw, int c, int fold,
     const int jo = o8 * 8 + j;                      // output (interleaved) channel, or a pad column
     float v = 0.f;
     if (jo < fold) {
-      const int g = jo / half, jj = jo - g * half;
+      const int g = jo >= half ? 1 : 0, jj = jo - g * half;       // jo < fold = 2 * half
       const int ch = g * half + (jj & 1) * quarter + (jj >> 1);   // out[2i+k] = in[k*quarter + i]
       const float xv = Elem<T>::ld(xt + ch);
       const float r = xv - (g == 0 ? g0 : g1) * xv;
@@ -303,6 +305,7 @@ static int launch_gsf(int mode, const void* x, int clips, int clip_len, int h, i
                       const float* bn_scale, const float* bn_shift, const float* w3d, const float* b3d,
                       const float* cc_w, const float* cc_b, float* ws, void* out, int ld_out, int copy_tail, cudaStream_t st) {
   const int n = clips * clip_len, hw = h * w;
+  TDEED_REQUIRE(n <= 65535, TDEED_ERR_UNSUPPORTED, "tdeed_gsf_fwd: %d frames per call (the Q-map kernel puts frames on grid.y: at most 65535; split the batch)", n);
   float* gate = ws;
   float* sums = gate + (size_t)n * hw * 2;
   float* wgt = sums + (size_t)n * fold * 2;
@@ -344,7 +347,7 @@ static int launch_gsf(int mode, const void* x, int clips, int clip_len, int h, i
     if (rc) return rc;
   }
   const long long total = (long long)n * hw * (ld_out / 8);
-  gsf_blend_kernel<T><<<(unsigned)ceil_div_ll(total, GS_THREADS), GS_THREADS, 0, st>>>(
+  gsf_blend_kernel<T><<<dim3((unsigned)n, (unsigned)ceil_div(hw * (ld_out / 8), GS_THREADS)), GS_THREADS, 0, st>>>(
       (const T*)x, clip_len, hw, c, fold, mode, gate, wgt, (T*)out, ld_out, total, copy_tail);
   return check_launch("tdeed_gsf_fwd(blend)");
 }
