@@ -138,9 +138,11 @@ gsf_bwd_pix_kernel(const T* __restrict__ x, const T* __restrict__ dcat, int clip
   const float gv = gate[(size_t)fp * 2 + g];
   const bool gsf = mode == TDEED_SHIFT_GSF;
   float dgate = 0.f;
+  int cq = 0, ck = 0;                              // ci = ck * quarter + cq, tracked without divisions
   for (int ci = 0; ci < half; ++ci) {
     const int ch = g * half + ci;
-    const int jo = g * half + 2 * (ci % quarter) + ci / quarter;
+    const int jo = g * half + 2 * cq + ck;
+    if (++cq == quarter) { cq = 0; ++ck; }
     const float dout = Elem<T>::ld(dt_ + jo);
     float d_r, d_ys = 0.f;
     if (gsf) {
@@ -310,8 +312,16 @@ gsf_bwd_final_kernel(const T* __restrict__ x, const T* __restrict__ dcat, const 
   const long long q = (long long)blockIdx.x * GB_THREADS + threadIdx.x;
   if (q >= total8) return;
   const int c8n = c / 8;
-  const int c0 = (int)(q % c8n) * 8;
-  const long long fp = q / c8n;
+  int c0;
+  long long fp;
+  if (total8 <= 0x7fffffffLL) {                   // 32-bit index math (a 64-bit division costs ~90 instructions)
+    const unsigned q32 = (unsigned)q, fq = q32 / (unsigned)c8n;
+    c0 = (int)(q32 - fq * (unsigned)c8n) * 8;
+    fp = fq;
+  } else {
+    c0 = (int)(q % c8n) * 8;
+    fp = q / c8n;
+  }
   float xv[8], dv[8], av[8], o[8];
   load8(x + q * 8, xv);
   load8(dcat + q * 8, dv);
