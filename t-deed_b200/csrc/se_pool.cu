@@ -113,12 +113,10 @@ static_assert(SE_FR == 8, "se_fc_kernel reads the frame values as two float4");
 template <typename T>
 __global__ void __launch_bounds__(SE_THREADS)
 se_scale_kernel(const T* x, T* out, long long total8, int per_frame8, int c8n, int c, const float* __restrict__ scale) {
-  // grid (frames, octet blocks of a frame): no 64-bit divisions per thread
-  const int local = blockIdx.y * SE_THREADS + threadIdx.x;
-  if (local >= per_frame8) return;
-  const long long f = blockIdx.x;
-  const long long q = f * per_frame8 + local;
-  const int c8 = local % c8n;
+  const long long q = (long long)blockIdx.x * SE_THREADS + threadIdx.x;
+  if (q >= total8) return;
+  const long long f = q / per_frame8;
+  const int c8 = (int)(q % c8n);
   float v[8];
   load8(x + q * 8, v);
   const float4 s0 = *reinterpret_cast<const float4*>(scale + f * c + c8 * 8);
@@ -175,7 +173,7 @@ static int se_forward(int dtype, const void* x, void* out, int n, int hw, int c,
     }
   }
   const long long total8 = (long long)n * hw * (c / 8);
-  const dim3 scale_grid((unsigned)n, (unsigned)ceil_div(hw * (c / 8), SE_THREADS));
+  const unsigned scale_grid = (unsigned)ceil_div_ll(total8, SE_THREADS);
   if (dtype == TDEED_BF16) {
     se_mean_kernel<__nv_bfloat16><<<n, SE_THREADS, smem_mean, st>>>((const __nv_bfloat16*)x, hw, c, mean);
   } else if (dtype == TDEED_F32) {
@@ -310,11 +308,10 @@ template <typename T>
 __global__ void __launch_bounds__(SE_THREADS)
 se_bwd_dx_kernel(const T* __restrict__ du, long long total8, int per_frame8, int c8n, int c, float inv_hw,
                  const float* __restrict__ scale, const float* __restrict__ dm, T* __restrict__ dx) {
-  const int local = blockIdx.y * SE_THREADS + threadIdx.x;      // grid (frames, octet blocks of a frame)
-  if (local >= per_frame8) return;
-  const long long f = blockIdx.x;
-  const long long q = f * per_frame8 + local;
-  const int c0 = (local % c8n) * 8;
+  const long long q = (long long)blockIdx.x * SE_THREADS + threadIdx.x;
+  if (q >= total8) return;
+  const long long f = q / per_frame8;
+  const int c0 = (int)(q % c8n) * 8;
   float v[8];
   load8(du + q * 8, v);
 #pragma unroll
@@ -365,7 +362,7 @@ extern "C" int tdeed_se_bwd(int dtype, const void* x, const void* du, int n, int
   const size_t smem_ds = part_floats(c) * sizeof(float);
   const size_t smem_fc = (size_t)(2 * c + 2 * rd) * sizeof(float);
   const long long total8 = (long long)n * hw * (c / 8);
-  const dim3 grid((unsigned)n, (unsigned)ceil_div(hw * (c / 8), SE_THREADS));
+  const unsigned grid = (unsigned)ceil_div_ll(total8, SE_THREADS);
   if (dtype == TDEED_BF16)
     se_bwd_ds_kernel<__nv_bfloat16><<<n, SE_THREADS, smem_ds, st>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)du, hw, c, ds);
   else if (dtype == TDEED_F32)
