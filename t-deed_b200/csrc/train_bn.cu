@@ -172,7 +172,7 @@ bn_act_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ z, const
     k1[j] = coef[ch];
     k2[j] = coef[C + ch];
   }
-  constexpr int U = 4;                        // rows per trip, loads of all issued before the first store
+  constexpr int U = 2;                        // rows per trip, loads of both issued before the first store
   const long long stride = (long long)gridDim.x * l.rpi;
   auto one = [&](long long at, float (&g)[8], const float (&yv)[8], const float* zv) {
     float o[8];
