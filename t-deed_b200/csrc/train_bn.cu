@@ -7,6 +7,7 @@
 // All per-channel reductions are two-stage with a fixed order (per-thread serial -> shared-memory tree in a fixed order ->
 // per-CTA partials summed in double by one thread per channel): bitwise deterministic, no atomics.
 #include "train_reduce.cuh"
+#include <cstdlib>
 
 namespace tdeed {
 
@@ -96,7 +97,7 @@ bn_act_fwd_kernel(const T* __restrict__ y, long long M, int C, const float* __re
 // ---- backward ----
 // MODE: 0 no activation, 1 ReLU mask recomputed from y as (y*scale + shift > 0) (the z == y sentinel: saves reading z),
 //       2 ReLU mask from the post-activation tensor z
-template <typename T, int MODE>
+template <typename T, int MODE, int KB = 4>
 struct BwdOp {
   const T* dz;
   const T* z;
@@ -114,7 +115,7 @@ struct BwdOp {
       sh[j] = j < nch ? mean[3 * C + ch0 + j] : 0.f;
     }
   }
-  static constexpr int kBatch = 4;
+  static constexpr int kBatch = KB;
   struct Regs { float g[8], yv[8], zv[MODE == 2 ? 8 : 1]; };
   __device__ void load(long long r, int ch0, Regs& q) const {
     load8(dz + r * C + ch0, q.g);
@@ -153,7 +154,7 @@ __global__ void bn_bwd_final_kernel(const float* __restrict__ part, int nparts, 
   coef[C + ch] = (float)(q / (double)M);
 }
 
-template <typename T, int MODE>
+template <typename T, int MODE, int U>
 __global__ void __launch_bounds__(BN_THREADS)
 bn_act_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ z, const T* __restrict__ y, long long M, int C,
                         const float* __restrict__ stats, const float* __restrict__ coef, T* __restrict__ dy,
@@ -172,7 +173,7 @@ bn_act_bwd_apply_kernel(const T* __restrict__ dz, const T* __restrict__ z, const
     k1[j] = coef[ch];
     k2[j] = coef[C + ch];
   }
-  constexpr int U = 2;                        // rows per trip, loads of both issued before the first store
+  // U rows per trip, the loads of all of them issued before the first store
   const long long stride = (long long)gridDim.x * l.rpi;
   auto one = [&](long long at, float (&g)[8], const float (&yv)[8], const float* zv) {
     float o[8];
@@ -232,10 +233,10 @@ static int run_stats(const void* x, long long M, int C, long long ld, const floa
   return check_launch("tdeed_bn_stats(final)");
 }
 
-template <typename T, int MODE>
-static int run_bwd_mode(const void* dz, const void* z, const void* y, long long M, int C, const float* stats, float* dgamma,
+template <typename T, int MODE, int KB, int U>
+static int run_bwd_cfg(const void* dz, const void* z, const void* y, long long M, int C, const float* stats, float* dgamma,
                         float* dbeta, void* dy, void* dres, float* ws, cudaStream_t st) {
-  BwdOp<T, MODE> op;
+  BwdOp<T, MODE, KB> op;
   op.dz = (const T*)dz;
   op.z = (const T*)z;
   op.y = (const T*)y;
@@ -245,15 +246,29 @@ static int run_bwd_mode(const void* dz, const void* z, const void* y, long long 
   const int grid = bn_grid(M, C);
   const int cpad = ((C + 7) / 8) * 8;
   float* coef = ws + (size_t)BN_MAX_GRID * 2 * cpad;
-  bn_reduce_kernel<T, BwdOp<T, MODE>><<<grid, BN_THREADS, 0, st>>>(op, M, C, ws);
+  bn_reduce_kernel<T, BwdOp<T, MODE, KB>><<<grid, BN_THREADS, 0, st>>>(op, M, C, ws);
   int rc = check_launch("tdeed_bn_act_bwd(partial)");
   if (rc) return rc;
   bn_bwd_final_kernel<<<ceil_div(C, 8), 256, 0, st>>>(ws, grid, M, C, dgamma, dbeta, coef);
   rc = check_launch("tdeed_bn_act_bwd(final)");
   if (rc) return rc;
-  bn_act_bwd_apply_kernel<T, MODE><<<bn_apply_grid(M, C), BN_THREADS, 0, st>>>((const T*)dz, (const T*)z, (const T*)y, M, C, stats,
+  bn_act_bwd_apply_kernel<T, MODE, U><<<bn_apply_grid(M, C), BN_THREADS, 0, st>>>((const T*)dz, (const T*)z, (const T*)y, M, C, stats,
                                                                                coef, (T*)dy, (T*)dres);
   return check_launch("tdeed_bn_act_bwd(apply)");
+}
+
+template <typename T, int MODE>
+static int run_bwd_mode(const void* dz, const void* z, const void* y, long long M, int C, const float* stats, float* dgamma,
+                        float* dbeta, void* dy, void* dres, float* ws, cudaStream_t st) {
+  // rows in flight per thread: reduction 4 (TDEED_BN_REDUCE_ROWS=8 to try 8: measured equal), apply 4 (TDEED_BN_APPLY_ROWS=2:
+  // 11.66 vs 11.32 ms per FineGym_big step)
+  static int kb = 0, u = 0;
+  if (!kb) { const char* e = getenv("TDEED_BN_REDUCE_ROWS"); kb = (e && atoi(e) == 8) ? 8 : 4; }
+  if (!u) { const char* e = getenv("TDEED_BN_APPLY_ROWS"); u = (e && atoi(e) == 2) ? 2 : 4; }
+  if (kb == 8) return u == 4 ? run_bwd_cfg<T, MODE, 8, 4>(dz, z, y, M, C, stats, dgamma, dbeta, dy, dres, ws, st)
+                             : run_bwd_cfg<T, MODE, 8, 2>(dz, z, y, M, C, stats, dgamma, dbeta, dy, dres, ws, st);
+  return u == 4 ? run_bwd_cfg<T, MODE, 4, 4>(dz, z, y, M, C, stats, dgamma, dbeta, dy, dres, ws, st)
+                : run_bwd_cfg<T, MODE, 4, 2>(dz, z, y, M, C, stats, dgamma, dbeta, dy, dres, ws, st);
 }
 
 template <typename T>
