@@ -181,6 +181,10 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
+    numa_cpus = None
+    if world > 1 and os.environ.get('TDEED_NUMA_BIND', '1') != '0':
+        from tdeed_b200.parallel import bind_to_gpu_numa
+        numa_cpus = bind_to_gpu_numa(local)          # before any pinned allocation: first touch places the pages
     dev = torch.device('cuda', local)
     if world > 1:
         import torch.distributed as dist
@@ -368,7 +372,7 @@ def main():
             'scaling': 'weak', 'vs_baseline': None, 'dtype': args.precision, 'data': 'synthetic',
             'config': {'workload': CONFIG['name'] + ' batched inference + NMS', 'clips_per_step': n_clips,
                        'clips_per_batch': B, 'e2e_cold_batch': cb, 'frame_shape': [100, 3, FRAME_H, FRAME_W], 'video_frames': VIDEO_FRAMES,
-                       'l2_policy': 'inputs (4.5 GB/video) larger than L2', 'parallelism': 'clip-sharded x%d' % world},
+                       'l2_policy': 'inputs (4.5 GB/video) larger than L2', 'parallelism': 'clip-sharded x%d' % world, 'numa_bound_cpus': (len(numa_cpus) if numa_cpus else None)},
             'e2e': {'value': total_clips / e2e_s, 'unit': 'clips/s', 'h2d_bytes_per_step': int(n_clips * 100 * 3 * crop_win[2] * crop_win[3]),
                     'd2h_bytes_per_step': int(d2h[0])},
             'gpu_launches': int(launches), 'clocks': clocks, 'roofline': roofline, 'cpu_baseline': cpu_baseline,

@@ -148,6 +148,9 @@ def run_train(args, quiet=False):
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local)
+    if world > 1 and os.environ.get('TDEED_NUMA_BIND', '1') != '0':
+        from tdeed_b200.parallel import bind_to_gpu_numa
+        bind_to_gpu_numa(local)                    # idempotent; before the pinned host batches are allocated
     dev = torch.device('cuda', local)
     import torch.distributed as dist
     if world > 1 and not dist.is_initialized():

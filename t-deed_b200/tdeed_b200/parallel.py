@@ -62,3 +62,32 @@ def broadcast_parameters(flat_param, src=0):
     rank, ws = world()
     if ws > 1:
         dist.broadcast(flat_param, src=src)
+
+
+def bind_to_gpu_numa(device_index):
+    """Restrict this process to the CPUs NVML reports as local to GPU `device_index` (its NUMA node / PCIe root complex), so that
+    the pinned staging buffers it allocates afterwards (first touch) and the threads that fill them sit next to the GPU.  With
+    eight ranks each streaming ~30 GB/s of pinned clips, un-pinned ranks share one socket's memory controllers and the
+    end-to-end rate stops scaling (5.5x at 8 GPUs, r1g).  Returns the CPU list, or None when NVML / the affinity call is
+    unavailable (the process is then left untouched).  Call it once per rank, before allocating pinned memory."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            pr = torch.cuda.get_device_properties(device_index)
+            bus = '%08x:%02x:%02x.0' % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+            h = pynvml.nvmlDeviceGetHandleByPciBusId(bus)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * i + b for i, w in enumerate(mask) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except Exception:
+        return None
