@@ -24,6 +24,7 @@ namespace tdeed {
 
 constexpr int TC_BM = 128, TC_BK = 64, TC_MAX_STAGES = 10;
 constexpr int TC_THREADS = 320;   // producer warp, MMA warp, 8 epilogue warps
+constexpr int TC_THREADS16 = 576; // producer warp, MMA warp, 16 epilogue warps (EPI == 2)
 
 struct TcParams {
   long long M;
@@ -182,13 +183,55 @@ __device__ __forceinline__ void epi_fast_tile(const TcParams& p, uint64_t* full_
   }
 }
 
+// 16-warp variant: the thread's pieces are the 16-column pieces quarter*16 + 64k of its row.  One TMEM load in flight, the
+// residual of the next piece requested while the current one is processed; latency is hidden by the other 15 warps.
+__device__ __forceinline__ void epi_fast16_tile(const TcParams& p, uint64_t* full_bar, uint32_t parity, uint32_t tmem_row, int quarter,
+                                                int ncols, int n0, long long m, bool row_ok, const float* s_bias) {
+  const bool has_res = p.residual != nullptr && row_ok;
+  const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + m * p.ldr + n0;
+  uint4 r0[2], r1[2];
+  auto load_res = [&](uint4 (&dst)[2], int c0) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      dst[q] = make_uint4(0u, 0u, 0u, 0u);
+      if (has_res && c0 + 8 * q < ncols) dst[q] = *reinterpret_cast<const uint4*>(rp + c0 + 8 * q);
+    }
+  };
+  load_res(r0, quarter * 16);
+  mbar_wait(full_bar, parity);
+  tcgen05_fence_after();
+  const float lo = p.act == TDEED_ACT_RELU ? 0.f : -INFINITY;
+  __nv_bfloat16* grow = row_ok ? reinterpret_cast<__nv_bfloat16*>(p.out) + m * p.ldo + n0 : nullptr;
+  const float* bias = s_bias + n0;
+  uint32_t v[16];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c0 = quarter * 16 + 64 * k;
+    if (c0 < ncols) {                          // uniform over the warp
+      tmem_ld16(tmem_row + (uint32_t)c0, v);
+      if (k & 1) {
+        if (k < 3) load_res(r0, c0 + 64);
+        tmem_ld_wait();
+        epi_fast_chunk<false>(v, r1[0], r1[1], bias, c0, ncols, lo, 0u, grow);
+      } else {
+        if (k < 3) load_res(r1, c0 + 64);
+        tmem_ld_wait();
+        epi_fast_chunk<false>(v, r0[0], r0[1], bias, c0, ncols, lo, 0u, grow);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- kernel
 struct TileCoord { int mt, nt; };
 
-// FAST: the specialised bf16 epilogue is a separate instantiation, so the generic epilogue (fp32 outputs, GELU) keeps its own
-// register allocation.
-template <bool FAST>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// EPI 0: generic epilogue (fp32 outputs, GELU, ...).  EPI 1: the specialised bf16 epilogue as a separate instantiation, so that the
+// generic one keeps its own register allocation.
+// EPI 2: the same straight-line epilogue on SIXTEEN warps (four per TMEM lane group, each taking every fourth 16-column piece;
+// direct stores only).  The 8-warp epilogue issues one instruction per ~14 cycles and warp (a latency chain TMEM -> bias ->
+// residual -> pack -> store with two warps per scheduler); twice the warps hide twice the latency.
+template <int EPI>
+__global__ void __launch_bounds__(EPI == 2 ? TC_THREADS16 : TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -228,12 +271,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 256);     // every epilogue thread arrives
+      mbar_init(&tmem_empty_bar[a], EPI == 2 ? 512 : 256);     // every epilogue thread arrives
     }
     mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < p.n_tiles * p.block_n; i += TC_THREADS) s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < p.n_tiles * p.block_n; i += (int)blockDim.x) s_bias[i] = (p.bias && i < p.N) ? p.bias[i] : 0.f;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"(p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -344,11 +387,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
         m = (long long)mt * TC_BM + r;
         row_ok = m < p.M;
       }
-      if (half == 0) s_rowm[r] = row_ok ? m : -1;           // global row of every tile row (or -1), for phase 2
       const int ncols = min(p.block_n, p.N - n0);           // multiple of 8
       const uint32_t tmem_row = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * (uint32_t)p.block_n;
+      if constexpr (EPI == 2) {
+        epi_fast16_tile(p, &tmem_full_bar[acc], (j >> 1) & 1u, tmem_row, half /* = column quarter */, ncols, n0, m, row_ok, s_bias);
+        tcgen05_fence_before();
+        mbar_arrive(&tmem_empty_bar[acc]);
+        continue;
+      }
+      if (half == 0) s_rowm[r] = row_ok ? m : -1;           // global row of every tile row (or -1), for phase 2
       uint8_t* srow = s_out + r * pitch;
-      if constexpr (FAST) {
+      if constexpr (EPI == 1) {
         if (p.staged && p.out_bufs == 1 && j > 0) epi_bar_sync();   // single staging tile: previous phase 2 must have drained
         if (p.staged) epi_fast_tile<true>(p, &tmem_full_bar[acc], (j >> 1) & 1u, tmem_row, half, ncols, n0, m, row_ok, s_bias, smem_u32(srow));
         else epi_fast_tile<false>(p, &tmem_full_bar[acc], (j >> 1) & 1u, tmem_row, half, ncols, n0, m, row_ok, s_bias, 0u);
@@ -640,8 +689,9 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
   const size_t smem = fixed2 + stages * stage_bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     TDEED_REQUIRE(e == cudaSuccess, TDEED_ERR_CUDA, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -653,8 +703,11 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
   if (trace)
     fprintf(stderr, "gemm_tc M=%lld N=%d K=%d nseg=%d gather=%d res=%d act=%d | block_n=%d n_tiles=%d w_res=%d stages=%d staged=%d out_bufs=%d fast=%d grid=%d smem=%zu\n",
             M, N, K, nseg, p.gather, residual != nullptr, act, block_n, p.n_tiles, p.w_res, stages, p.staged, p.out_bufs, p.fast, grid, smem);
-  if (p.fast) gemm_tc_kernel<true><<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], p);
-  else gemm_tc_kernel<false><<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], p);
+  static int epi16_env = -1;
+  if (epi16_env < 0) { const char* e = getenv("TDEED_GEMM_EPI16"); epi16_env = e ? atoi(e) : 0; }
+  if (p.fast && !p.staged && epi16_env) gemm_tc_kernel<2><<<grid, TC_THREADS16, smem, st>>>(maps[0], maps[1], maps[2], p);
+  else if (p.fast) gemm_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], p);
+  else gemm_tc_kernel<0><<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], p);
   return check_launch("tdeed_gemm_fwd(tcgen05)");
 }
 
