@@ -173,7 +173,13 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl != 'reference' else args.warmup
     if args.workload == 'train':
         import bench_train
-        return bench_train.run_train_reference(args) if args.impl == 'reference' else bench_train.run_train(args)
+        if args.impl == 'reference':
+            return bench_train.run_train_reference(args)
+        out = bench_train.run_train(args)
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+        return out
     if args.impl == 'reference':
         return run_reference(args)
 
