@@ -44,6 +44,7 @@ struct ThinParams {
   uint32_t tmem_cols;
   int nacc_log2;   // log2 of the number of TMEM accumulators (2..8): thin tiles are cheap, the MMA warp may run that far ahead
   int fast;    // specialised bf16 epilogue (act none|relu): pipelined TMEM loads, cross-tile residual prefetch
+  int mma_pair; // staged tiles the MMA warp handles per proxy fence (1..4)
   int split;   // fast && N <= 32: the two epilogue warp halves take alternate tiles (otherwise half of them would idle)
 };
 
@@ -228,24 +229,38 @@ gemm_thin_kernel(const ThinParams p) {
     int stage = 0;
     uint32_t round = 0;
     const int num_stages = p.num_stages, m_tiles = p.m_tiles, nacc_log2 = p.nacc_log2;
-    for (int tile = blockIdx.x; tile < m_tiles; tile += gridDim.x, ++it) {
-      const uint32_t acc = it & ((1u << nacc_log2) - 1u);
-      th_wait(&tmem_empty_bar[acc], ((it >> nacc_log2) & 1u) ^ 1u);
-      th_wait(&full_bar[stage], round & 1u);
+    // Two tiles per trip: the generic->async proxy fence and the tcgen05 fence are paid once per PAIR of staged tiles (per
+    // tile they kept this single warp ~70 % busy and made it the pacing role of the thin layers: ncu r1h).
+    const int pair_env = p.mma_pair;
+    for (int tile = blockIdx.x; tile < m_tiles; ) {
+      int ntl = 1;                                   // tiles of this trip: up to p.mma_pair, limited by what is left
+      while (ntl < pair_env && tile + ntl * (int)gridDim.x < m_tiles) ++ntl;
+      uint32_t accs[4];
+      int stages[4];
+      for (int u = 0; u < ntl; ++u) {
+        accs[u] = (it + u) & ((1u << nacc_log2) - 1u);
+        th_wait(&tmem_empty_bar[accs[u]], (((it + u) >> nacc_log2) & 1u) ^ 1u);
+        th_wait(&full_bar[stage], round & 1u);
+        stages[u] = stage;
+        if (++stage == num_stages) { stage = 0; ++round; }
+      }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) data -> visible to the MMA (async proxy)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (lane == 0) {
-        const uint32_t a0 = sA_u32 + (uint32_t)stage * p.stage_bytes;
-        for (int k = 0; k < p.planes / 2; ++k) {
-          const uint64_t adesc = th_desc(a0 + (uint32_t)(2 * k) * p.a_plane_bytes, p.a_plane_bytes, 128u);
-          const uint64_t bdesc = th_desc(sW_u32 + (uint32_t)(2 * k) * p.w_plane_bytes, p.w_plane_bytes, 128u);
-          th_umma(tmem_base + acc * (uint32_t)p.block_n, adesc, bdesc, idesc, k != 0 ? 1u : 0u);
+        for (int u = 0; u < ntl; ++u) {
+          const uint32_t a0 = sA_u32 + (uint32_t)stages[u] * p.stage_bytes;
+          for (int k = 0; k < p.planes / 2; ++k) {
+            const uint64_t adesc = th_desc(a0 + (uint32_t)(2 * k) * p.a_plane_bytes, p.a_plane_bytes, 128u);
+            const uint64_t bdesc = th_desc(sW_u32 + (uint32_t)(2 * k) * p.w_plane_bytes, p.w_plane_bytes, 128u);
+            th_umma(tmem_base + accs[u] * (uint32_t)p.block_n, adesc, bdesc, idesc, k != 0 ? 1u : 0u);
+          }
+          th_commit(&empty_bar[stages[u]]);
+          th_commit(&tmem_full_bar[accs[u]]);
         }
-        th_commit(&empty_bar[stage]);
-        th_commit(&tmem_full_bar[acc]);
       }
       __syncwarp();
-      if (++stage == num_stages) { stage = 0; ++round; }
+      it += ntl;
+      tile += ntl * (int)gridDim.x;
     }
   } else {
     // ===== epilogue (8 warps): TMEM -> bias / residual / activation -> global =====
@@ -441,6 +456,10 @@ int gemm_thin_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* 
   if (fast_env < 0) { const char* e = getenv("TDEED_GEMM_FAST_EPI"); fast_env = e ? atoi(e) : 1; }
   p.fast = (fast_env && out_dtype == TDEED_BF16 && (act == TDEED_ACT_NONE || act == TDEED_ACT_RELU)) ? 1 : 0;
   p.split = (p.fast && N <= 32) ? 1 : 0;
+  static int pair_env = -1;
+  if (pair_env < 0) { const char* e = getenv("TDEED_THIN_MMA_PAIR"); pair_env = e ? atoi(e) : 2; }
+  p.mma_pair = p.num_stages >= 8 ? (pair_env > 4 ? 4 : (pair_env < 1 ? 1 : pair_env)) : 1;     // tiles per MMA-warp trip
+  if (p.mma_pair > (1 << p.nacc_log2)) p.mma_pair = 1 << p.nacc_log2;   // a trip must not wait for an accumulator it fills itself
   const int grid = p.m_tiles < kNumSMs ? p.m_tiles : kNumSMs;
   gemm_thin_kernel<<<grid, TH_THREADS, smem, st>>>(p);
   return check_launch("tdeed_gemm_fwd(tcgen05 thin-K)");
