@@ -75,3 +75,16 @@ def test_data_parallel_gradient_allreduce_world2():
     for r in range(ws):
         g, scale, p = out[r]
         assert g == want and scale == 0.5 and p == [5.0] * 10
+
+
+def test_bind_to_gpu_numa_is_harmless_without_a_gpu():
+    """The per-rank CPU binding used by the multi-rank bench must never raise and must leave the affinity alone when NVML (or
+    the device) is not there."""
+    from tdeed_b200.parallel import bind_to_gpu_numa
+    before = os.sched_getaffinity(0)
+    cpus = bind_to_gpu_numa(0)
+    after = os.sched_getaffinity(0)
+    assert cpus is None or set(cpus) == after
+    if cpus is None:
+        assert after == before
+    os.sched_setaffinity(0, before)
