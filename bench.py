@@ -356,6 +356,7 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, 'oracle'))
         import tdeed_oracle as O
         cores = os.cpu_count()
+        prev_threads = torch.get_num_threads()
         torch.set_num_threads(cores)
         cfg = O.named_config(CONFIG['name'])
         sd = {k_: v.detach().cpu() for k_, v in model.state_dict().items()}
@@ -368,6 +369,8 @@ def main():
         dt = (time.perf_counter() - t0) / reps
         cpu_baseline = {'value': 1.0 / dt, 'unit': 'clips/s', 'cores': cores, 'kind': 'port',
                         'sample': '%d x 1 clip (100x3x224x398 u8) through the CPU oracle fp32 forward, torch threads = %d' % (reps, cores)}
+        # the training side measurement below enqueues from this thread: do not leave a wide intra-op pool spinning next to it
+        torch.set_num_threads(max(1, min(prev_threads, 2)))
 
     if rank == 0:
         total_clips = n_clips * args.steps * world
