@@ -472,6 +472,7 @@ static int run_gsf_bwd(int mode, const void* x, const void* dcat, const void* ad
                        int fold, const float* stats, const float* w3d, const float* cc_w, const float* fwd_ws, float* ws,
                        void* dx, float* dw3d, float* db3d, float* dcc, float* dgamma, float* dbeta, cudaStream_t st) {
   const int n = clips * clip_len, hw = h * w;
+  TDEED_REQUIRE(n <= 65535, TDEED_ERR_UNSUPPORTED, "tdeed_gsf_bwd: %d frames per call (frames sit on grid.y of the dW3d kernel: at most 65535; split the batch)", n);
   const long long M = (long long)n * hw;
   const float* gate = fwd_ws;
   const float* sums = gate + (size_t)n * hw * 2;
