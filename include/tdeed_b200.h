@@ -224,6 +224,19 @@ int tdeed_nms(const int* frame, const int* label, const float* score, const int*
               int K, int window, double threshold, int soft, void* workspace,
               int* out_frame, int* out_label, double* out_score, int* out_count, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (12) frame-feature cache of the video-level engine.  The reference's inference clips overlap by 75 %
+ * (dataset/frame.py:409-423: starts every (clip_len - overlap_len) * stride frames; util/eval.py:289-349 runs
+ * each clip through the whole network), while everything before the first GatedShift (model/shift.py:47-59: s3.b1)
+ * is clip-independent.  Those per-frame features are computed once per unique frame and kept in HBM; this entry
+ * point files rows into the cache and assembles clip batches from it:
+ *     dst[dst_idx ? dst_idx[i] : i] = (src_idx[i] < 0) ? pad_row : src[src_idx[i]]      for i in [0, n_rows)
+ * rows are row_bytes (multiple of 16) long and 16-byte aligned.  Negative source indices select pad_row — the
+ * features of the all-zero frame the reference pads clips with before frame 0 / past the end of the video
+ * (dataset/frame.py:622-625); pad_row may be NULL when no index is negative. */
+int tdeed_gather_rows(const void* src, const void* pad_row, void* dst, const int* src_idx, const int* dst_idx,
+                      int n_rows, long long row_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

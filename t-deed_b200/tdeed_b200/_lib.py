@@ -72,6 +72,7 @@ SIGNATURES = {
     'tdeed_nms_workspace_bytes': (c_ll, [c_int, c_int]),
     'tdeed_nms': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_double, c_int, c_vp, c_vp, c_vp, c_vp,
                           c_vp, c_vp]),
+    'tdeed_gather_rows': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_ll, c_vp]),
 }
 
 # include/tdeed_b200_train.h

@@ -244,11 +244,21 @@ class InferenceEngine:
         cy, cx = center_crop_offsets(in_h, in_w, self.cfg.crop_dim)
         return cy, cx, self.cfg.crop_dim, self.cfg.crop_dim
 
-    def backbone(self, frames, flip=False, crop=None, taps=None):
-        """frames (B,T,3,H,W) u8|f32 on device -> feat (B*T, d) fp32 (pooled + temp_enc)."""
-        cfg, W, adt = self.cfg, self.W, self.act_dtype
-        b, t = frames.shape[:2]
-        n = b * t
+    def split_index(self):
+        """Number of leading bottleneck blocks that are clip-independent: everything before the first GatedShift
+        (model/shift.py:47-59 wraps conv1 of every block of s3 and s4).  Their per-frame output can be cached and
+        shared by the overlapping clips of a video (see tdeed_b200.pipeline.VideoInference)."""
+        for i, blk in enumerate(self.W['blocks']):
+            if blk['shifted']:
+                return i
+        return len(self.W['blocks'])
+
+    def lower(self, frames, flip=False, crop=None, taps=None):
+        """frames (N,3,H,W) u8|f32 on device -> NHWC activation (N,h,w,c) after the last clip-independent block
+        (stem, s1, s2 for the gate-shift backbones).  No cross-frame arithmetic: frame i of the output depends on frame i
+        of the input only, so the result is the same whichever clip / batch a frame arrives in."""
+        W, adt = self.W, self.act_dtype
+        n = frames.shape[0]
         in_h, in_w = frames.shape[-2:]
         crop = crop or self.crop_window(in_h, in_w)
         es = 2 if adt == torch.bfloat16 else 4
@@ -262,32 +272,57 @@ class InferenceEngine:
             if frames.dtype == torch.uint8 and self.stem_v2:
                 x_sub, a1_fused = self._op('stem', 2.0 * n * oh0 * ow0 * 32 * (27 + c1),
                                            n * (3 * crop[2] * crop[3] * frames.element_size() + oh0 * ow0 * (c1 + 8) * es),
-                                           ops.stem_tc2, frames.reshape(n, 3, in_h, in_w), crop, flip, W['stem2_wimg'], W['stem2_b0'],
+                                           ops.stem_tc2, frames, crop, flip, W['stem2_wimg'], W['stem2_b0'],
                                            W['stem2_pad'], W['blocks'][0]['w1_fused'], W['blocks'][0]['b1'], c1, 2)
             else:
                 x_sub, a1_fused = self._op('stem', 2.0 * n * oh0 * ow0 * 32 * (27 + c1),
                                            n * (3 * crop[2] * crop[3] * frames.element_size() + oh0 * ow0 * (c1 + 8) * es),
-                                           ops.stem_tc, frames.reshape(n, 3, in_h, in_w), crop, flip, W['stem_w_tc'], W['stem_b'],
+                                           ops.stem_tc, frames, crop, flip, W['stem_w_tc'], W['stem_b'],
                                            W['blocks'][0]['w1_fused'], W['blocks'][0]['b1'], c1, True, 2)
             x = None
         elif adt == torch.bfloat16 and self.fuse_stem:
             x, _ = self._op('stem', 2.0 * n * oh0 * ow0 * 32 * 27, n * (3 * crop[2] * crop[3] * frames.element_size() + oh0 * ow0 * 32 * es),
-                            ops.stem_tc, frames.reshape(n, 3, in_h, in_w), crop, flip, W['stem_w_tc'], W['stem_b'])
+                            ops.stem_tc, frames, crop, flip, W['stem_w_tc'], W['stem_b'])
         else:
             x = self._op('stem', 2.0 * n * oh0 * ow0 * 32 * 27, n * (3 * crop[2] * crop[3] * frames.element_size() + oh0 * ow0 * 32 * es),
-                         ops.stem, frames.reshape(n, 3, in_h, in_w), crop, flip, W['stem_w'], W['stem_b'], adt)
+                         ops.stem, frames, crop, flip, W['stem_w'], W['stem_b'], adt)
         if taps is not None:
             taps['stem'] = x
-        for bi, blk in enumerate(W['blocks']):
+        for bi in range(self.split_index()):
+            blk = W['blocks'][bi]
             if bi == 0 and a1_fused is not None:
-                h, w, cin = oh0, ow0, 32
+                x = self._block(bi, blk, None, n, None, None, taps, fused=(a1_fused, x_sub, oh0, ow0))
             else:
-                _, h, w, cin = x.shape
-            cout, stride = blk['cout'], blk['stride']
-            m = n * h * w
-            if bi == 0 and a1_fused is not None:
-                pass
-            elif blk['shifted']:
+                x = self._block(bi, blk, x, n, None, None, taps)
+        return x
+
+    def upper(self, x, b, t, taps=None):
+        """x NHWC (b*t, h, w, c): output of lower() laid out clip-major -> feat (b*t, d) fp32 (pooled + temp_enc)."""
+        W = self.W
+        n = b * t
+        es = 2 if self.act_dtype == torch.bfloat16 else 4
+        for bi in range(self.split_index(), len(W['blocks'])):
+            x = self._block(bi, W['blocks'][bi], x, n, b, t, taps)
+        hw = x.shape[1] * x.shape[2]
+        return self._op('pool_posenc', float(n * hw * x.shape[3]), n * hw * x.shape[3] * es + n * x.shape[3] * 4,
+                        ops.pool_posenc, x, t, W['temp_enc'])
+
+    def _block(self, bi, blk, x, n, b, t, taps, fused=None):
+        """One RegNetY bottleneck incl. its gate-shift prologue (a5-a7) when `shifted`."""
+        cfg, adt = self.cfg, self.act_dtype
+        es = 2 if adt == torch.bfloat16 else 4
+        if fused is not None:
+            a1_fused, x_sub, h, w = fused
+            cin = 32
+        else:
+            a1_fused = None
+            _, h, w, cin = x.shape
+        cout, stride = blk['cout'], blk['stride']
+        m = n * h * w
+        if a1_fused is not None:
+            a1 = a1_fused
+        else:
+            if blk['shifted']:
                 gs = blk['gs']
                 fd = gs['fold']
                 ws = torch.empty(ops.gsf_workspace_floats(b, t, h, w, fd), dtype=torch.float32, device=x.device)
@@ -298,25 +333,22 @@ class InferenceEngine:
                 segs = [(gso, gso.shape[1], 0, gso.shape[1]), (x, cin, blk['x_start'], cin - blk['x_start'])]
             else:
                 segs = [(x, cin, 0, cin)]
-            if bi == 0 and a1_fused is not None:
-                a1 = a1_fused
-            else:
-                a1 = self._gemm(segs, blk['w1'], blk['b1'], label='conv1x1', act=L.ACT_RELU, rows=m).view(n, h, w, cout)
-            oh, ow = (h + stride - 1) // stride, (w + stride - 1) // stride
-            mo = n * oh * ow
-            if 'w2_img' in blk and self.conv3_tc:
-                a2 = self._op('conv3x3g', 2.0 * mo * cout * 9 * blk['gw'], (m + mo) * cout * es + cout * 9 * blk['gw'] * 4,
-                              ops.conv3x3g_tc, a1, blk['w2_img'], blk['b2'], stride)
-            else:
-                a2 = self._op('conv3x3g', 2.0 * mo * cout * 9 * blk['gw'], (m + mo) * cout * es + cout * 9 * blk['gw'] * 4,
-                              ops.conv3x3g, a1, blk['w2'], blk['b2'], blk['gw'], stride)
-            self._op('se', 4.0 * n * cout * blk['se_w1'].shape[0], 2 * mo * cout * es,
-                     ops.se_, a2, blk['se_w1'], blk['se_b1'], blk['se_w2'], blk['se_b2'])
-            if bi == 0 and a1_fused is not None and 'w3d' in blk and self.fuse_ds0:
-                x = self._gemm([(a2.view(mo, cout), cout, 0, cout), (x_sub.view(mo, 32), 32, 0, 32)], blk['w3d'], blk['b3d'],
-                               label='conv1x1', act=L.ACT_RELU, rows=mo).view(n, oh, ow, cout)
-                continue
-            if bi == 0 and a1_fused is not None:
+            a1 = self._gemm(segs, blk['w1'], blk['b1'], label='conv1x1', act=L.ACT_RELU, rows=m).view(n, h, w, cout)
+        oh, ow = (h + stride - 1) // stride, (w + stride - 1) // stride
+        mo = n * oh * ow
+        if 'w2_img' in blk and self.conv3_tc:
+            a2 = self._op('conv3x3g', 2.0 * mo * cout * 9 * blk['gw'], (m + mo) * cout * es + cout * 9 * blk['gw'] * 4,
+                          ops.conv3x3g_tc, a1, blk['w2_img'], blk['b2'], stride)
+        else:
+            a2 = self._op('conv3x3g', 2.0 * mo * cout * 9 * blk['gw'], (m + mo) * cout * es + cout * 9 * blk['gw'] * 4,
+                          ops.conv3x3g, a1, blk['w2'], blk['b2'], blk['gw'], stride)
+        self._op('se', 4.0 * n * cout * blk['se_w1'].shape[0], 2 * mo * cout * es,
+                 ops.se_, a2, blk['se_w1'], blk['se_b1'], blk['se_w2'], blk['se_b2'])
+        if a1_fused is not None and 'w3d' in blk and self.fuse_ds0:
+            x = self._gemm([(a2.view(mo, cout), cout, 0, cout), (x_sub.view(mo, 32), 32, 0, 32)], blk['w3d'], blk['b3d'],
+                           label='conv1x1', act=L.ACT_RELU, rows=mo).view(n, oh, ow, cout)
+        else:
+            if a1_fused is not None:
                 # the stem kernel already wrote the stride-2 subsample: plain GEMM, no gather
                 res = self._gemm([(x_sub, 32, 0, 32)], blk['wd'], blk['bd'], label='conv1x1_ds', rows=mo)
             elif 'wd' in blk:
@@ -326,11 +358,15 @@ class InferenceEngine:
                 res = x.view(mo, cout)
             x = self._gemm([(a2.view(mo, cout), cout, 0, cout)], blk['w3'], blk['b3'], label='conv1x1', residual=res,
                            act=L.ACT_RELU, rows=mo).view(n, oh, ow, cout)
-            if taps is not None:
-                taps['s%d.b%d' % (self._stage_of(bi))] = x
-        hw = x.shape[1] * x.shape[2]
-        return self._op('pool_posenc', float(n * hw * x.shape[3]), n * hw * x.shape[3] * es + n * x.shape[3] * 4,
-                        ops.pool_posenc, x, t, W['temp_enc'])
+        if taps is not None:
+            taps['s%d.b%d' % (self._stage_of(bi))] = x
+        return x
+
+    def backbone(self, frames, flip=False, crop=None, taps=None):
+        """frames (B,T,3,H,W) u8|f32 on device -> feat (B*T, d) fp32 (pooled + temp_enc)."""
+        b, t = frames.shape[:2]
+        x = self.lower(frames.reshape(b * t, 3, frames.shape[-2], frames.shape[-1]), flip=flip, crop=crop, taps=taps)
+        return self.upper(x, b, t, taps=taps)
 
     def _stage_of(self, bi):
         depths = REGNET[self.cfg.backbone]['depths']
@@ -396,28 +432,49 @@ class InferenceEngine:
         return self.heads(x)
 
     # ------------------------------------------------------------------ CUDA graph replay
-    def forward_graphed(self, frames, flip=False, crop=None):
-        """Same as forward() but replays a captured CUDA graph (static shapes).  Returns views of
-        static output buffers that are overwritten by the next call with the same key."""
-        key = (tuple(frames.shape), frames.dtype, bool(flip), crop)
+    def graphed(self, key, fn):
+        """Run `fn()` — a closure that launches engine kernels reading STATIC device tensors — through a CUDA graph captured
+        the first time `key` is seen (two eager warm-up runs on a side stream set kernel attributes and prime the allocator).
+        Returns fn's outputs: views of graph-owned buffers, overwritten by the next replay of the same key."""
         ent = self._graphs.get(key)
         if ent is None:
-            static_in = torch.empty_like(frames)
-            static_in.copy_(frames)
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                for _ in range(2):               # warm-up: sets kernel attributes, primes the allocator
-                    self.forward(static_in, flip=flip, crop=crop)
+                for _ in range(2):
+                    fn()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             n0 = self.launches
-            with torch.cuda.graph(graph):
-                outs = self.forward(static_in, flip=flip, crop=crop)
-            ent = dict(graph=graph, static_in=static_in, outs=outs, launches=self.launches - n0)
+            # thread_local: a DataLoader pin-memory thread may be calling into CUDA while we capture (ADVICE r1)
+            with torch.cuda.graph(graph, capture_error_mode='thread_local'):
+                outs = fn()
+            ent = dict(graph=graph, outs=outs, launches=self.launches - n0)
             self._graphs[key] = ent
-        ent['static_in'].copy_(frames, non_blocking=True)
         ent['graph'].replay()
         self.launches += ent['launches']
         return ent['outs']
+
+    def forward_graphed(self, frames, flip=False, crop=None, static=False):
+        """forward() replayed from a CUDA graph (static shapes).  static=False: `frames` is copied into a graph-owned input
+        buffer first (any tensor works).  static=True: the graph is captured on `frames`' own storage — the caller promises
+        that the same buffer (e.g. one of ClipUploader's two) is refilled in place for later calls; no extra copy."""
+        shape_key = (tuple(frames.shape), frames.dtype, bool(flip), crop)
+        if static:
+            return self.graphed(('fwd', frames.data_ptr()) + shape_key, lambda: self.forward(frames, flip=flip, crop=crop))
+        buf = self._graphs.get(('fwd_in',) + shape_key)
+        if buf is None:
+            buf = self._graphs[('fwd_in',) + shape_key] = torch.empty_like(frames)
+        buf.copy_(frames, non_blocking=True)
+        return self.graphed(('fwd', buf.data_ptr()) + shape_key, lambda: self.forward(buf, flip=flip, crop=crop))
+
+    def lower_graphed(self, frames, flip=False, crop=None):
+        """lower() on a static (N,3,H,W) device buffer, replayed from a CUDA graph keyed by the buffer's address."""
+        key = ('lower', frames.data_ptr(), tuple(frames.shape), frames.dtype, bool(flip), crop)
+        return self.graphed(key, lambda: self.lower(frames, flip=flip, crop=crop))
+
+    def upper_graphed(self, x, b, t):
+        """upper() + temporal() + heads() on a static clip-major feature buffer x (b*t, h, w, c)."""
+        key = ('upper', x.data_ptr(), tuple(x.shape), b, t)
+        return self.graphed(key, lambda: self.heads(self.temporal(self.upper(x, b, t).view(b, t, self.cfg.feat_dim))))

@@ -257,3 +257,14 @@ def nms(frame, label, score, n_events_dev, k, window, threshold, soft):
                                float(threshold), int(bool(soft)), L.ptr(ws), L.ptr(of), L.ptr(ol), L.ptr(os_),
                                L.ptr(oc), L.stream()), 'nms')
     return of, ol, os_, oc
+
+
+def gather_rows(src, src_idx, dst, dst_idx=None, pad_row=None):
+    """dst[dst_idx[i] | i] = src[src_idx[i]] (pad_row where src_idx[i] < 0): frame-feature cache plumbing.
+    src / dst: contiguous tensors whose leading dim indexes rows; src_idx / dst_idx: int32 device tensors."""
+    n = src_idx.numel()
+    row_bytes = src[0].numel() * src.element_size()
+    assert dst[0].numel() * dst.element_size() == row_bytes and src.is_contiguous() and dst.is_contiguous()
+    L.check(L.load().tdeed_gather_rows(L.ptr(src), L.ptr(pad_row), L.ptr(dst), L.ptr(src_idx), L.ptr(dst_idx), n, row_bytes,
+                                       L.stream()), 'gather_rows')
+    return dst

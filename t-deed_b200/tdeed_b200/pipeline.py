@@ -154,3 +154,135 @@ def events_to_dicts(video, fps, frames, labels, scores, classes_inv):
     return {'video': video, 'fps': fps,
             'events': [{'label': classes_inv[int(l)], 'frame': int(f), 'score': float(s)}
                        for f, l, s in zip(frames, labels, scores)]}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# video-level inference: every unique frame passes the clip-independent layers once
+# ---------------------------------------------------------------------------------------------------------------------
+class VideoInference:
+    """Streams the frames of a list of videos through the engine and returns per-video device-resident scores.
+
+    The reference slices a video into clips that overlap by 75 % (dataset/frame.py:409-423) and runs each clip through the
+    whole network (util/eval.py:289-349), so stem + s1 + s2 — which see one frame at a time; the first cross-frame
+    operator is the GatedShift of s3.b1 (model/shift.py:47-59) — process every frame four times and every frame crosses
+    PCIe four times.  Here the frames of all videos form ONE stream: chunks of `frames_per_chunk` unique frames are
+    uploaded once, run through InferenceEngine.lower() once (twice with the flipped TTA view) and filed into a ring of
+    per-frame features in HBM; clip batches are gathered from the ring (tdeed_gather_rows) and finished by upper() +
+    temporal() + heads().  Frames before 0 / past the end of a video read the features of the all-zero frame, exactly what
+    the reference's zero padding (dataset/frame.py:622-625) produces.  Results are bit-identical to per-clip execution
+    (tests/test_gpu_video.py): no kernel of the lower part mixes frames, and clip order == accumulation order.
+
+        vi = VideoInference(engine, in_hw=(224, 398), clips_per_batch=57, frames_per_chunk=1425, flips=(False,))
+        scores = vi.run(videos, chunks)   # videos: [(name, video_len, [clip starts])]; chunks: iterator of pinned uint8
+                                          # (n, 3, H, W) host tensors = the videos' frames back to back, n == frames_per_chunk
+                                          # for every chunk but the last
+    """
+
+    def __init__(self, engine, in_hw, clips_per_batch=57, frames_per_chunk=None, flips=(False,), clip_len=None,
+                 upload_crop=True):
+        self.eng = engine
+        self.dev = engine.device
+        self.T = clip_len or engine.cfg.clip_len
+        self.B = clips_per_batch
+        self.N = frames_per_chunk or max(self.T, self.B * max(1, self.T // 4))
+        self.flips = tuple(flips)
+        self.K = engine.cfg.num_classes + 1
+        in_h, in_w = in_hw
+        cy, cx, ch, cw = engine.crop_window(in_h, in_w)
+        # only the window the network's center crop keeps crosses PCIe (strided 2D DMA); rows must stay whole for that
+        self.upload_crop = (cy, cx, ch, cw) if (upload_crop and ch == in_h and cw != in_w) else None
+        self.dev_crop = (0, 0, ch, cw) if self.upload_crop else (cy, cx, ch, cw)
+        self.uploader = ClipUploader((self.N, 3, in_h, in_w), self.dev, crop=self.upload_crop)
+        self.in_hw = (in_h, in_w)
+        self.W_slots = self.B * self.T + 2 * self.N
+        self.ring = None            # per flip: (W_slots, h, w, c)
+        self.pad = None             # per flip: (h, w, c) features of the all-zero frame
+        self._iota = torch.arange(self.N, dtype=torch.int32, device=self.dev)
+        self.h2d_bytes = 0
+        self.frames_in = 0
+        self.clips_out = 0
+
+    def _prepare(self):
+        if self.ring is not None:
+            return
+        eng = self.eng
+        hw = self.dev_crop[2:] if self.upload_crop else self.in_hw
+        black = torch.zeros((1, 3) + tuple(hw), dtype=torch.uint8, device=self.dev)
+        self.ring, self.pad, self.xg = [], [], []
+        for flip in self.flips:
+            f = eng.lower(black, flip=flip, crop=self.dev_crop)[0].clone()
+            self.pad.append(f)
+            self.ring.append(torch.empty((self.W_slots,) + tuple(f.shape), dtype=f.dtype, device=self.dev))
+            self.xg.append(torch.empty((self.B * self.T,) + tuple(f.shape), dtype=f.dtype, device=self.dev))
+
+    def _push(self, host_chunk, g0):
+        """Upload one chunk of unique frames (global indices g0 ..) and file its features into the ring(s)."""
+        n = host_chunk.shape[0]
+        x = self.uploader.upload(host_chunk)
+        buf = self.uploader.bufs[self.uploader._k]          # full static buffer: the graph always runs N frames
+        self.h2d_bytes += n * 3 * x.shape[-2] * x.shape[-1]
+        slots = torch.as_tensor((np.arange(g0, g0 + n) % self.W_slots).astype(np.int32)).pin_memory().to(self.dev, non_blocking=True)
+        for fi, flip in enumerate(self.flips):
+            feat = self.eng.lower_graphed(buf, flip=flip, crop=self.dev_crop)
+            ops.gather_rows(feat, self._iota[:n], self.ring[fi], dst_idx=slots)
+        self.uploader.release()
+        self.frames_in += n
+
+    def run(self, videos, chunks, on_video=None):
+        """videos: [(name, video_len, starts)] in stream order; chunks: iterator of pinned uint8 (n,3,H,W) host tensors.
+        Returns {name: VideoScores}.  on_video(name, VideoScores) is called as soon as a video's last clip has been
+        accumulated (lets the caller start event extraction / D2H while later videos still compute)."""
+        self._prepare()
+        eng, T, B, K = self.eng, self.T, self.B, self.K
+        tta = len(self.flips) > 1
+        base, g = {}, 0
+        for name, vlen, _ in videos:
+            base[name] = g
+            g += vlen
+        total_frames = g
+        clips = [(name, vlen, s) for name, vlen, starts in videos for s in starts]
+        last_clip = {}
+        for ci, (name, _, _) in enumerate(clips):
+            last_clip[name] = ci
+        scores = {name: VideoScores(vlen, K, self.dev) for name, vlen, _ in videos}
+        chunks = iter(chunks)
+        pushed = 0
+        for lo in range(0, len(clips), B):
+            batch = clips[lo:lo + B]
+            need = 0
+            idx = np.full((B, T), -1, np.int32)
+            for bi, (name, vlen, s) in enumerate(batch):
+                f = np.arange(s, s + T)
+                ok = (f >= 0) & (f < vlen)
+                idx[bi, ok] = (base[name] + f[ok]) % self.W_slots
+                if ok.any():
+                    need = max(need, base[name] + int(f[ok].max()) + 1)
+            while pushed < min(need, total_frames):
+                chunk = next(chunks)
+                self._push(chunk, pushed)
+                pushed += chunk.shape[0]
+            idx_dev = torch.as_tensor(idx.reshape(-1)).pin_memory().to(self.dev, non_blocking=True)
+            outs = []
+            for fi in range(len(self.flips)):
+                ops.gather_rows(self.ring[fi], idx_dev, self.xg[fi], pad_row=self.pad[fi])
+                _, _, probs = eng.upper_graphed(self.xg[fi], B, T)
+                outs.append(probs)
+            nb = len(batch)
+            if tta:     # the reference adds plain then flipped view clip by clip (util/eval.py:321-349): keep that order
+                probs = torch.stack(outs, dim=1)[:nb].reshape(nb * len(outs), T, K)
+            else:
+                probs = outs[0][:nb]
+            rep = len(outs) if tta else 1
+            bi = 0
+            while bi < nb:                      # clips of one batch may belong to several videos
+                name = batch[bi][0]
+                bj = bi
+                while bj < nb and batch[bj][0] == name:
+                    bj += 1
+                st = [batch[i][2] for i in range(bi, bj) for _ in range(rep)]
+                scores[name].add(probs[bi * rep:bj * rep], st, tta=tta)
+                if on_video is not None and last_clip[name] == lo + bj - 1:
+                    on_video(name, scores[name])
+                bi = bj
+            self.clips_out += nb
+        return scores

@@ -104,9 +104,19 @@ def test_graph_replay_matches_eager_and_tracks_weight_updates(dev):
     m.load(O.random_state(cfg, 6))                    # new weights must invalidate prepared weights + graphs
     _, p_new = m.predict(frames, use_amp=True, use_graph=True)
     assert not np.array_equal(p_new, p_graph)
-    cls, ref = O.predict(O.random_state(cfg, 6), cfg, frames)
-    assert np.abs(p_new - ref).max() < BF16_TOL_PROBS * 2 or True   # scatter targets may differ in bf16; shape/finite only
     assert np.isfinite(p_new).all()
+    # the new weights really are the ones in use: the exact fp32 engine (rebuilt by the same load) matches the oracle,
+    # and wherever bf16 and the oracle agree on the displacement scatter targets the bf16 probabilities are close too
+    _, ref = O.predict(O.random_state(cfg, 6), cfg, frames)
+    _, p32 = m.predict(frames, use_amp=False, use_graph=True)
+    with torch.no_grad():
+        pred32, _ = m._model(frames.to(dev), inference=True)
+        _, displ_ref = O.forward(O.random_state(cfg, 6), cfg, frames)
+    if np.array_equal(np.rint(pred32['displ_feat'].cpu().numpy()), np.rint(displ_ref.numpy())):
+        assert np.abs(p32 - ref).max() < 2e-3
+    with torch.no_grad(), torch.autocast('cuda', dtype=torch.bfloat16):
+        pred16, _ = m._model(frames.to(dev), inference=True)
+    assert rel_err(pred16['im_feat'].cpu().numpy(), pred32['im_feat'].cpu().numpy()) < BF16_TOL_LOGITS
 
 
 def test_full_size_clip_fp32_vs_oracle(dev):
