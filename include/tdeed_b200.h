@@ -237,6 +237,19 @@ int tdeed_nms(const int* frame, const int* label, const float* score, const int*
 int tdeed_gather_rows(const void* src, const void* pad_row, void* dst, const int* src_idx, const int* dst_idx,
                       int n_rows, long long row_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * (13) greedy prediction <-> ground-truth matching of the mAP scorer (util/score.py:45-89,
+ * compute_average_precision).  A unit = the predictions of one (class, video) in descending-score order
+ * (pred_frame[pred_off[u] .. pred_off[u+1])) and that video's ground-truth frames of the class in label-file order
+ * (gt_frame[gt_off[u] .. gt_off[u+1])).  For every tolerance independently, predictions are visited in order; each takes
+ * the closest ground-truth frame not recalled yet (lowest list index among equal distances) and, if it lies within the
+ * tolerance, recalls it (all duplicates of that frame value with it): tp[t][p] = 1, else 0.  tp is u8 [n_tol][total_pred]
+ * (entries of predictions that belong to no unit are left untouched: zero them beforehand);
+ * recalled_ws: u8 [n_tol][total_gt] scratch. */
+int tdeed_match_events(const int* pred_frame, const int* pred_off, const int* gt_frame, const int* gt_off, int n_units,
+                       int total_pred, int total_gt, const int* tolerances, int n_tol, unsigned char* recalled_ws,
+                       unsigned char* tp, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

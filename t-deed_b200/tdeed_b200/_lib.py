@@ -73,6 +73,7 @@ SIGNATURES = {
     'tdeed_nms': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_double, c_int, c_vp, c_vp, c_vp, c_vp,
                           c_vp, c_vp]),
     'tdeed_gather_rows': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_ll, c_vp]),
+    'tdeed_match_events': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp]),
 }
 
 # include/tdeed_b200_train.h

@@ -215,6 +215,7 @@ class InferenceEngine:
             W['displ_w'] = W['displ_b'] = None
         self.W = W
         self._graphs.clear()
+        self.version = getattr(self, 'version', 0) + 1      # bumps whenever prepared weights change (caches keyed on it)
 
     # ------------------------------------------------------------------ forward
     def _op(self, label, flops, nbytes, fn, *a, **k):

@@ -268,3 +268,19 @@ def gather_rows(src, src_idx, dst, dst_idx=None, pad_row=None):
     L.check(L.load().tdeed_gather_rows(L.ptr(src), L.ptr(pad_row), L.ptr(dst), L.ptr(src_idx), L.ptr(dst_idx), n, row_bytes,
                                        L.stream()), 'gather_rows')
     return dst
+
+
+def match_events(pred_frame, pred_off, gt_frame, gt_off, tolerances, total_pred=None):
+    """Greedy matching of util/score.py:45-89 for all (class, video) units x tolerances; int32 device tensors in,
+    tp uint8 (n_tol, total_pred) out (see include/tdeed_b200.h (13))."""
+    dev = pred_off.device
+    n_units = pred_off.numel() - 1
+    total_pred = pred_frame.numel() if total_pred is None else total_pred
+    total_gt = gt_frame.numel()
+    n_tol = tolerances.numel()
+    tp = torch.zeros((n_tol, total_pred), dtype=torch.uint8, device=dev)
+    if n_units > 0:
+        ws = torch.empty((n_tol, max(total_gt, 1)), dtype=torch.uint8, device=dev)
+        L.check(L.load().tdeed_match_events(L.ptr(pred_frame), L.ptr(pred_off), L.ptr(gt_frame), L.ptr(gt_off), n_units, total_pred,
+                                            total_gt, L.ptr(tolerances), n_tol, L.ptr(ws), L.ptr(tp), L.stream()), 'match_events')
+    return tp

@@ -165,17 +165,17 @@ class VideoInference:
     The reference slices a video into clips that overlap by 75 % (dataset/frame.py:409-423) and runs each clip through the
     whole network (util/eval.py:289-349), so stem + s1 + s2 — which see one frame at a time; the first cross-frame
     operator is the GatedShift of s3.b1 (model/shift.py:47-59) — process every frame four times and every frame crosses
-    PCIe four times.  Here the frames of all videos form ONE stream: chunks of `frames_per_chunk` unique frames are
-    uploaded once, run through InferenceEngine.lower() once (twice with the flipped TTA view) and filed into a ring of
-    per-frame features in HBM; clip batches are gathered from the ring (tdeed_gather_rows) and finished by upper() +
-    temporal() + heads().  Frames before 0 / past the end of a video read the features of the all-zero frame, exactly what
-    the reference's zero padding (dataset/frame.py:622-625) produces.  Results are bit-identical to per-clip execution
-    (tests/test_gpu_video.py): no kernel of the lower part mixes frames, and clip order == accumulation order.
+    PCIe four times.  Here the frames of all videos form ONE stream: unique frames are uploaded once into one of two
+    `frames_per_chunk`-frame device buffers (side stream, overlapping the kernels of the previous chunk), run through
+    InferenceEngine.lower() once (twice with the flipped TTA view) and filed into a ring of per-frame features in HBM; clip
+    batches are gathered from the ring (tdeed_gather_rows) and finished by upper() + temporal() + heads().  Frames before 0 /
+    past the end of a video read the features of the all-zero frame, exactly what the reference's zero padding
+    (dataset/frame.py:622-625) produces.  Results are bit-identical to per-clip execution (tests/test_gpu_video.py): no
+    kernel of the lower part mixes frames, and clip order == accumulation order.
 
         vi = VideoInference(engine, in_hw=(224, 398), clips_per_batch=57, frames_per_chunk=1425, flips=(False,))
-        scores = vi.run(videos, chunks)   # videos: [(name, video_len, [clip starts])]; chunks: iterator of pinned uint8
-                                          # (n, 3, H, W) host tensors = the videos' frames back to back, n == frames_per_chunk
-                                          # for every chunk but the last
+        scores = vi.run(videos, pieces)   # videos: [(name, video_len, [clip starts])]; pieces: iterator of pinned uint8
+                                          # (n, 3, H, W) host tensors (any n) = the videos' frames back to back
     """
 
     def __init__(self, engine, in_hw, clips_per_batch=57, frames_per_chunk=None, flips=(False,), clip_len=None,
@@ -192,44 +192,90 @@ class VideoInference:
         # only the window the network's center crop keeps crosses PCIe (strided 2D DMA); rows must stay whole for that
         self.upload_crop = (cy, cx, ch, cw) if (upload_crop and ch == in_h and cw != in_w) else None
         self.dev_crop = (0, 0, ch, cw) if self.upload_crop else (cy, cx, ch, cw)
-        self.uploader = ClipUploader((self.N, 3, in_h, in_w), self.dev, crop=self.upload_crop)
         self.in_hw = (in_h, in_w)
+        self.dev_hw = (ch, cw) if self.upload_crop else (in_h, in_w)
         self.W_slots = self.B * self.T + 2 * self.N
         self.ring = None            # per flip: (W_slots, h, w, c)
         self.pad = None             # per flip: (h, w, c) features of the all-zero frame
+        self.stream = torch.cuda.Stream(device=self.dev)
+        self.bufs = [torch.zeros((self.N, 3) + self.dev_hw, dtype=torch.uint8, device=self.dev) for _ in range(2)]
+        self.ready = [torch.cuda.Event() for _ in range(2)]
+        self.free = [torch.cuda.Event() for _ in range(2)]
+        self._used = [False, False]
+        self._k, self._fill = 0, 0
+        self._inflight = []         # (event, host pieces): keeps pinned pieces alive until their (raw 2D) DMA has run
+        self._pieces = []
         self._iota = torch.arange(self.N, dtype=torch.int32, device=self.dev)
         self.h2d_bytes = 0
-        self.frames_in = 0
+        self.frames_in = 0          # frames whose features are in the ring (global stream index of the next one)
         self.clips_out = 0
 
     def _prepare(self):
-        if self.ring is not None:
-            return
         eng = self.eng
-        hw = self.dev_crop[2:] if self.upload_crop else self.in_hw
-        black = torch.zeros((1, 3) + tuple(hw), dtype=torch.uint8, device=self.dev)
-        self.ring, self.pad, self.xg = [], [], []
-        for flip in self.flips:
-            f = eng.lower(black, flip=flip, crop=self.dev_crop)[0].clone()
-            self.pad.append(f)
-            self.ring.append(torch.empty((self.W_slots,) + tuple(f.shape), dtype=f.dtype, device=self.dev))
-            self.xg.append(torch.empty((self.B * self.T,) + tuple(f.shape), dtype=f.dtype, device=self.dev))
+        if self.ring is not None and self._version == eng.version:
+            return
+        black = torch.zeros((1, 3) + self.dev_hw, dtype=torch.uint8, device=self.dev)
+        pad = [eng.lower(black, flip=flip, crop=self.dev_crop)[0].clone() for flip in self.flips]
+        if self.ring is None:
+            self.ring = [torch.empty((self.W_slots,) + tuple(f.shape), dtype=f.dtype, device=self.dev) for f in pad]
+            self.xg = [torch.empty((self.B * self.T,) + tuple(f.shape), dtype=f.dtype, device=self.dev) for f in pad]
+            self.pad = pad
+        else:                       # new weights (engine.load_state): same buffers (graphs may be keyed on them), new contents
+            for dst, f in zip(self.pad, pad):
+                dst.copy_(f)
+        self._version = eng.version
 
-    def _push(self, host_chunk, g0):
-        """Upload one chunk of unique frames (global indices g0 ..) and file its features into the ring(s)."""
-        n = host_chunk.shape[0]
-        x = self.uploader.upload(host_chunk)
-        buf = self.uploader.bufs[self.uploader._k]          # full static buffer: the graph always runs N frames
-        self.h2d_bytes += n * 3 * x.shape[-2] * x.shape[-1]
+    def _feed(self, piece):
+        """Queue the H2D copy of a pinned host piece (n,3,H,W) into the filling device buffer; flush full buffers."""
+        assert piece.dtype == torch.uint8 and piece.dim() == 4 and tuple(piece.shape[-2:]) == self.in_hw, \
+            'expected uint8 (n,3,%d,%d) frames, got %s %s' % (self.in_hw + (piece.dtype, tuple(piece.shape)))
+        if not piece.is_pinned():
+            piece = piece.contiguous().pin_memory()
+        off, n = 0, piece.shape[0]
+        while off < n:
+            take = min(self.N - self._fill, n - off)
+            k = self._k
+            with torch.cuda.stream(self.stream):
+                if self._fill == 0 and self._used[k]:
+                    self.stream.wait_event(self.free[k])          # the kernels that read this buffer two chunks ago are done
+                dst = self.bufs[k][self._fill:self._fill + take]
+                src = piece[off:off + take]
+                if self.upload_crop is None:
+                    dst.copy_(src, non_blocking=True)
+                else:
+                    _, x0, h, w = self.upload_crop
+                    in_h, in_w = self.in_hw
+                    _memcpy2d_async(dst.data_ptr(), w, src.data_ptr() + x0, in_w, w, take * 3 * in_h, self.stream.cuda_stream)
+            self.h2d_bytes += take * 3 * self.dev_hw[0] * self.dev_hw[1]
+            self._fill += take
+            off += take
+            self._pieces.append(piece)
+            if self._fill == self.N:
+                self._flush()
+
+    def _flush(self):
+        """Run lower() on the filling buffer (the graph always processes N frames; stale tail rows are ignored) and file
+        the features of its `_fill` valid frames into the ring(s)."""
+        n, k = self._fill, self._k
+        if n == 0:
+            return
+        self.ready[k].record(self.stream)
+        self._inflight = [(e, p) for e, p in self._inflight if not e.query()]
+        self._inflight.append((self.ready[k], self._pieces))
+        self._pieces = []
+        torch.cuda.current_stream().wait_event(self.ready[k])
+        g0 = self.frames_in
         slots = torch.as_tensor((np.arange(g0, g0 + n) % self.W_slots).astype(np.int32)).pin_memory().to(self.dev, non_blocking=True)
         for fi, flip in enumerate(self.flips):
-            feat = self.eng.lower_graphed(buf, flip=flip, crop=self.dev_crop)
+            feat = self.eng.lower_graphed(self.bufs[k], flip=flip, crop=self.dev_crop)
             ops.gather_rows(feat, self._iota[:n], self.ring[fi], dst_idx=slots)
-        self.uploader.release()
+        self.free[k].record(torch.cuda.current_stream())
+        self._used[k] = True
+        self._k, self._fill = k ^ 1, 0
         self.frames_in += n
 
     def run(self, videos, chunks, on_video=None):
-        """videos: [(name, video_len, starts)] in stream order; chunks: iterator of pinned uint8 (n,3,H,W) host tensors.
+        """videos: [(name, video_len, starts)] in stream order; chunks: iterator of pinned uint8 (n,3,H,W) host pieces.
         Returns {name: VideoScores}.  on_video(name, VideoScores) is called as soon as a video's last clip has been
         accumulated (lets the caller start event extraction / D2H while later videos still compute)."""
         self._prepare()
@@ -246,7 +292,7 @@ class VideoInference:
             last_clip[name] = ci
         scores = {name: VideoScores(vlen, K, self.dev) for name, vlen, _ in videos}
         chunks = iter(chunks)
-        pushed = 0
+        self.frames_in, self._fill = 0, 0
         for lo in range(0, len(clips), B):
             batch = clips[lo:lo + B]
             need = 0
@@ -257,10 +303,14 @@ class VideoInference:
                 idx[bi, ok] = (base[name] + f[ok]) % self.W_slots
                 if ok.any():
                     need = max(need, base[name] + int(f[ok].max()) + 1)
-            while pushed < min(need, total_frames):
-                chunk = next(chunks)
-                self._push(chunk, pushed)
-                pushed += chunk.shape[0]
+            while self.frames_in < min(need, total_frames):
+                piece = next(chunks, None)
+                if piece is not None:
+                    self._feed(piece)
+                elif self._fill:
+                    self._flush()                # end of the stream: ragged last chunk
+                else:
+                    raise RuntimeError('frame stream ended after %d frames; the clip list needs %d' % (self.frames_in, need))
             idx_dev = torch.as_tensor(idx.reshape(-1)).pin_memory().to(self.dev, non_blocking=True)
             outs = []
             for fi in range(len(self.flips)):

@@ -82,7 +82,7 @@ def test_video_inference_is_bit_identical_to_per_clip(dev, arch, precision, tta,
         assert torch.equal(got[name].support, ref.support), name
         assert torch.equal(got[name].scores, ref.scores), '%s: max diff %g' % (name, float((got[name].scores - ref.scores).abs().max()))
     # and a second run over the same engine (graphs replayed, ring reused) reproduces it
-    again = vi.run(videos, _chunks(vids, 20))
+    again = vi.run(videos, _chunks(vids, 7))          # pieces that straddle the device buffers
     for name, _, _ in videos:
         assert torch.equal(again[name].scores, got[name].scores)
 
