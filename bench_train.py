@@ -257,7 +257,9 @@ def run_train(args, quiet=False):
         # algorithmic work of the families that can dominate (FineGym_big, per step of CLIPS_PER_GPU clips):
         #   conv outputs of the backbone: 5.24 M elements per frame (every BatchNorm'd tensor)
         elems = 5.24e6 * 100 * CLIPS_PER_GPU
-        alg_bytes = {'bn_act_bwd': elems * 2 * (2 * 2 + 1 + 0.3 * 2), 'bn_act_fwd': elems * 2 * 2.3, 'bn_stats': elems * 2}
+        # COMPULSORY bytes: bn_act_bwd reads dy and y once and writes dx (+ the 0.3 share of tensors that also emit a
+        # residual gradient); the implementation's second pass over dy / y is traffic, not algorithm
+        alg_bytes = {'bn_act_bwd': elems * 2 * (3 + 0.3), 'bn_act_fwd': elems * 2 * 2.3, 'bn_stats': elems * 2}
         alg_flops = {'gemm_tn': 2 * 0.5 * (126.05e9 + 6.38e9) * CLIPS_PER_GPU, 'gemm': 2 * (126.05e9 + 6.38e9) * CLIPS_PER_GPU}
         if top in alg_flops:
             roofline = {'kernel': top, 'bound': 'tensor', 'achieved': alg_flops[top] / sec / 1e12, 'peak': pk['tf'], 'unit': 'TFLOP/s'}
@@ -288,6 +290,17 @@ def run_train(args, quiet=False):
             'final_loss': float(loss),
             'kernel_families_ms_per_step': {k_: round(v['ms'], 3) for k_, v in sorted(families.items(), key=lambda kv: -kv[1]['ms'])},
         }
+        if world == 1 and not getattr(args, 'no_ref_gpu', False):
+            # stock-torch training step of the same network on the same GPU (cuDNN / cuBLAS + autograd), see bench_ref_gpu.py
+            try:
+                import bench_ref_gpu
+                sd = {k_: v.detach() for k_, v in model.state_dict().items()}
+                del dev_batch
+                model._model._train_graphs.clear()
+                torch.cuda.empty_cache()
+                out['ref_gpu'] = {'train': bench_ref_gpu.run_train(TRAIN_CONFIG['name'], sd, dev, clips=CLIPS_PER_GPU)}
+            except Exception as exc:
+                out['ref_gpu'] = {'error': repr(exc)[:300]}
         if not quiet:
             print(json.dumps(out))
     return out

@@ -209,6 +209,8 @@ class VideoInference:
         self.h2d_bytes = 0
         self.frames_in = 0          # frames whose features are in the ring (global stream index of the next one)
         self.clips_out = 0
+        self.use_graphs = True      # False: launch lower / upper eagerly (per-kernel profiling with engine.prof)
+        self.launches = 0           # kernels launched outside the engine (gather / accumulate)
 
     def _prepare(self):
         eng = self.eng
@@ -229,7 +231,7 @@ class VideoInference:
         """Queue the H2D copy of a pinned host piece (n,3,H,W) into the filling device buffer; flush full buffers."""
         assert piece.dtype == torch.uint8 and piece.dim() == 4 and tuple(piece.shape[-2:]) == self.in_hw, \
             'expected uint8 (n,3,%d,%d) frames, got %s %s' % (self.in_hw + (piece.dtype, tuple(piece.shape)))
-        if not piece.is_pinned():
+        if not piece.is_cuda and not piece.is_pinned():
             piece = piece.contiguous().pin_memory()
         off, n = 0, piece.shape[0]
         while off < n:
@@ -240,13 +242,20 @@ class VideoInference:
                     self.stream.wait_event(self.free[k])          # the kernels that read this buffer two chunks ago are done
                 dst = self.bufs[k][self._fill:self._fill + take]
                 src = piece[off:off + take]
-                if self.upload_crop is None:
+                if piece.is_cuda:                                  # frames already resident in HBM (bench `value` arm)
+                    self.stream.wait_stream(torch.cuda.current_stream())
+                    if self.upload_crop is None:
+                        dst.copy_(src)
+                    else:
+                        dst.copy_(src[..., self.upload_crop[1]:self.upload_crop[1] + self.upload_crop[3]])
+                elif self.upload_crop is None:
                     dst.copy_(src, non_blocking=True)
                 else:
                     _, x0, h, w = self.upload_crop
                     in_h, in_w = self.in_hw
                     _memcpy2d_async(dst.data_ptr(), w, src.data_ptr() + x0, in_w, w, take * 3 * in_h, self.stream.cuda_stream)
-            self.h2d_bytes += take * 3 * self.dev_hw[0] * self.dev_hw[1]
+            if not piece.is_cuda:
+                self.h2d_bytes += take * 3 * self.dev_hw[0] * self.dev_hw[1]
             self._fill += take
             off += take
             self._pieces.append(piece)
@@ -267,8 +276,10 @@ class VideoInference:
         g0 = self.frames_in
         slots = torch.as_tensor((np.arange(g0, g0 + n) % self.W_slots).astype(np.int32)).pin_memory().to(self.dev, non_blocking=True)
         for fi, flip in enumerate(self.flips):
-            feat = self.eng.lower_graphed(self.bufs[k], flip=flip, crop=self.dev_crop)
+            lower = self.eng.lower_graphed if self.use_graphs else self.eng.lower
+            feat = lower(self.bufs[k], flip=flip, crop=self.dev_crop)
             ops.gather_rows(feat, self._iota[:n], self.ring[fi], dst_idx=slots)
+            self.launches += 1
         self.free[k].record(torch.cuda.current_stream())
         self._used[k] = True
         self._k, self._fill = k ^ 1, 0
@@ -315,8 +326,12 @@ class VideoInference:
             outs = []
             for fi in range(len(self.flips)):
                 ops.gather_rows(self.ring[fi], idx_dev, self.xg[fi], pad_row=self.pad[fi])
-                _, _, probs = eng.upper_graphed(self.xg[fi], B, T)
+                if self.use_graphs:
+                    _, _, probs = eng.upper_graphed(self.xg[fi], B, T)
+                else:
+                    _, _, probs = eng.heads(eng.temporal(eng.upper(self.xg[fi], B, T).view(B, T, eng.cfg.feat_dim)))
                 outs.append(probs)
+                self.launches += 1
             nb = len(batch)
             if tta:     # the reference adds plain then flipped view clip by clip (util/eval.py:321-349): keep that order
                 probs = torch.stack(outs, dim=1)[:nb].reshape(nb * len(outs), T, K)
@@ -331,6 +346,7 @@ class VideoInference:
                     bj += 1
                 st = [batch[i][2] for i in range(bi, bj) for _ in range(rep)]
                 scores[name].add(probs[bi * rep:bj * rep], st, tta=tta)
+                self.launches += 1
                 if on_video is not None and last_clip[name] == lo + bj - 1:
                     on_video(name, scores[name])
                 bi = bj
