@@ -202,6 +202,10 @@ int tdeed_softmax_scatter_fwd(const float* logits, int ld_logits, const float* d
  *   TTA path]; rows before frame 0 / past video_len are dropped.  pred fp32 [n_clips, T, K]; starts i32. */
 int tdeed_clip_accumulate(float* scores, int* support, int video_len, int K,
                           const float* pred, const int* starts, int n_clips, int T, int mode, void* stream);
+/* same with the clip starts given as a HOST array (n_clips <= TDEED_MAX_STARTS_PER_CALL; passed to the kernel by value) */
+#define TDEED_MAX_STARTS_PER_CALL 256
+int tdeed_clip_accumulate_host(float* scores, int* support, int video_len, int K,
+                               const float* pred, const int* starts_host, int n_clips, int T, int mode, void* stream);
 
 /* extract (util/eval.py:87-193): support==0 -> 1; scores /= support; pred = argmax; events = frames with
  * pred != 0; high-recall events = every (frame, class>=1) with score >= threshold (fp32 compare),
@@ -236,6 +240,18 @@ int tdeed_nms(const int* frame, const int* label, const float* score, const int*
  * (dataset/frame.py:622-625); pad_row may be NULL when no index is negative. */
 int tdeed_gather_rows(const void* src, const void* pad_row, void* dst, const int* src_idx, const int* dst_idx,
                       int n_rows, long long row_bytes, void* stream);
+/* (12b) the two steady-state maps of the video engine without index tensors (the integers travel as kernel parameters,
+ * so no small host->device copy competes with the frame uploads for the DMA engine):
+ *   scatter_rows_ring:  ring[(first_slot + i) % ring_slots] = src[i]                                   i in [0, n_rows)
+ *   gather_clip_rows:   dst[b*T + t] = (lo[b] <= t < hi[b]) ? ring[(first_slot[b] + t) % ring_slots] : pad_row
+ *                       — clip b of T frames whose frame 0 sits in ring slot first_slot[b]; frames outside [lo, hi) lie before
+ *                       frame 0 / past the end of the video (dataset/frame.py:412-423,622-625: zero padding).
+ * *_host arrays are HOST pointers with n_clips <= TDEED_MAX_CLIPS_PER_CALL entries. */
+#define TDEED_MAX_CLIPS_PER_CALL 128
+int tdeed_scatter_rows_ring(const void* src, void* ring, int n_rows, int first_slot, int ring_slots, long long row_bytes,
+                            void* stream);
+int tdeed_gather_clip_rows(const void* ring, const void* pad_row, void* dst, int n_clips, int T, const int* first_slot_host,
+                           const int* lo_host, const int* hi_host, int ring_slots, long long row_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (13) greedy prediction <-> ground-truth matching of the mAP scorer (util/score.py:45-89,

@@ -25,7 +25,91 @@ gather_rows_kernel(const uint4* __restrict__ src, const uint4* __restrict__ pad_
   for (long long v = lo + threadIdx.x; v < hi; v += GR_THREADS) to[v] = __ldg(from + v);
 }
 
+// Index-free variants for the steady state of the video engine: the maps are a few hundred integers, passed BY VALUE as kernel
+// parameters.  An index tensor would need its own small host->device copy per launch, and those copies queue on the same DMA
+// engine as the multi-hundred-MB frame uploads of the side stream — measured (tools/e2e_diag.py): 7.5 ms of idle GPU per
+// 58 ms video in the end-to-end arm, none in the device-resident arm.
+struct ClipMap {
+  int first[TDEED_MAX_CLIPS_PER_CALL];     // ring slot of the clip's frame t = 0 (already reduced mod ring_slots, >= 0)
+  short lo[TDEED_MAX_CLIPS_PER_CALL];      // frames t in [lo, hi) exist in the video; the others are padding
+  short hi[TDEED_MAX_CLIPS_PER_CALL];
+};
+
+__global__ void __launch_bounds__(GR_THREADS)
+gather_clip_rows_kernel(const uint4* __restrict__ ring, const uint4* __restrict__ pad_row, uint4* __restrict__ dst, const ClipMap m,
+                        int T, int ring_slots, long long row_vec, int slices) {
+  const int i = blockIdx.x;
+  const int b = i / T, t = i - b * T;
+  const bool valid = t >= m.lo[b] && t < m.hi[b];
+  const uint4* from = valid ? ring + (long long)((m.first[b] + t) % ring_slots) * row_vec : pad_row;
+  uint4* to = dst + (long long)i * row_vec;
+  const long long per = ceil_div_ll(row_vec, slices);
+  const long long lo = per * blockIdx.y, hi = lo + per < row_vec ? lo + per : row_vec;
+  for (long long v = lo + threadIdx.x; v < hi; v += GR_THREADS) to[v] = __ldg(from + v);
+}
+
+__global__ void __launch_bounds__(GR_THREADS)
+scatter_rows_ring_kernel(const uint4* __restrict__ src, uint4* __restrict__ ring, int first_slot, int ring_slots, long long row_vec,
+                         int slices) {
+  const long long i = blockIdx.x;
+  const uint4* from = src + i * row_vec;
+  uint4* to = ring + (long long)((first_slot + i) % ring_slots) * row_vec;
+  const long long per = ceil_div_ll(row_vec, slices);
+  const long long lo = per * blockIdx.y, hi = lo + per < row_vec ? lo + per : row_vec;
+  for (long long v = lo + threadIdx.x; v < hi; v += GR_THREADS) to[v] = __ldg(from + v);
+}
+
+static int row_slices(long long row_vec, int n_rows) {
+  // enough CTAs to fill the machine even for a handful of rows: slices of >= 4 KB
+  long long slices = ceil_div_ll(row_vec, 256);
+  const long long want = ceil_div_ll(4LL * kNumSMs, n_rows);
+  if (slices > want) slices = want < 1 ? 1 : want;
+  if (slices > 65535) slices = 65535;
+  return (int)slices;
+}
+
 }  // namespace tdeed
+
+extern "C" int tdeed_gather_clip_rows(const void* ring, const void* pad_row, void* dst, int n_clips, int T, const int* first_slot_host,
+                                      const int* lo_host, const int* hi_host, int ring_slots, long long row_bytes, void* stream) {
+  using namespace tdeed;
+  TDEED_REQUIRE(ring && pad_row && dst && first_slot_host && lo_host && hi_host, TDEED_ERR_SHAPE, "tdeed_gather_clip_rows: null pointer");
+  TDEED_REQUIRE(n_clips > 0 && n_clips <= TDEED_MAX_CLIPS_PER_CALL && T > 0 && T < 32768 && ring_slots > 0 && row_bytes > 0 &&
+                row_bytes % 16 == 0, TDEED_ERR_SHAPE, "tdeed_gather_clip_rows: n_clips=%d (max %d) T=%d ring_slots=%d row_bytes=%lld",
+                n_clips, TDEED_MAX_CLIPS_PER_CALL, T, ring_slots, row_bytes);
+  TDEED_REQUIRE(((uintptr_t)ring | (uintptr_t)dst | (uintptr_t)pad_row) % 16 == 0, TDEED_ERR_SHAPE,
+                "tdeed_gather_clip_rows: pointers must be 16-byte aligned");
+  ClipMap m;
+  for (int b = 0; b < n_clips; ++b) {
+    TDEED_REQUIRE(first_slot_host[b] >= 0 && first_slot_host[b] < ring_slots && lo_host[b] >= 0 && hi_host[b] <= T, TDEED_ERR_SHAPE,
+                  "tdeed_gather_clip_rows: clip %d: first_slot=%d lo=%d hi=%d", b, first_slot_host[b], lo_host[b], hi_host[b]);
+    m.first[b] = first_slot_host[b];
+    m.lo[b] = (short)lo_host[b];
+    m.hi[b] = (short)hi_host[b];
+  }
+  const long long row_vec = row_bytes / 16;
+  const int slices = row_slices(row_vec, n_clips * T);
+  dim3 grid((unsigned)(n_clips * T), (unsigned)slices);
+  gather_clip_rows_kernel<<<grid, GR_THREADS, 0, (cudaStream_t)stream>>>((const uint4*)ring, (const uint4*)pad_row, (uint4*)dst, m, T,
+                                                                          ring_slots, row_vec, slices);
+  return check_launch("tdeed_gather_clip_rows");
+}
+
+extern "C" int tdeed_scatter_rows_ring(const void* src, void* ring, int n_rows, int first_slot, int ring_slots, long long row_bytes,
+                                       void* stream) {
+  using namespace tdeed;
+  TDEED_REQUIRE(src && ring, TDEED_ERR_SHAPE, "tdeed_scatter_rows_ring: null pointer");
+  TDEED_REQUIRE(n_rows > 0 && n_rows <= ring_slots && first_slot >= 0 && first_slot < ring_slots && row_bytes > 0 && row_bytes % 16 == 0,
+                TDEED_ERR_SHAPE, "tdeed_scatter_rows_ring: n_rows=%d first_slot=%d ring_slots=%d row_bytes=%lld", n_rows, first_slot,
+                ring_slots, row_bytes);
+  TDEED_REQUIRE(((uintptr_t)src | (uintptr_t)ring) % 16 == 0, TDEED_ERR_SHAPE, "tdeed_scatter_rows_ring: pointers must be 16-byte aligned");
+  const long long row_vec = row_bytes / 16;
+  const int slices = row_slices(row_vec, n_rows);
+  dim3 grid((unsigned)n_rows, (unsigned)slices);
+  scatter_rows_ring_kernel<<<grid, GR_THREADS, 0, (cudaStream_t)stream>>>((const uint4*)src, (uint4*)ring, first_slot, ring_slots,
+                                                                           row_vec, slices);
+  return check_launch("tdeed_scatter_rows_ring");
+}
 
 extern "C" int tdeed_gather_rows(const void* src, const void* pad_row, void* dst, const int* src_idx, const int* dst_idx,
                                  int n_rows, long long row_bytes, void* stream) {
@@ -36,13 +120,9 @@ extern "C" int tdeed_gather_rows(const void* src, const void* pad_row, void* dst
   TDEED_REQUIRE(((uintptr_t)src | (uintptr_t)dst | (uintptr_t)pad_row) % 16 == 0, TDEED_ERR_SHAPE,
                 "tdeed_gather_rows: pointers must be 16-byte aligned");
   const long long row_vec = row_bytes / 16;
-  // enough CTAs to fill the machine even for a handful of rows: slices of >= 4 KB
-  long long slices = ceil_div_ll(row_vec, 256);
-  const long long want = ceil_div_ll(4LL * kNumSMs, n_rows);
-  if (slices > want) slices = want < 1 ? 1 : want;
-  if (slices > 65535) slices = 65535;
+  const int slices = row_slices(row_vec, n_rows);
   dim3 grid((unsigned)n_rows, (unsigned)slices);
   gather_rows_kernel<<<grid, GR_THREADS, 0, (cudaStream_t)stream>>>((const uint4*)src, (const uint4*)pad_row, (uint4*)dst, src_idx,
-                                                                     dst_idx, row_vec, (int)slices);
+                                                                     dst_idx, row_vec, slices);
   return check_launch("tdeed_gather_rows");
 }

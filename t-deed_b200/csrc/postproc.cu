@@ -52,6 +52,32 @@ clip_accumulate_kernel(float* __restrict__ scores, int* __restrict__ support, in
   }
 }
 
+// same, with the clip starts passed by value (no index upload: see csrc/frames.cu)
+struct ClipStarts { int v[TDEED_MAX_STARTS_PER_CALL]; };
+
+__global__ void __launch_bounds__(256)
+clip_accumulate_hs_kernel(float* __restrict__ scores, int* __restrict__ support, int video_len, int K,
+                          const float* __restrict__ pred, const ClipStarts starts, int n_clips, int T, int mode) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)video_len * K) return;
+  const int l = (int)(idx / K), k = (int)(idx - (long long)l * K);
+  float s = scores[idx];
+  int sup = 0;
+  bool touched = false;
+  for (int i = 0; i < n_clips; ++i) {          // clip order == the reference's `+=` order
+    const int t = l - starts.v[i];
+    if (t < 0 || t >= T) continue;
+    const float* row = pred + ((size_t)i * T + t) * K;
+    s = __fadd_rn(s, row[k]);
+    touched = true;
+    if (k == 0) sup += (mode == 0) ? (numpy_rowsum(row, K) != 0.f ? 1 : 0) : 1;
+  }
+  if (touched) {
+    scores[idx] = s;
+    if (k == 0 && sup) support[l] += sup;
+  }
+}
+
 // ---- extraction: one CTA per video, frames processed in order in chunks of blockDim ----
 constexpr int EX_THREADS = 1024;
 
@@ -340,6 +366,21 @@ extern "C" int tdeed_clip_accumulate(float* scores, int* support, int video_len,
   clip_accumulate_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(scores, support, video_len, K, pred,
                                                                                              starts, n_clips, T, mode);
   return check_launch("tdeed_clip_accumulate");
+}
+
+extern "C" int tdeed_clip_accumulate_host(float* scores, int* support, int video_len, int K, const float* pred,
+                                          const int* starts_host, int n_clips, int T, int mode, void* stream) {
+  using namespace tdeed;
+  TDEED_REQUIRE(scores && support && pred && starts_host, TDEED_ERR_SHAPE, "tdeed_clip_accumulate_host: null pointer");
+  TDEED_REQUIRE(video_len > 0 && K > 0 && K < 128 && n_clips > 0 && n_clips <= TDEED_MAX_STARTS_PER_CALL && T > 0 &&
+                (mode == 0 || mode == 1), TDEED_ERR_SHAPE, "tdeed_clip_accumulate_host: bad shape L=%d K=%d clips=%d (max %d) T=%d mode=%d",
+                video_len, K, n_clips, TDEED_MAX_STARTS_PER_CALL, T, mode);
+  ClipStarts st;
+  for (int i = 0; i < n_clips; ++i) st.v[i] = starts_host[i];
+  const long long total = (long long)video_len * K;
+  clip_accumulate_hs_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(scores, support, video_len, K, pred,
+                                                                                                st, n_clips, T, mode);
+  return check_launch("tdeed_clip_accumulate_host");
 }
 
 extern "C" int tdeed_extract_events(float* scores, int* support, int video_len, int K, float threshold, int* pred,

@@ -16,6 +16,8 @@ ACT_NONE, ACT_RELU, ACT_GELU = 0, 1, 2
 SHIFT_GSM, SHIFT_GSF = 0, 1
 GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05, GEMM_TCGEN05_THIN = 0, 1, 2, 3
 GEMM_MAX_SEGS = 2
+MAX_CLIPS_PER_CALL = 128
+MAX_STARTS_PER_CALL = 256
 
 c_int, c_ll, c_float, c_double, c_vp = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_double, ctypes.c_void_p
 
@@ -73,6 +75,10 @@ SIGNATURES = {
     'tdeed_nms': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_double, c_int, c_vp, c_vp, c_vp, c_vp,
                           c_vp, c_vp]),
     'tdeed_gather_rows': (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_ll, c_vp]),
+    'tdeed_scatter_rows_ring': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_ll, c_vp]),
+    'tdeed_gather_clip_rows': (c_int, [c_vp, c_vp, c_vp, c_int, c_int, ctypes.POINTER(c_int), ctypes.POINTER(c_int),
+                                       ctypes.POINTER(c_int), c_int, c_ll, c_vp]),
+    'tdeed_clip_accumulate_host': (c_int, [c_vp, c_vp, c_int, c_int, c_vp, ctypes.POINTER(c_int), c_int, c_int, c_int, c_vp]),
     'tdeed_match_events': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_vp, c_vp, c_vp]),
 }
 

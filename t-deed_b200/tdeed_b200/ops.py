@@ -218,10 +218,20 @@ def softmax_scatter(logits, displ, k_softmax):
 
 
 def clip_accumulate(scores, support, pred, starts, mode):
+    """starts: int32 device tensor, or a host sequence of ints (<= MAX_STARTS_PER_CALL: passed by value, no upload)."""
     video_len, k = scores.shape
     n_clips, t, _ = pred.shape
-    L.check(L.load().tdeed_clip_accumulate(L.ptr(scores), L.ptr(support), video_len, k, L.ptr(pred), L.ptr(starts),
-                                           n_clips, t, mode, L.stream()), 'clip_accumulate')
+    if isinstance(starts, torch.Tensor):
+        L.check(L.load().tdeed_clip_accumulate(L.ptr(scores), L.ptr(support), video_len, k, L.ptr(pred), L.ptr(starts),
+                                               n_clips, t, mode, L.stream()), 'clip_accumulate')
+        return
+    starts = [int(s) for s in starts]
+    assert len(starts) == n_clips
+    for lo in range(0, n_clips, L.MAX_STARTS_PER_CALL):            # chunks run in order: same accumulation order
+        part = starts[lo:lo + L.MAX_STARTS_PER_CALL]
+        arr = (ctypes.c_int * len(part))(*part)
+        L.check(L.load().tdeed_clip_accumulate_host(L.ptr(scores), L.ptr(support), video_len, k, L.ptr(pred[lo:lo + len(part)]), arr,
+                                                    len(part), t, mode, L.stream()), 'clip_accumulate_host')
 
 
 def extract_events(scores, support, threshold):
@@ -284,3 +294,25 @@ def match_events(pred_frame, pred_off, gt_frame, gt_off, tolerances, total_pred=
         L.check(L.load().tdeed_match_events(L.ptr(pred_frame), L.ptr(pred_off), L.ptr(gt_frame), L.ptr(gt_off), n_units, total_pred,
                                             total_gt, L.ptr(tolerances), n_tol, L.ptr(ws), L.ptr(tp), L.stream()), 'match_events')
     return tp
+
+
+def scatter_rows_ring(src, n_rows, ring, first_slot):
+    """ring[(first_slot + i) % len(ring)] = src[i] for i < n_rows (frame-feature ring of the video engine)."""
+    row_bytes = src[0].numel() * src.element_size()
+    assert ring[0].numel() * ring.element_size() == row_bytes and src.is_contiguous() and ring.is_contiguous()
+    L.check(L.load().tdeed_scatter_rows_ring(L.ptr(src), L.ptr(ring), n_rows, int(first_slot), ring.shape[0], row_bytes, L.stream()),
+            'scatter_rows_ring')
+
+
+def gather_clip_rows(ring, pad_row, dst, clip_len, first_slots, los, his):
+    """dst[b*T + t] = ring[(first_slots[b] + t) % len(ring)] if los[b] <= t < his[b] else pad_row; host int sequences."""
+    n = len(first_slots)
+    row_bytes = ring[0].numel() * ring.element_size()
+    assert dst[0].numel() * dst.element_size() == row_bytes and dst.shape[0] >= n * clip_len and dst.is_contiguous()
+    for lo in range(0, n, L.MAX_CLIPS_PER_CALL):
+        m = min(L.MAX_CLIPS_PER_CALL, n - lo)
+        a = (ctypes.c_int * m)(*[int(v) for v in first_slots[lo:lo + m]])
+        b = (ctypes.c_int * m)(*[int(v) for v in los[lo:lo + m]])
+        c = (ctypes.c_int * m)(*[int(v) for v in his[lo:lo + m]])
+        L.check(L.load().tdeed_gather_clip_rows(L.ptr(ring), L.ptr(pad_row), L.ptr(dst[lo * clip_len:]), m, clip_len, a, b, c,
+                                                ring.shape[0], row_bytes, L.stream()), 'gather_clip_rows')

@@ -23,8 +23,7 @@ class VideoScores:
     def add(self, probs, starts, tta=False):
         """probs (n_clips, T, K) fp32 device tensor; starts: list/array of clip start frames (already // stride).
         Clip order == the reference's accumulation order (bit-exact fp32 sums)."""
-        st = torch.as_tensor(np.asarray(starts, np.int32)).to(self.scores.device, non_blocking=True)
-        ops.clip_accumulate(self.scores, self.support, probs.contiguous(), st, 1 if tta else 0)
+        ops.clip_accumulate(self.scores, self.support, probs.contiguous(), [int(s) for s in starts], 1 if tta else 0)
 
     def events(self, threshold=0.01):
         """Normalise in place and extract events (util/eval.py:87-193).  Returns the device-side dict of
@@ -205,7 +204,6 @@ class VideoInference:
         self._k, self._fill = 0, 0
         self._inflight = []         # (event, host pieces): keeps pinned pieces alive until their (raw 2D) DMA has run
         self._pieces = []
-        self._iota = torch.arange(self.N, dtype=torch.int32, device=self.dev)
         self.h2d_bytes = 0
         self.frames_in = 0          # frames whose features are in the ring (global stream index of the next one)
         self.clips_out = 0
@@ -237,6 +235,11 @@ class VideoInference:
         while off < n:
             take = min(self.N - self._fill, n - off)
             k = self._k
+            if piece.is_cuda and self._fill == 0 and take == self.N and piece.is_contiguous():
+                # a whole chunk already resident in HBM: lower() reads it in place (its own crop window), no staging copy
+                self._flush(direct=piece[off:off + take])
+                off += take
+                continue
             with torch.cuda.stream(self.stream):
                 if self._fill == 0 and self._used[k]:
                     self.stream.wait_event(self.free[k])          # the kernels that read this buffer two chunks ago are done
@@ -262,27 +265,31 @@ class VideoInference:
             if self._fill == self.N:
                 self._flush()
 
-    def _flush(self):
+    def _flush(self, direct=None):
         """Run lower() on the filling buffer (the graph always processes N frames; stale tail rows are ignored) and file
-        the features of its `_fill` valid frames into the ring(s)."""
-        n, k = self._fill, self._k
+        the features of its `_fill` valid frames into the ring(s).  direct: a resident (N,3,H,W) device chunk to read in
+        place instead of the staging buffer."""
+        n, k = (self.N, None) if direct is not None else (self._fill, self._k)
         if n == 0:
             return
-        self.ready[k].record(self.stream)
-        self._inflight = [(e, p) for e, p in self._inflight if not e.query()]
-        self._inflight.append((self.ready[k], self._pieces))
-        self._pieces = []
-        torch.cuda.current_stream().wait_event(self.ready[k])
-        g0 = self.frames_in
-        slots = torch.as_tensor((np.arange(g0, g0 + n) % self.W_slots).astype(np.int32)).pin_memory().to(self.dev, non_blocking=True)
+        if direct is None:
+            self.ready[k].record(self.stream)
+            self._inflight = [(e, p) for e, p in self._inflight if not e.query()]
+            self._inflight.append((self.ready[k], self._pieces))
+            self._pieces = []
+            torch.cuda.current_stream().wait_event(self.ready[k])
+            src, crop = self.bufs[k], self.dev_crop
+        else:
+            src, crop = direct, self.eng.crop_window(*self.in_hw)
         for fi, flip in enumerate(self.flips):
             lower = self.eng.lower_graphed if self.use_graphs else self.eng.lower
-            feat = lower(self.bufs[k], flip=flip, crop=self.dev_crop)
-            ops.gather_rows(feat, self._iota[:n], self.ring[fi], dst_idx=slots)
+            feat = lower(src, flip=flip, crop=crop)
+            ops.scatter_rows_ring(feat, n, self.ring[fi], self.frames_in % self.W_slots)
             self.launches += 1
-        self.free[k].record(torch.cuda.current_stream())
-        self._used[k] = True
-        self._k, self._fill = k ^ 1, 0
+        if direct is None:
+            self.free[k].record(torch.cuda.current_stream())
+            self._used[k] = True
+            self._k, self._fill = k ^ 1, 0
         self.frames_in += n
 
     def run(self, videos, chunks, on_video=None):
@@ -307,13 +314,12 @@ class VideoInference:
         for lo in range(0, len(clips), B):
             batch = clips[lo:lo + B]
             need = 0
-            idx = np.full((B, T), -1, np.int32)
+            first, los, his = [0] * B, [0] * B, [0] * B        # clips beyond len(batch) (ragged last batch): all padding
             for bi, (name, vlen, s) in enumerate(batch):
-                f = np.arange(s, s + T)
-                ok = (f >= 0) & (f < vlen)
-                idx[bi, ok] = (base[name] + f[ok]) % self.W_slots
-                if ok.any():
-                    need = max(need, base[name] + int(f[ok].max()) + 1)
+                lo_t, hi_t = min(T, max(0, -s)), max(0, min(T, vlen - s))
+                if hi_t > lo_t:
+                    first[bi], los[bi], his[bi] = (base[name] + s) % self.W_slots, lo_t, hi_t
+                    need = max(need, base[name] + s + hi_t)
             while self.frames_in < min(need, total_frames):
                 piece = next(chunks, None)
                 if piece is not None:
@@ -322,10 +328,9 @@ class VideoInference:
                     self._flush()                # end of the stream: ragged last chunk
                 else:
                     raise RuntimeError('frame stream ended after %d frames; the clip list needs %d' % (self.frames_in, need))
-            idx_dev = torch.as_tensor(idx.reshape(-1)).pin_memory().to(self.dev, non_blocking=True)
             outs = []
             for fi in range(len(self.flips)):
-                ops.gather_rows(self.ring[fi], idx_dev, self.xg[fi], pad_row=self.pad[fi])
+                ops.gather_clip_rows(self.ring[fi], self.pad[fi], self.xg[fi], T, first, los, his)
                 if self.use_graphs:
                     _, _, probs = eng.upper_graphed(self.xg[fi], B, T)
                 else:
