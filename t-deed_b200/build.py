@@ -43,16 +43,18 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=True):
+def build(force=False, verbose=True, dev=False):
+    """dev=True adds -DTDEED_DEV_KNOBS: the TDEED_* environment switches of DESIGN.md 4c (never in the shipped library)."""
     if not force and not needs_build():
         return LIB
     nvcc = _nvcc()
+    flags = NVCC_FLAGS + (['-DTDEED_DEV_KNOBS'] if dev else [])
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
 
     def compile_one(src):
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + '.o')
-        cmd = [nvcc] + NVCC_FLAGS + ['-c', src, '-o', obj]
+        cmd = [nvcc] + flags + ['-c', src, '-o', obj]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError('nvcc failed for %s:\n%s\n%s' % (src, r.stdout, r.stderr))
@@ -70,4 +72,4 @@ def build(force=False, verbose=True):
 
 
 if __name__ == '__main__':
-    build(force='--force' in sys.argv)
+    build(force='--force' in sys.argv or '--dev' in sys.argv, dev='--dev' in sys.argv)

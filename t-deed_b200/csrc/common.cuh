@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/tdeed_b200.h"
 
@@ -30,6 +31,14 @@ inline int check_launch(const char* what) {
   } while (0)
 
 constexpr int kNumSMs = 148;
+
+// Development knobs (TDEED_* environment variables: A/B switches, tracing, timing experiments that skip work) exist only
+// in -DTDEED_DEV_KNOBS builds (`python t-deed_b200/build.py --dev`).  The release library never reads the environment.
+#ifdef TDEED_DEV_KNOBS
+inline const char* dev_env(const char* name) { return ::getenv(name); }
+#else
+inline const char* dev_env(const char*) { return nullptr; }
+#endif
 
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }

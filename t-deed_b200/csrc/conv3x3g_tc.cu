@@ -325,7 +325,7 @@ static int conv3x3g_tc_run(const void* in, int n, int h, int w, int c, int strid
   int max_pairs = (int)((200 * 1024 - 2 * (size_t)p.npos * p.nplanes * sizeof(int)) / per_pair);
   if (max_pairs > C3T_MAX_PAIRS) max_pairs = C3T_MAX_PAIRS;
   static int pairs_env = -1;
-  if (pairs_env < 0) { const char* e = getenv("TDEED_C3_MAX_PAIRS"); pairs_env = e ? atoi(e) : 0; }
+  if (pairs_env < 0) { const char* e = tdeed::dev_env("TDEED_C3_MAX_PAIRS"); pairs_env = e ? atoi(e) : 0; }
   if (pairs_env > 0 && max_pairs > pairs_env) max_pairs = pairs_env;
   TDEED_REQUIRE(max_pairs >= 1, TDEED_ERR_UNSUPPORTED, "tdeed_conv3x3g_tc_fwd: frame width %d too large for the staged window", w);
   const int nblk = ceil_div(p.pairs_total, max_pairs);

@@ -645,7 +645,7 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
 
   const size_t w_kb_stride = ((size_t)block_n * TC_BK * 2 + 1023) & ~(size_t)1023;
   static int wres_env = -2;
-  if (wres_env == -2) { const char* e = getenv("TDEED_GEMM_WRES"); wres_env = e ? atoi(e) : -1; }
+  if (wres_env == -2) { const char* e = tdeed::dev_env("TDEED_GEMM_WRES"); wres_env = e ? atoi(e) : -1; }
   // one n-tile: W <= 72 KB stays resident next to a deep ring.  Several n-tiles (s4-sized layers, W ~ 280 KB): every CTA keeps the
   // SLICE of its own n-tile (tile index % n_tiles is constant per CTA when the grid is a multiple of n_tiles) — up to 150 KB,
   // with a 3-stage A ring and direct (unstaged) stores; A is then read n_tiles times but W no longer once per M tile.
@@ -665,16 +665,16 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
   // residual (s3/s4 conv1: -10..-25 %) and to lose for thin rows or when the residual read already pulled the
   // row's lines into L1.
   static int dbg = -1;
-  if (dbg < 0) { const char* e = getenv("TDEED_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+  if (dbg < 0) { const char* e = tdeed::dev_env("TDEED_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
   p.debug = dbg;
   static int fast_env = -1;
-  if (fast_env < 0) { const char* e = getenv("TDEED_GEMM_FAST_EPI"); fast_env = e ? atoi(e) : 1; }
+  if (fast_env < 0) { const char* e = tdeed::dev_env("TDEED_GEMM_FAST_EPI"); fast_env = e ? atoi(e) : 1; }
   p.fast = (fast_env && dbg == 0 && out_dtype == TDEED_BF16 && (act == TDEED_ACT_NONE || act == TDEED_ACT_RELU) && block_n <= 256) ? 1 : 0;
   // With the specialised epilogue the direct row-piece stores win for one-n-tile and short-K layers (ncu per-launch times,
   // 57-clip batch: N = 152 conv1 198 vs 281 us, K 152 -> N 368 454 vs 571 us, strided shortcut convs 252 vs 370 us): no
   // CTA-wide barrier, no second pass over the tile.  The wide long-K layers without a residual (s4 conv1, K = N = 368) still
   // prefer the staged, coalesced stores (171 vs 245 us).
-  const char* force_staged = getenv("TDEED_GEMM_STAGED");
+  const char* force_staged = tdeed::dev_env("TDEED_GEMM_STAGED");
   const bool direct_wins = p.fast && (N <= 256 || K <= 192);
   p.staged = force_staged ? atoi(force_staged) : (!direct_wins && residual == nullptr && N >= 96 ? 1 : 0);
   if (p.w_res && big_slice) p.staged = 0;
@@ -699,12 +699,12 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
   int grid = num_tiles < kNumSMs ? num_tiles : kNumSMs;
   if (p.w_res) grid -= grid % p.n_tiles;             // every CTA then sees one fixed n-tile: its resident W slice
   static int trace = -1;
-  if (trace < 0) { const char* e = getenv("TDEED_GEMM_TRACE"); trace = e ? atoi(e) : 0; }
+  if (trace < 0) { const char* e = tdeed::dev_env("TDEED_GEMM_TRACE"); trace = e ? atoi(e) : 0; }
   if (trace)
     fprintf(stderr, "gemm_tc M=%lld N=%d K=%d nseg=%d gather=%d res=%d act=%d | block_n=%d n_tiles=%d w_res=%d stages=%d staged=%d out_bufs=%d fast=%d grid=%d smem=%zu\n",
             M, N, K, nseg, p.gather, residual != nullptr, act, block_n, p.n_tiles, p.w_res, stages, p.staged, p.out_bufs, p.fast, grid, smem);
   static int epi16_env = -1;
-  if (epi16_env < 0) { const char* e = getenv("TDEED_GEMM_EPI16"); epi16_env = e ? atoi(e) : 0; }
+  if (epi16_env < 0) { const char* e = tdeed::dev_env("TDEED_GEMM_EPI16"); epi16_env = e ? atoi(e) : 0; }
   if (p.fast && !p.staged && epi16_env) gemm_tc_kernel<2><<<grid, TC_THREADS16, smem, st>>>(maps[0], maps[1], maps[2], p);
   else if (p.fast) gemm_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], p);
   else gemm_tc_kernel<0><<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], p);

@@ -453,11 +453,11 @@ int gemm_thin_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* 
     attr_set = true;
   }
   static int fast_env = -1;
-  if (fast_env < 0) { const char* e = getenv("TDEED_GEMM_FAST_EPI"); fast_env = e ? atoi(e) : 1; }
+  if (fast_env < 0) { const char* e = tdeed::dev_env("TDEED_GEMM_FAST_EPI"); fast_env = e ? atoi(e) : 1; }
   p.fast = (fast_env && out_dtype == TDEED_BF16 && (act == TDEED_ACT_NONE || act == TDEED_ACT_RELU)) ? 1 : 0;
   p.split = (p.fast && N <= 32) ? 1 : 0;
   static int pair_env = -1;
-  if (pair_env < 0) { const char* e = getenv("TDEED_THIN_MMA_PAIR"); pair_env = e ? atoi(e) : 2; }
+  if (pair_env < 0) { const char* e = tdeed::dev_env("TDEED_THIN_MMA_PAIR"); pair_env = e ? atoi(e) : 2; }
   p.mma_pair = p.num_stages >= 8 ? (pair_env > 4 ? 4 : (pair_env < 1 ? 1 : pair_env)) : 1;     // tiles per MMA-warp trip
   if (p.mma_pair > (1 << p.nacc_log2)) p.mma_pair = 1 << p.nacc_log2;   // a trip must not wait for an accumulator it fills itself
   const int grid = p.m_tiles < kNumSMs ? p.m_tiles : kNumSMs;

@@ -54,69 +54,83 @@ se_mean_kernel(const T* __restrict__ x, int hw, int c, float* __restrict__ mean)
   for (int ch = threadIdx.x; ch < c; ch += SE_THREADS) mean[(size_t)f * c + ch] = s_sum[ch] * inv;
 }
 
-// fc1 + ReLU + fc2 + sigmoid for F frames per CTA (F chosen so that the grid is about one wave).  The fc weights (2*rd*c
-// floats: 270 KB at stage 4 of RegNetY-200MF, 1.2 MB at 800MF) stay in L2 and are streamed once per CTA with 16-byte loads,
-// several rows in flight; every weight meets all F frames of the CTA from registers / broadcast shared-memory reads.
-// r1 processed 8 frames per CTA with scalar weight loads: one L2 round trip per 8 FMAs, 95 us per stage-4 launch.
+// fc1 + ReLU + fc2 + sigmoid for F frames per CTA (F = 8, 16 or 32: about one wave of CTAs).  The fc weights (2*rd*c floats:
+// 270 KB at stage 4 of RegNetY-200MF, 1.2 MB at 800MF) stay in L2 and are streamed once per CTA with coalesced loads; every
+// weight meets all F frames of the CTA: F/4 conflict-free 16-byte shared-memory reads (s_mean is [F/4][c][4]) and F FMAs.
+// The cross-lane sums of fc1 are a reduce-scatter (F - 1 shuffles per row instead of 5 F): lane l ends up with frame l % F.
+// r1 processed 8 frames per CTA: one L2 round trip per 8 FMAs and 40 shuffles per row, 95 us per stage-4 launch.
 template <int F>
-__global__ void __launch_bounds__(SE_THREADS)
+__device__ __forceinline__ float reduce_scatter(float (&acc)[F], int lane) {
+  // offsets >= F: plain butterfly (every lane keeps all F values); offsets < F: halve the set a lane is responsible for
+#pragma unroll
+  for (int off = 16; off >= F; off >>= 1)
+#pragma unroll
+    for (int j = 0; j < F; ++j) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], off);
+#pragma unroll
+  for (int n = F / 2; n >= 1; n >>= 1) {
+    const bool upper = (lane & n) != 0;
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+      const float send = upper ? acc[j] : acc[j + n];
+      const float keep = upper ? acc[j + n] : acc[j];
+      acc[j] = keep + __shfl_xor_sync(0xffffffffu, send, n);
+    }
+  }
+  return acc[0];                                 // sum over the warp for frame (lane % F)
+}
+
+constexpr int SE_FC_THREADS = 512;
+
+template <int F>
+__global__ void __launch_bounds__(SE_FC_THREADS, (F <= 16 ? 2 : 1))
 se_fc_kernel(const float* __restrict__ mean, int n, int c, int rd, const float* __restrict__ w1,
              const float* __restrict__ b1, const float* __restrict__ w2t, const float* __restrict__ b2,
              float* __restrict__ scale) {
   extern __shared__ __align__(16) float smem[];
-  float* s_mean = smem;                         // [c][F]   frame-minor: the F values of a channel are F/4 16-byte reads
-  float* s_hid = s_mean + (size_t)F * c;        // [rd][F]
+  constexpr int G = F / 4;
+  float4* s_mean = reinterpret_cast<float4*>(smem);               // [G][c]  (4 frames per element)
+  float* s_hid = smem + (size_t)F * c;                            // [rd][F]
   const int f0 = blockIdx.x * F;
   const int nf = min(F, n - f0);
-  for (int i = threadIdx.x; i < F * c; i += SE_THREADS) {
-    const int f = i / c, ch = i - f * c;          // coalesced global read, transposed store
-    s_mean[ch * F + f] = (f < nf) ? mean[(size_t)(f0 + f) * c + ch] : 0.f;
+  for (int i = threadIdx.x; i < F * c; i += SE_FC_THREADS) {
+    const int f = i / c, ch = i - f * c;          // coalesced global read, scattered 4-byte store
+    reinterpret_cast<float*>(s_mean + (size_t)(f >> 2) * c + ch)[f & 3] = (f < nf) ? mean[(size_t)(f0 + f) * c + ch] : 0.f;
   }
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c4 = c >> 2;                          // c % 8 == 0
-  for (int r = warp; r < rd; r += SE_THREADS / 32) {
+  for (int r = warp; r < rd; r += SE_FC_THREADS / 32) {
     float acc[F];
 #pragma unroll
     for (int f = 0; f < F; ++f) acc[f] = 0.f;
-    const float4* wr = reinterpret_cast<const float4*>(w1 + (size_t)r * c);
-#pragma unroll 2
-    for (int q = lane; q < c4; q += 32) {
-      const float4 wv = __ldg(wr + q);
-      const float w4[4] = {wv.x, wv.y, wv.z, wv.w};
+    const float* wr = w1 + (size_t)r * c;
+#pragma unroll 4
+    for (int ch = lane; ch < c; ch += 32) {        // 4 coalesced weight loads in flight
+      const float wv = __ldg(wr + ch);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4* m = reinterpret_cast<const float4*>(s_mean + (size_t)(4 * q + j) * F);
-#pragma unroll
-        for (int g = 0; g < F / 4; ++g) {
-          const float4 mv = m[g];
-          acc[4 * g] = fmaf(w4[j], mv.x, acc[4 * g]);
-          acc[4 * g + 1] = fmaf(w4[j], mv.y, acc[4 * g + 1]);
-          acc[4 * g + 2] = fmaf(w4[j], mv.z, acc[4 * g + 2]);
-          acc[4 * g + 3] = fmaf(w4[j], mv.w, acc[4 * g + 3]);
-        }
+      for (int g = 0; g < G; ++g) {
+        const float4 mv = s_mean[(size_t)g * c + ch];
+        acc[4 * g] = fmaf(wv, mv.x, acc[4 * g]);
+        acc[4 * g + 1] = fmaf(wv, mv.y, acc[4 * g + 1]);
+        acc[4 * g + 2] = fmaf(wv, mv.z, acc[4 * g + 2]);
+        acc[4 * g + 3] = fmaf(wv, mv.w, acc[4 * g + 3]);
       }
     }
-    const float bb = b1[r];
-#pragma unroll
-    for (int f = 0; f < F; ++f) {
-      const float sres = warp_sum(acc[f]);
-      if (lane == 0) s_hid[r * F + f] = fmaxf(sres + bb, 0.f);
-    }
+    const float sres = reduce_scatter<F>(acc, lane);
+    if (lane < F) s_hid[r * F + lane] = fmaxf(sres + b1[r], 0.f);
   }
   __syncthreads();
-  for (int ch = threadIdx.x; ch < c; ch += SE_THREADS) {
+  for (int ch = threadIdx.x; ch < c; ch += SE_FC_THREADS) {
     float acc[F];
     const float bb = b2[ch];
 #pragma unroll
     for (int f = 0; f < F; ++f) acc[f] = bb;
-#pragma unroll 8
+#pragma unroll 4
     for (int r = 0; r < rd; ++r) {
-      const float wv = __ldg(w2t + (size_t)r * c + ch);      // coalesced over ch, 8 rows in flight
+      const float wv = __ldg(w2t + (size_t)r * c + ch);      // coalesced over ch
       const float4* h = reinterpret_cast<const float4*>(s_hid + r * F);
 #pragma unroll
-      for (int g = 0; g < F / 4; ++g) {
-        const float4 hv = h[g];
+      for (int g = 0; g < G; ++g) {
+        const float4 hv = h[g];                              // broadcast
         acc[4 * g] = fmaf(wv, hv.x, acc[4 * g]);
         acc[4 * g + 1] = fmaf(wv, hv.y, acc[4 * g + 1]);
         acc[4 * g + 2] = fmaf(wv, hv.z, acc[4 * g + 2]);
@@ -139,23 +153,20 @@ static int launch_se_fc(const float* mean, int n, int c, int rd, const float* w1
     TDEED_REQUIRE(e == cudaSuccess, TDEED_ERR_CUDA, "tdeed_se_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     set = true;
   }
-  se_fc_kernel<F><<<ceil_div(n, F), SE_THREADS, smem_fc, st>>>(mean, n, c, rd, w1, b1, w2, b2, scale);
+  se_fc_kernel<F><<<ceil_div(n, F), SE_FC_THREADS, smem_fc, st>>>(mean, n, c, rd, w1, b1, w2, b2, scale);
   return check_launch("tdeed_se_fwd(fc)");
 }
 
 // frames per CTA: about one wave of CTAs, bounded by shared memory (F * (c + rd) floats)
 static int se_fc_dispatch(const float* mean, int n, int c, int rd, const float* w1, const float* b1, const float* w2, const float* b2,
                           float* scale, cudaStream_t st) {
-  int F = ((ceil_div(n, kNumSMs) + 7) / 8) * 8;
-  if (F > 40) F = 40;
-  while (F > 8 && (size_t)F * (c + rd) * sizeof(float) > 190 * 1024) F -= 8;
-  switch (F) {
-    case 8: return launch_se_fc<8>(mean, n, c, rd, w1, b1, w2, b2, scale, st);
-    case 16: return launch_se_fc<16>(mean, n, c, rd, w1, b1, w2, b2, scale, st);
-    case 24: return launch_se_fc<24>(mean, n, c, rd, w1, b1, w2, b2, scale, st);
-    case 32: return launch_se_fc<32>(mean, n, c, rd, w1, b1, w2, b2, scale, st);
-    default: return launch_se_fc<40>(mean, n, c, rd, w1, b1, w2, b2, scale, st);
-  }
+  // 16 frames per 512-thread CTA, two CTAs per SM: 32 warps per SM hide the L2 latency of the weight stream (one 8-warp CTA
+  // of 32 frames per SM issued 28 % of the time: ncu r2); 8 frames when there are too few frames to fill the machine
+  const int per = ceil_div(n, 2 * kNumSMs);
+  int F = per > 8 ? 16 : 8;
+  while (F > 8 && (size_t)F * (c + rd) * sizeof(float) > 190 * 1024) F >>= 1;
+  if (F == 16) return launch_se_fc<16>(mean, n, c, rd, w1, b1, w2, b2, scale, st);
+  return launch_se_fc<8>(mean, n, c, rd, w1, b1, w2, b2, scale, st);
 }
 
 template <typename T>

@@ -431,7 +431,7 @@ static bool launch_cluster16(void (*kern)(Args...), dim3 grid, size_t smem, cuda
 static bool sgp_no_cluster() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("TDEED_SGP_NO_CLUSTER");
+    const char* e = tdeed::dev_env("TDEED_SGP_NO_CLUSTER");
     v = (e && e[0] == '1') ? 1 : 0;
   }
   return v == 1;

@@ -263,8 +263,8 @@ static int run_bwd_mode(const void* dz, const void* z, const void* y, long long 
   // rows in flight per thread: reduction 4 (TDEED_BN_REDUCE_ROWS=8 to try 8: measured equal), apply 4 (TDEED_BN_APPLY_ROWS=2:
   // 11.66 vs 11.32 ms per FineGym_big step)
   static int kb = 0, u = 0;
-  if (!kb) { const char* e = getenv("TDEED_BN_REDUCE_ROWS"); kb = (e && atoi(e) == 8) ? 8 : 4; }
-  if (!u) { const char* e = getenv("TDEED_BN_APPLY_ROWS"); u = (e && atoi(e) == 2) ? 2 : 4; }
+  if (!kb) { const char* e = tdeed::dev_env("TDEED_BN_REDUCE_ROWS"); kb = (e && atoi(e) == 8) ? 8 : 4; }
+  if (!u) { const char* e = tdeed::dev_env("TDEED_BN_APPLY_ROWS"); u = (e && atoi(e) == 2) ? 2 : 4; }
   if (kb == 8) return u == 4 ? run_bwd_cfg<T, MODE, 8, 4>(dz, z, y, M, C, stats, dgamma, dbeta, dy, dres, ws, st)
                              : run_bwd_cfg<T, MODE, 8, 2>(dz, z, y, M, C, stats, dgamma, dbeta, dy, dres, ws, st);
   return u == 4 ? run_bwd_cfg<T, MODE, 4, 4>(dz, z, y, M, C, stats, dgamma, dbeta, dy, dres, ws, st)

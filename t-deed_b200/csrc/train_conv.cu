@@ -345,7 +345,7 @@ int conv3x3g_bwd_weight_tc_launch(const void* x, const void* dy, int n, int h, i
 static bool conv_force_simt() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("TDEED_CONV_BWD_SIMT");
+    const char* e = tdeed::dev_env("TDEED_CONV_BWD_SIMT");
     v = (e && e[0] == '1') ? 1 : 0;
   }
   return v == 1;

@@ -174,7 +174,7 @@ int gemm_tn_tc_launch(const void* A, long long lda, const void* B, long long ldb
 static bool tn_force_simt() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("TDEED_GEMM_TN_SIMT");
+    const char* e = tdeed::dev_env("TDEED_GEMM_TN_SIMT");
     v = (e && e[0] == '1') ? 1 : 0;
   }
   return v == 1;

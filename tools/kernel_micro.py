@@ -1,0 +1,53 @@
+#!/usr/bin/env python3
+"""Stand-alone timings (CUDA events, L2 flushed between repetitions) of the small per-frame kernels at the shapes of one
+57-clip batch of the bench workload: SE (mean / fc / scale), gate-shift, pool.  usage: python tools/kernel_micro.py [se gsf]"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, 't-deed_b200'))
+import torch
+from tdeed_b200 import ops, _lib as L
+
+dev = torch.device('cuda')
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(fn, reps=10):
+    fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+what = sys.argv[1:] or ['se', 'gsf']
+N = 5700
+if 'se' in what:
+    for (hw, c, rd, n) in ((49, 368, 92, N), (196, 152, 38, N), (196, 152, 14, N), (49, 368, 38, N), (784, 56, 6, 1425), (3136, 24, 8, 1425)):
+        x = torch.randn(n, hw, 1, c, device=dev).to(torch.bfloat16)
+        w1 = torch.randn(rd, c, device=dev) * 0.1
+        b1 = torch.randn(rd, device=dev) * 0.1
+        w2 = torch.randn(rd, c, device=dev) * 0.1
+        b2 = torch.randn(c, device=dev) * 0.1
+        t = timeit(lambda: ops.se_(x, w1, b1, w2, b2))
+        print('se   n=%d hw=%d c=%d rd=%d: %.1f us total (mean+fc+scale), %.2f TB/s on 3 passes' % (n, hw, c, rd, t, 3 * x.numel() * 2 / t / 1e6), flush=True)
+if 'gsf' in what:
+    for (h, c, fold) in ((28, 56, 16), (14, 152, 40), (14, 152, 40), (7, 368, 92)):
+        b, t_ = 57, 100
+        x = torch.randn(b * t_, h, h, c, device=dev).to(torch.bfloat16)
+        p = dict(bn_scale=torch.rand(fold, device=dev) + 0.5, bn_shift=torch.randn(fold, device=dev) * 0.1,
+                 w3d=(torch.randn(2 * (fold // 2) * 27, device=dev) * 0.05), b3d=torch.randn(2, device=dev) * 0.1,
+                 cc_w=torch.randn(36, device=dev) * 0.2, cc_b=torch.randn(2, device=dev) * 0.1)
+        ws = torch.empty(ops.gsf_workspace_floats(b, t_, h, h, fold), dtype=torch.float32, device=dev)
+        out = torch.empty((b * t_ * h * h, (fold + 7) // 8 * 8), dtype=torch.bfloat16, device=dev)
+        t = timeit(lambda: ops.gsf(x, b, t_, fold, L.SHIFT_GSF, p, ws, out))
+        print('gsf  %dx%dx%d fold=%d: %.1f us (q+gate+weight+blend)' % (h, h, c, fold, t), flush=True)
