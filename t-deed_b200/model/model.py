@@ -90,6 +90,8 @@ class TDEEDModel(BaseRGBModel):
             self._train_graphs = {}
             self.fused_augmentation = True   # False: run self.augmentation (torchvision ops) instead of train_aug.cu
             self.use_train_graph = True      # replay forward+loss+backward as a CUDA graph from the 3rd step of a signature on
+            self.overlap_allreduce = True    # data parallel: all-reduce the temporal-stack gradients during the backbone backward
+            self._grads_reduced = False
             self._train_calls = 0
 
         # ---- engine management -------------------------------------------------------------
@@ -120,6 +122,22 @@ class TDEEDModel(BaseRGBModel):
                 self._train_graphs.clear()
             return self._flat
 
+        def sync_replicas(self, force=False):
+            """Data-parallel training (one process per GPU, torch.distributed initialised): broadcast rank 0's parameters and
+            buffers once, so that replicas — whose temp_enc / SGP / heads / backbone were drawn from each rank's own RNG — apply
+            the averaged gradients to identical weights.  Per-rank data / augmentation / mixup seeds remain the
+            caller's job (tools/train_ddp.py offsets them by the rank).  BatchNorm running statistics stay per replica during
+            training, as in the reference's single-GPU semantics per shard."""
+            import torch.distributed as dist
+            if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+                return
+            if self.__dict__.get('_replicas_synced') and not force:
+                return
+            from tdeed_b200.parallel import broadcast_model
+            broadcast_model(self)
+            self._engines.clear()
+            self.__dict__['_replicas_synced'] = True
+
         def train_engine(self, precision):
             from tdeed_b200.train_engine import TrainEngine
             flat = self.flat_params()
@@ -140,6 +158,7 @@ class TDEEDModel(BaseRGBModel):
             loss as a device tensor [3] = (total, CE, MSE) — no host sync."""
             from tdeed_b200 import train_ops as TO
             flat = self.flat_params()
+            self.sync_replicas()
             eng = self.train_engine(precision)
             if precision == 'bf16':
                 flat.refresh_shadow()
@@ -183,21 +202,36 @@ class TDEEDModel(BaseRGBModel):
                     raise ValueError("double-head training needs batch['dataset'] (1 | 2 per clip)")
                 ds_dev = torch.as_tensor(dataset, dtype=torch.int32).reshape(-1).to(frame.device)
 
-            def run(fr, hd, sf, ld, grads):
+            def run_a(fr, hd, sf, ld, grads):
+                """forward + loss + backward of the heads and the temporal stack"""
                 eng.G = grads
                 logits, displ = eng.forward(fr, (cy, cx, ch, cw), unit_input=unit, dropout_p=dropout_p)
                 loss = eng.loss(logits, displ, hd, sf, ld, fg_weight=fg_weight, dataset=ds_dev)
-                eng.backward()
+                eng.backward_temporal()
                 return loss, logits, displ
 
+            def run(fr, hd, sf, ld, grads):
+                out = run_a(fr, hd, sf, ld, grads)
+                eng.backward_backbone()
+                return out
+
             direct = not accumulate and grad_scale == 1.0
+            # data parallel (one process per GPU): the gradients of the temporal stack + heads — the tail of the flat buffer, ~80 %
+            # of its bytes — are all-reduced over NVLink while the backbone backward still runs; the rest follows at the end
+            import torch.distributed as dist
+            overlap = (direct and self.overlap_allreduce and dist.is_available() and dist.is_initialized()
+                       and dist.get_world_size() > 1)
+            if overlap:
+                from tdeed_b200.parallel import GradReducer, temporal_grad_range
+                reducer = self.__dict__.setdefault('_reducer', GradReducer())
+                t_lo, t_hi = temporal_grad_range(flat)
             if use_graph is None:
                 use_graph = self.use_train_graph and not self._double_head     # (dataset ids are not a static graph input yet)
             if use_graph:
                 # CUDA graph of forward + loss + backward for this (shapes, crop, dtypes) signature: ~3500 launches replayed
                 # with one host call.  Inputs are copied into static buffers; gradients land in a static buffer.
                 key = (precision, tuple(frame.shape), frame.dtype, (cy, cx, ch, cw), unit, hard is not None, use_d, dropout_p,
-                       fg_weight, flat.p.data_ptr())
+                       fg_weight, flat.p.data_ptr(), overlap)
                 ent = self._train_graphs.get(key)
                 if ent is None:                      # first sight of this signature: run eagerly (warms every kernel / allocator)
                     self._train_graphs[key] = 'warm'
@@ -208,11 +242,27 @@ class TDEEDModel(BaseRGBModel):
                               g=torch.zeros_like(flat.g))
                     st['G'] = {n: st['g'][o:o + cnt].view(flat.P[n].shape) for n, (o, cnt) in flat.offsets.items()}
                     torch.cuda.synchronize()
-                    graph = torch.cuda.CUDAGraph()
-                    with torch.cuda.graph(graph):
-                        st['out'] = run(st['frame'], st['hard'], st['soft'], st['labD'], st['G'])
-                    st['graph'] = graph
-                    self._train_graphs[key] = ent = st
+                    # thread_local capture: the DataLoader's pin-memory thread and the prefetch stream may touch CUDA meanwhile
+                    # (ADVICE r1); a failed capture falls back to eager execution for this signature
+                    try:
+                        graph = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(graph, capture_error_mode='thread_local'):
+                            st['out'] = (run_a if overlap else run)(st['frame'], st['hard'], st['soft'], st['labD'], st['G'])
+                        st['graph'] = graph
+                        if overlap:         # second graph (same memory pool): the backbone backward, replayed after the first all-reduce is launched
+                            graph_b = torch.cuda.CUDAGraph()
+                            with torch.cuda.graph(graph_b, pool=graph.pool(), capture_error_mode='thread_local'):
+                                eng.backward_backbone()
+                            st['graph_b'] = graph_b
+                        self._train_graphs[key] = ent = st
+                    except RuntimeError as exc:
+                        import warnings
+                        warnings.warn('tdeed_b200: CUDA-graph capture of the training step failed (%s); running eagerly' % (exc,))
+                        self._train_graphs[key] = ent = 'eager'
+                        eng.tape = None
+                        use_graph = False
+                elif ent == 'eager':
+                    use_graph = False
                 if use_graph:
                     ent['frame'].copy_(frame)
                     if hard is not None:
@@ -222,6 +272,12 @@ class TDEEDModel(BaseRGBModel):
                     if labD is not None:
                         ent['labD'].copy_(labD)
                     ent['graph'].replay()
+                    if 'graph_b' in ent:
+                        reducer.launch(ent['g'], t_lo, t_hi)
+                        ent['graph_b'].replay()
+                        reducer.launch(ent['g'], 0, t_lo)
+                        reducer.wait()
+                        self._grads_reduced = True
                     loss, logits, displ = ent['out']
                     if accumulate:
                         TO.axpy_(ent['g'], grad_scale, flat.g)
@@ -231,7 +287,14 @@ class TDEEDModel(BaseRGBModel):
                         flat.g.zero_()
                         TO.axpy_(ent['g'], grad_scale, flat.g)
             if not use_graph:
-                if direct:
+                if overlap:
+                    loss, logits, displ = run_a(frame, hard, soft, labD, flat.G)
+                    reducer.launch(flat.g, t_lo, t_hi)
+                    eng.backward_backbone()
+                    reducer.launch(flat.g, 0, t_lo)
+                    reducer.wait()
+                    self._grads_reduced = True
+                elif direct:
                     loss, logits, displ = run(frame, hard, soft, labD, flat.G)
                 else:                               # accumulate / scale: write into a scratch buffer, then axpy
                     scratch = torch.zeros_like(flat.g)
@@ -306,7 +369,11 @@ class TDEEDModel(BaseRGBModel):
             return
         from tdeed_b200.parallel import allreduce_gradients
         flat = self._model.flat_params()
-        scale = allreduce_gradients(flat.g)
+        if self._model._grads_reduced:          # already summed, overlapped with the backward pass (Impl.train_step)
+            self._model._grads_reduced = False
+            scale = 1.0 / dist.get_world_size()
+        else:
+            scale = allreduce_gradients(flat.g)
         if hasattr(optimizer, 'grad_scale'):
             optimizer.grad_scale = scale
         else:

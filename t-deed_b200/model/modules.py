@@ -55,6 +55,8 @@ class BaseRGBModel(ABCModel):
         # tdeed_adamw_step launch over the flat parameter buffer (tdeed_b200/optim.py).
         from tdeed_b200.optim import FusedAdamW
         flat = self._model.flat_params() if hasattr(self._model, 'flat_params') else None
+        if hasattr(self._model, 'sync_replicas'):
+            self._model.sync_replicas()        # data parallel: every replica starts from rank 0's weights and BN buffers
         return FusedAdamW(self._get_params(), flat=flat, **opt_args), \
             torch.amp.GradScaler('cuda', enabled=False) if self.device == 'cuda' else None
 

@@ -80,7 +80,38 @@ class RegNet(nn.Module):
                 nn.init.zeros_(m.conv3.bn.weight)
 
 
-def create_model(name, pretrained=False):
-    """Stand-in for timm.create_model: there is no network, so `pretrained` weights must come from a
-    checkpoint (`TDEEDModel.load`)."""
-    return RegNet(name)
+PRETRAINED_ENV = 'TDEED_REGNET_WEIGHTS'
+
+
+def create_model(name, pretrained=False, pretrained_path=None):
+    """Stand-in for timm.create_model (model/model.py:37-46 of the reference calls it with pretrained=True, i.e. it
+    starts from timm's ImageNet weights).  There is no network here, so the weights come from a LOCAL file:
+    `pretrained_path`, or `$TDEED_REGNET_WEIGHTS` — a directory holding `<name>.pth` / `<name>.pt` / `<name>.bin`, or that
+    file itself — containing timm's state_dict for `name` (keys `stem.conv.weight`, `s1.b1.conv1.conv.weight`, ...,
+    `head.fc.*`); it is loaded STRICTLY.  With pretrained=True and no file this warns loudly and returns the random
+    initialisation: fine for loading a full T-DEED checkpoint afterwards (`TDEEDModel.load`, what evaluation does), NOT
+    equivalent to the reference for training from scratch."""
+    model = RegNet(name)
+    if not pretrained:
+        return model
+    import os
+    import warnings
+    path = pretrained_path or os.environ.get(PRETRAINED_ENV)
+    if path and os.path.isdir(path):
+        cands = [os.path.join(path, name + ext) for ext in ('.pth', '.pt', '.bin')]
+        path = next((c for c in cands if os.path.isfile(c)), None)
+        if path is None:
+            raise FileNotFoundError('%s is set but holds none of %s' % (PRETRAINED_ENV, [os.path.basename(c) for c in cands]))
+    if not path:
+        msg = ('tdeed_b200: create_model(%r, pretrained=True) but no local weights: the backbone is RANDOMLY initialised (timm would '
+               'have downloaded ImageNet weights).  Set %s=<dir or file with timm\'s %s state_dict> to match the reference when '
+               'training from scratch; loading a T-DEED checkpoint afterwards overwrites the backbone anyway.' % (name, PRETRAINED_ENV, name))
+        warnings.warn(msg, RuntimeWarning, stacklevel=2)
+        print('WARNING: ' + msg)
+        return model
+    import torch
+    sd = torch.load(path, map_location='cpu')
+    if isinstance(sd, dict) and 'state_dict' in sd and not any(k.startswith('stem.') for k in sd):
+        sd = sd['state_dict']
+    model.load_state_dict(sd, strict=True)
+    return model

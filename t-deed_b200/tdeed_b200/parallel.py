@@ -57,6 +57,81 @@ def allreduce_gradients(flat_grad, bucket_elems=16 << 20):
     return 1.0 / ws
 
 
+class GradReducer:
+    """All-reduce of RANGES of the flat gradient buffer, launched as soon as a range is final while the rest of the
+    backward pass still runs: `launch()` enqueues bucketed async all-reduces (NCCL runs them on its own stream, ordered
+    after the kernels already enqueued on the current stream), `wait()` makes the current stream wait for all of them and
+    returns the sum -> mean factor 1 / world.  With one process both are no-ops."""
+
+    def __init__(self, bucket_elems=16 << 20):
+        self.bucket_elems = bucket_elems
+        self.handles = []
+        self.reduced = []              # [(lo, hi)] ranges launched since the last wait()
+
+    def launch(self, flat_grad, lo, hi):
+        rank, ws = world()
+        self.reduced.append((lo, hi))
+        if ws == 1:
+            return
+        for a in range(lo, hi, self.bucket_elems):
+            self.handles.append(dist.all_reduce(flat_grad[a:min(hi, a + self.bucket_elems)], op=dist.ReduceOp.SUM, async_op=True))
+
+    def wait(self):
+        for h in self.handles:
+            h.wait()
+        self.handles = []
+        self.reduced = []
+        return 1.0 / world()[1]
+
+
+def temporal_grad_range(flat):
+    """[lo, hi) of the flat buffers holding the parameters whose gradients are final after TrainEngine.backward_temporal():
+    everything from the first `_temp_fine.*` parameter to the end (`_temp_fine`, `_pred_fine`, `_pred_displ` are registered
+    after the backbone in TDEEDModel.Impl.__init__, model/model.py:65-75 of the reference)."""
+    names = list(flat.offsets)
+    first = next(i for i, n in enumerate(names) if n.startswith('_temp_fine.'))
+    assert all(not n.startswith(('_features.', 'temp_enc')) for n in names[first:]), 'unexpected parameter order'
+    return flat.offsets[names[first]][0], flat.total
+
+
+def broadcast_model(impl, src=0):
+    """Make every replica identical to rank `src`: the flat parameter buffer (or every parameter when it has not been built
+    yet) and all buffers (BatchNorm running statistics).  ADVICE r1: replicas initialise temp_enc / SGP / heads from their own
+    RNG, and averaged gradients applied to different weights diverge."""
+    rank, ws = world()
+    if ws == 1:
+        return
+    flat = impl.__dict__.get('_flat')
+    if flat is not None and flat.valid():
+        dist.broadcast(flat.p, src=src)
+        flat.version += 1
+    else:
+        for p in impl.parameters():
+            dist.broadcast(p.data, src=src)
+    for b in impl.buffers():
+        dist.broadcast(b, src=src)
+
+
+def init_distributed(backend=None):
+    """One process per GPU under torchrun (RANK / LOCAL_RANK / WORLD_SIZE / MASTER_* from the environment): binds the process
+    to its GPU (and that GPU's NUMA node), creates the process group.  Returns (rank, world, local_rank); (0, 1, 0) and no
+    process group when WORLD_SIZE is unset or 1."""
+    import os
+    import torch
+    ws = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local)
+    if ws > 1 and not dist.is_initialized():
+        if torch.cuda.is_available():
+            bind_to_gpu_numa(local)
+            dist.init_process_group(backend or 'nccl', device_id=torch.device('cuda', local))
+        else:
+            dist.init_process_group(backend or 'gloo')
+    return rank, ws, local
+
+
 def broadcast_parameters(flat_param, src=0):
     """Make every replica start from rank `src`'s weights (flat parameter buffer, in place)."""
     rank, ws = world()

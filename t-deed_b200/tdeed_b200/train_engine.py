@@ -257,6 +257,13 @@ class TrainEngine:
 
     # ------------------------------------------------------------------ backward
     def backward(self):
+        self.backward_temporal()
+        self.backward_backbone()
+
+    def backward_temporal(self):
+        """Heads + ED-SGP-Mixer backward: afterwards every gradient of `_temp_fine.*` / `_pred_*` is final (they are the
+        contiguous tail of the flat gradient buffer and ~80 % of its bytes), so a data-parallel caller can start their
+        all-reduce while backward_backbone() still runs (tdeed_b200.parallel.GradReducer)."""
         cfg, P, G, tape = self.cfg, self.P, self.G, self.tape
         b, t = tape['b'], tape['t']
         n = b * t
@@ -290,7 +297,15 @@ class TrainEngine:
                 dx = T.dropout_bwd(T.linear_bwd_data(dd2, P['_pred_displ._fc_out.weight']), hd['mask_d'], hd['p'], add=dx)
             else:
                 dx = T.linear_bwd_data(dd2, P['_pred_displ._fc_out.weight'], add=dx)
-        dfeat = self._temporal_bwd(dx.view(b, t, d))
+        tape['dfeat'] = self._temporal_bwd(dx.view(b, t, d))
+
+    def backward_backbone(self):
+        """pool + temp_enc, the RegNetY blocks in reverse, the stem."""
+        cfg, P, G, tape = self.cfg, self.P, self.G, self.tape
+        b, t = tape['b'], tape['t']
+        n = b * t
+        d = cfg.feat_dim
+        dfeat = tape['dfeat']
         # pool + temp_enc
         last = tape['last']
         nfr, h, w, _ = last.shape

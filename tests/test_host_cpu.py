@@ -65,3 +65,31 @@ def test_gemm_rejects_bad_arguments_without_gpu():
     seg[0].a, seg[0].lda, seg[0].col0, seg[0].k = 16, 8, 0, 8
     rc = lib.tdeed_gemm_fwd(L.F32, 4, 12, 1, seg, 1, 0, 0, 16, None, None, 0, 0, 0, 16, 16, 0, 0, None)
     assert rc == -1 and b'multiples of 8' in lib.tdeed_last_error()
+
+
+def test_pretrained_backbone_is_loaded_strictly_or_warned_about(tmp_path, monkeypatch):
+    """create_model(pretrained=True) must not silently return random weights (model/model.py:38-46 of the
+    reference starts from timm's ImageNet weights)."""
+    import warnings
+    import torch
+    from model import regnet
+    monkeypatch.delenv(regnet.PRETRAINED_ENV, raising=False)
+    with pytest.warns(RuntimeWarning, match='RANDOMLY initialised'):
+        regnet.create_model('regnety_002', pretrained=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter('error')
+        src = regnet.create_model('regnety_002', pretrained=False)          # no warning without pretrained
+    with torch.no_grad():
+        for p in src.parameters():
+            p.normal_()
+    torch.save(src.state_dict(), tmp_path / 'regnety_002.pth')
+    monkeypatch.setenv(regnet.PRETRAINED_ENV, str(tmp_path))
+    with warnings.catch_warnings():
+        warnings.simplefilter('error')
+        got = regnet.create_model('regnety_002', pretrained=True)
+    for (k, a), (_, b) in zip(src.state_dict().items(), got.state_dict().items()):
+        assert torch.equal(a, b), k
+    bad = {k: v for k, v in src.state_dict().items() if k != 'stem.conv.weight'}
+    torch.save(bad, tmp_path / 'regnety_008.pth')
+    with pytest.raises(RuntimeError):                                        # strict: wrong / missing keys raise
+        regnet.create_model('regnety_008', pretrained=True)
