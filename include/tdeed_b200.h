@@ -157,8 +157,11 @@ typedef struct {
   const float *ln_w, *ln_b, *gn_w, *gn_b;
   const float *psi_w, *psi_b, *fc_w, *fc_b, *convw_w, *convw_b, *convkw_w, *convkw_b, *gfc_w, *gfc_b;
 } tdeed_sgp_weights;
+long long tdeed_sgp_mix_workspace_floats(int B, int t_out, int C);
 int tdeed_sgp_mix_fwd(const float* x, int B, int t_in, int t_out, int C, int ks, int up,
-                      const tdeed_sgp_weights* w_host, float* y, void* g, int g_dtype, void* stream);
+                      const tdeed_sgp_weights* w_host, float* workspace, float* y, void* g, int g_dtype, void* stream);
+/* workspace: >= tdeed_sgp_mix_workspace_floats(B, t_out, C) floats, 16-byte aligned (LayerNorm row statistics, partial
+ * column sums for the phi gate, partial GroupNorm sums in double: the clip-wide reductions are two-level and deterministic). */
 
 /* (8) SGPMixer token mixing (model/modules.py:283-307): z = LN1(skip) [B,T,C], xu =
  * linear-upsample(align_corners) of LN2(x) [B,t_coarse,C] to T; writes the 6C-wide concat
@@ -169,13 +172,15 @@ typedef struct {
   const float *convw2_w, *convw2_b, *convkw2_w, *convkw2_b;
   const float *fc1_w, *fc1_b, *gfc1_w, *gfc1_b, *fc2_w, *fc2_b, *gfc2_w, *gfc2_b;
 } tdeed_mixer_weights;
+long long tdeed_sgp_mixer_workspace_floats(int B, int t_coarse, int T, int C);
 int tdeed_sgp_mixer_mix_fwd(const float* x_coarse, const float* skip, int B, int t_coarse, int T, int C,
-                            int ks, int up, const tdeed_mixer_weights* w_host,
+                            int ks, int up, const tdeed_mixer_weights* w_host, float* workspace,
                             void* cat, int cat_dtype, void* stream);
 
 /* (9) GroupNorm(16, C) over [B, T, C] fp32 -> out of out_dtype (model/modules.py:115,186,311). */
+long long tdeed_groupnorm_workspace_floats(int B, int T, int C, int groups);
 int tdeed_groupnorm_fwd(const float* x, int B, int T, int C, int groups, const float* gamma, const float* beta,
-                        void* out, int out_dtype, void* stream);
+                        float* workspace, void* out, int out_dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (10) heads + softmax + displacement scatter-max.  Replaces FCLayers/FC2Layers (eval: dropout is

@@ -60,11 +60,14 @@ SIGNATURES = {
     'tdeed_gsf_fwd': (c_int, [c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
                               c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     'tdeed_pool_posenc_fwd': (c_int, [c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
-    'tdeed_sgp_mix_fwd': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(SgpWeights), c_vp,
+    'tdeed_sgp_mix_workspace_floats': (c_ll, [c_int, c_int, c_int]),
+    'tdeed_sgp_mix_fwd': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(SgpWeights), c_vp, c_vp,
                                   c_vp, c_int, c_vp]),
+    'tdeed_sgp_mixer_workspace_floats': (c_ll, [c_int, c_int, c_int, c_int]),
     'tdeed_sgp_mixer_mix_fwd': (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int,
-                                        ctypes.POINTER(MixerWeights), c_vp, c_int, c_vp]),
-    'tdeed_groupnorm_fwd': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp]),
+                                        ctypes.POINTER(MixerWeights), c_vp, c_vp, c_int, c_vp]),
+    'tdeed_groupnorm_workspace_floats': (c_ll, [c_int, c_int, c_int, c_int]),
+    'tdeed_groupnorm_fwd': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     'tdeed_heads_fwd': (c_int, [c_vp, c_int, c_int, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_vp, c_vp, c_vp,
                                 c_vp]),
     'tdeed_softmax_scatter_fwd': (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_vp, c_vp]),

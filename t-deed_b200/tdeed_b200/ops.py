@@ -173,7 +173,8 @@ def sgp_mix(x, t_out, ks, up, w, g_dtype):
     y = torch.empty((b, t_out, c), dtype=torch.float32, device=x.device)
     g = torch.empty((b, t_out, c), dtype=g_dtype, device=x.device)
     ws = _fill(L.SgpWeights(), w)
-    L.check(L.load().tdeed_sgp_mix_fwd(L.ptr(x), b, t_in, t_out, c, ks, up, ctypes.byref(ws), L.ptr(y), L.ptr(g),
+    scratch = torch.empty(int(L.load().tdeed_sgp_mix_workspace_floats(b, t_out, c)), dtype=torch.float32, device=x.device)
+    L.check(L.load().tdeed_sgp_mix_fwd(L.ptr(x), b, t_in, t_out, c, ks, up, ctypes.byref(ws), L.ptr(scratch), L.ptr(y), L.ptr(g),
                                        L.dtype_code(g_dtype), L.stream()), 'sgp_mix')
     return y, g
 
@@ -183,7 +184,8 @@ def sgp_mixer_mix(x_coarse, skip, ks, up, w, cat_dtype):
     t = skip.shape[1]
     cat = torch.empty((b * t, 6 * c), dtype=cat_dtype, device=skip.device)
     ws = _fill(L.MixerWeights(), w)
-    L.check(L.load().tdeed_sgp_mixer_mix_fwd(L.ptr(x_coarse), L.ptr(skip), b, tc, t, c, ks, up, ctypes.byref(ws),
+    scratch = torch.empty(int(L.load().tdeed_sgp_mixer_workspace_floats(b, tc, t, c)), dtype=torch.float32, device=skip.device)
+    L.check(L.load().tdeed_sgp_mixer_mix_fwd(L.ptr(x_coarse), L.ptr(skip), b, tc, t, c, ks, up, ctypes.byref(ws), L.ptr(scratch),
                                              L.ptr(cat), L.dtype_code(cat_dtype), L.stream()), 'sgp_mixer_mix')
     return cat
 
@@ -191,7 +193,8 @@ def sgp_mixer_mix(x_coarse, skip, ks, up, w, cat_dtype):
 def groupnorm(x, gamma, beta, out_dtype, groups=16):
     b, t, c = x.shape
     out = torch.empty((b, t, c), dtype=out_dtype, device=x.device)
-    L.check(L.load().tdeed_groupnorm_fwd(L.ptr(x), b, t, c, groups, L.ptr(gamma), L.ptr(beta), L.ptr(out),
+    scratch = torch.empty(int(L.load().tdeed_groupnorm_workspace_floats(b, t, c, groups)), dtype=torch.float32, device=x.device)
+    L.check(L.load().tdeed_groupnorm_fwd(L.ptr(x), b, t, c, groups, L.ptr(gamma), L.ptr(beta), L.ptr(scratch), L.ptr(out),
                                          L.dtype_code(out_dtype), L.stream()), 'groupnorm')
     return out
 

@@ -54,16 +54,17 @@ def main():
     from tdeed_b200.engine import sgp_up_size
     dev = torch.device('cuda')
     hbm, tf = peaks()
-    Bs = [1, 8, 32] if not args.quick else [8]
+    Bs = [1, 4, 8, 32] if not args.quick else [8, 57]
     Ts = [50, 100, 200, 400, 800] if not args.quick else [100, 800]
     Cs = [368, 768]
-    KR = [(3, 2), (7, 4), (11, 4)] if not args.quick else [(9, 4)]
+    KR = [(ks, r) for ks in (3, 5, 7, 9, 11) for r in (2, 4)] if not args.quick else [(5, 4), (9, 4)]
     rows = []
     for C in Cs:
         for ks, r in KR:
             up = sgp_up_size(ks, r)
             torch.manual_seed(0)
             blk = SGPBlock(C, kernel_size=ks, k=r, init_conv_vars=0.1).to(dev).eval()
+            mixer = SGPMixer(C, kernel_size=ks, k=r, init_conv_vars=0.1, t_size=100).to(dev).eval()
             for B in Bs:
                 for T in Ts:
                     x = torch.randn((B, T, C), device=dev)
@@ -79,6 +80,15 @@ def main():
                         t_blk = timed(lambda: blk.forward_btc(x, T), args.reps)
                     flops = 16.0 * B * T * C * C
                     rec.update(block_us=t_blk * 1e6, block_mlp_tflops_if_all_gemm=flops / t_blk / 1e12)
+                    # (3) SGPMixer token mixing alone: skip (T rows) + coarse (ceil(T/2) rows) -> 6C-wide bf16 concat
+                    mw = mixer.mix_weights() if hasattr(mixer, 'mix_weights') else None
+                    if mw is not None:
+                        tc = (T + 1) // 2
+                        xc = torch.randn((B, tc, C), device=dev)
+                        t_mx = timed(lambda: ops.sgp_mixer_mix(xc, x, ks, up, mw, torch.bfloat16), args.reps)
+                        nb = B * C * (T * 4 + tc * 4 + 6 * T * 2) + C * (4 * ks + 2 * up + 16) * 4
+                        rec.update(mixer_us=t_mx * 1e6, mixer_gbs=nb / t_mx / 1e9, mixer_frac_hbm=nb / t_mx / 1e9 / hbm)
+                    rec['launches'] = dict(mix=4, mixer=3)
                     rows.append(rec)
                     print(json.dumps(rec))
         # full encoder-decoder stack, reference config (n_layers 2, ks 9, r 4)
