@@ -597,7 +597,7 @@ extern "C" int tdeed_sgp_mix_fwd(const float* x, int B, int t_in, int t_out, int
   float* colpart = workspace + ws.colpart;
   double* gnpart = reinterpret_cast<double*>(workspace + ws.gnpart);
   float* gstats = workspace + ws.gstats;
-  static size_t cur_mix = 48 * 1024;
+  static size_t cur_mix = 0;      // 0: always opt in (static + dynamic shared memory can exceed 48 KB even when dynamic alone does not)
   int rc = launch_rowstats(x, B, t_in, t_out, C, 0, stats, colpart, st, "tdeed_sgp_mix_fwd(rowstats)");
   if (rc) return rc;
   const size_t smem_mix = ((size_t)(SG_TT + 2 * (up / 2)) * SG_CB + (size_t)SG_TT * SG_CB + (size_t)(up + ks + 1) * SG_CB) * sizeof(float) +
@@ -633,7 +633,7 @@ extern "C" int tdeed_sgp_mixer_mix_fwd(const float* x_coarse, const float* skip,
   float* colpart_z = stats_z + align4(2LL * B * T);
   float* stats_x = colpart_z + align4((long long)B * nrb_z * C);
   float* colpart_x = stats_x + align4(2LL * B * t_coarse);
-  static size_t cur_mix = 48 * 1024;
+  static size_t cur_mix = 0;      // 0: always opt in (static + dynamic shared memory can exceed 48 KB even when dynamic alone does not)
   int rc = launch_rowstats(skip, B, T, T, C, 0, stats_z, colpart_z, st, "tdeed_sgp_mixer_mix_fwd(rowstats z)");
   if (rc) return rc;
   rc = launch_rowstats(x_coarse, B, t_coarse, t_coarse, C, T, stats_x, colpart_x, st, "tdeed_sgp_mixer_mix_fwd(rowstats x)");
