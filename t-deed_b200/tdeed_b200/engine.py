@@ -99,8 +99,12 @@ class InferenceEngine:
 
     # ------------------------------------------------------------------ weights
     def load_state(self, state):
-        cfg, dev, adt = self.cfg, self.device, self.act_dtype
-        sd = {k: v.detach().to(dev) for k, v in state.items()}
+        # Weight preparation (BatchNorm folding, K-segment padding, UMMA weight images) is host arithmetic on CPU tensors, uploaded
+        # once at the end: no eager-torch GPU kernels (r1 launched ~600 ATen elementwise kernels per engine build, which
+        # drowned the library's own kernels in the driver's launch list).
+        cfg, adt = self.cfg, self.act_dtype
+        dev = torch.device('cpu')
+        sd = {k: v.detach().cpu() for k, v in state.items()}
         f32 = lambda t: t.float().contiguous()
         W = {}
         sc, sh = _bn_fold(sd, '_features.stem.bn')
@@ -213,7 +217,15 @@ class InferenceEngine:
             W['displ_b'] = f32(sd['_pred_displ._fc_out.bias'])
         else:
             W['displ_w'] = W['displ_b'] = None
-        self.W = W
+        def upload(o):
+            if isinstance(o, torch.Tensor):
+                return o.to(self.device)
+            if isinstance(o, dict):
+                return {k: upload(v) for k, v in o.items()}
+            if isinstance(o, list) and o and isinstance(o[0], (dict, torch.Tensor)):
+                return [upload(v) for v in o]
+            return o
+        self.W = upload(W)
         self._graphs.clear()
         self.version = getattr(self, 'version', 0) + 1      # bumps whenever prepared weights change (caches keyed on it)
 

@@ -13,8 +13,9 @@ Not on the hot path — `valMAP_SN`, `evaluate_SNB`, `aux_evaluate`, `label2vect
 which loads the reference checkout's own util/eval.py (the next one on sys.path) under a private name and re-exports
 those five names.
 
-`t-deed_b200/util/` deliberately has NO __init__.py: like the reference's `util/` it is a namespace-package portion, so
-`util.io`, `util.score`, `util.dataset` keep resolving to the reference checkout.
+`t-deed_b200/util/` deliberately has NO __init__.py: like the reference's `util/` it is a namespace-package portion; this
+portion comes first on sys.path, so `util.eval`, `util.score`, `util.io`, `util.dataset` resolve here and anything else in
+the reference's `util/` stays reachable.
 """
 import importlib.util
 import math
@@ -28,7 +29,7 @@ from tqdm import tqdm
 
 from tdeed_b200 import ops
 from tdeed_b200.parallel import gather_video_results, shard_videos, world
-from tdeed_b200.pipeline import PendingEvents, VideoInference, VideoScores
+from tdeed_b200.pipeline import PendingEvents, ThreadedFrameSource, VideoInference, VideoScores
 
 # Constants (util/eval.py:24-32 of the reference)
 TOLERANCES = [1, 2, 4]
@@ -344,10 +345,9 @@ def _stream_scores(model, dataset, mine, augment, k, dev):
     starts = vlist[0][2] if vlist else []
     hop = (starts[1] - starts[0]) if len(starts) > 1 else max(1, T // 4)
     pieces = _FramePieces(dataset, [(name, vlen[name], per_video[name][0]) for name in order], STREAM_PIECE_FRAMES)
-    it = iter(DataLoader(pieces, batch_size=None, num_workers=STREAM_WORKERS, pin_memory=True, prefetch_factor=4))
-    first = next(it, None)
-    if first is None:
+    if len(pieces) == 0:
         return {}
+    first = pieces[0]
     in_hw = tuple(first.shape[-2:])
     ch, cw = eng.crop_window(*in_hw)[2:]
     B = max(2, min(STREAM_CLIPS_PER_BATCH, int(STREAM_CLIPS_PER_BATCH * (224 * 224) / (ch * cw))))
@@ -357,13 +357,10 @@ def _stream_scores(model, dataset, mine, augment, k, dev):
         impl.__dict__['_video_inference'] = {key: VideoInference(eng, in_hw, clips_per_batch=B, frames_per_chunk=max(T, B * hop),
                                                                  flips=(False, True) if augment else (False,), clip_len=T)}
         vi = impl.__dict__['_video_inference'][key]
-
-    def chain():
-        yield first
-        for p in tqdm(it, total=len(pieces) - 1):
-            yield p
+    # frames are decoded by worker threads straight into pinned buffers (tdeed_b200.pipeline.ThreadedFrameSource)
+    source = ThreadedFrameSource(pieces, vi.stream, workers=STREAM_WORKERS)
     with torch.no_grad():
-        return vi.run(vlist, chain())
+        return vi.run(vlist, tqdm(source, total=len(pieces)))
 
 
 def _clip_loop_scores(model, dataset, videos, augment, k, dev):
