@@ -225,8 +225,9 @@ def run_evaluate_path(args, model, dev, rank, world):
     classes = {'c%d' % i: i for i in range(1, CONFIG['num_classes'] + 1)}
     out = {}
     for tag, augment in (('batched', False), ('tta', True)):
-        with contextlib.redirect_stdout(io.StringIO()):
-            E.evaluate(model, ds, 'VAL', classes, printed=False, test=False, augment=augment)       # warm-up: graphs, workers
+        for _ in range(2):              # warm-up: CUDA graphs of this chunk / batch geometry, the pinned host ring
+            with contextlib.redirect_stdout(io.StringIO()):
+                E.evaluate(model, ds, 'VAL', classes, printed=False, test=False, augment=augment)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         with contextlib.redirect_stdout(io.StringIO()):

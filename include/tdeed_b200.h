@@ -106,6 +106,15 @@ int tdeed_gemm_fwd(int dtype, long long M, int N, int nseg, const tdeed_gemm_seg
                    const void* residual, long long ldr, int res_dtype,
                    int act, void* out, long long ldo, int out_dtype, int backend, void* stream);
 
+/* (2c) conv3 of a RegNetY bottleneck with the squeeze-excite gate folded into its A operand (timm Bottleneck.forward:
+ * x = conv3(se(conv2(...)))):  out[m, n] = act( sum_k (A[m, k] * a_scale[m / scale_rows][k]) * W[n, k] + bias[n] + residual[m, n] ).
+ * A, W, residual, out bf16; a_scale fp32 [M / scale_rows][K] (the gate of tdeed_se_gate_fwd; scale_rows = pixels per frame).
+ * The product A * gate is rounded to bf16 exactly like the stand-alone scale pass of tdeed_se_fwd, inside shared memory between
+ * the TMA load and the tcgen05 MMA.  bf16 tcgen05 backend only (N tile <= 256 per accumulator; act none | relu). */
+int tdeed_gemm_scaled_fwd(long long M, int N, int K, const void* A, long long lda, const float* a_scale, int scale_rows,
+                          const void* W, const float* bias, const void* residual, long long ldr, int act, void* out,
+                          long long ldo, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * (3) grouped 3x3 convolution (+folded BN + ReLU): timm Bottleneck conv2, group width 8 / 16,
  * stride 1 or 2, pad 1.  in: NHWC [n, h, w, c]; weight fp32 [c][group_width][3][3] (torch layout,
@@ -125,6 +134,10 @@ int tdeed_conv3x3g_tc_fwd(const void* in, int n, int h, int w, int c, int stride
 long long tdeed_se_workspace_floats(int n, int c);
 int tdeed_se_fwd(int dtype, void* x, int n, int hw, int c, int rd,
                  const float* w1, const float* b1, const float* w2t, const float* b2, float* workspace, void* stream);
+/* gate only (mean -> fc1 -> ReLU -> fc2 -> sigmoid): the gate [n, c] fp32 is left at workspace + n*c for a consumer that applies
+ * it itself (tdeed_gemm_scaled_fwd); x is not modified. */
+int tdeed_se_gate_fwd(int dtype, const void* x, int n, int hw, int c, int rd, const float* w1, const float* b1,
+                      const float* w2_t, const float* b2, float* workspace, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * (5) Gate-Shift module on the first `fold` channels of x (model/shift.py:64-93):

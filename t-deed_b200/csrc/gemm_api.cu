@@ -14,7 +14,7 @@ int gemm_simt_launch(int dtype, long long M, int N, int K, const SimtSegs& segs,
                      int act, void* out, long long ldo, int out_dtype, cudaStream_t st);
 int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* segs, int gstride, int gh, int gw,
                    const void* W, const float* bias, const void* residual, long long ldr, int res_dtype, int act,
-                   void* out, long long ldo, int out_dtype, cudaStream_t st);
+                   void* out, long long ldo, int out_dtype, cudaStream_t st, const float* a_scale = nullptr, int scale_rows = 0);
 bool gemm_thin_applicable(int N, int K, int nseg, const tdeed_gemm_seg* segs, int gstride);
 int gemm_thin_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* segs, const void* W, const float* bias,
                      const void* residual, long long ldr, int res_dtype, int act, void* out, long long ldo, int out_dtype,
@@ -63,4 +63,21 @@ extern "C" int tdeed_gemm_fwd(int dtype, long long M, int N, int nseg, const tde
   }
   return gemm_simt_launch(dtype, M, N, K, ss, gather_stride, gather_h, gather_w, W, bias, residual, ldr, res_dtype,
                           act, out, ldo, out_dtype, st);
+}
+
+// (2c) conv3 of a RegNetY bottleneck with the squeeze-excite gate folded into the A operand (timm Bottleneck: x = conv3(se(x))):
+//   out[m, n] = act( sum_k (A[m, k] * a_scale[m / scale_rows][k]) * W[n, k] + bias[n] + residual[m, n] )
+// bf16 tcgen05 backend only (K > 64 layers: stages 3-4); A * gate is rounded to bf16 exactly like the stand-alone scale pass.
+extern "C" int tdeed_gemm_scaled_fwd(long long M, int N, int K, const void* A, long long lda, const float* a_scale, int scale_rows,
+                                     const void* W, const float* bias, const void* residual, long long ldr, int act, void* out,
+                                     long long ldo, void* stream) {
+  using namespace tdeed;
+  TDEED_REQUIRE(A && a_scale && W && out, TDEED_ERR_SHAPE, "tdeed_gemm_scaled_fwd: null pointer");
+  TDEED_REQUIRE(M > 0 && N > 0 && N % 8 == 0 && K > 0 && K % 8 == 0 && lda >= K && lda % 8 == 0 && ldo % 8 == 0 && ldo >= N &&
+                scale_rows > 0 && M % scale_rows == 0, TDEED_ERR_SHAPE,
+                "tdeed_gemm_scaled_fwd: M=%lld N=%d K=%d lda=%lld ldo=%lld scale_rows=%d", M, N, K, lda, ldo, scale_rows);
+  TDEED_REQUIRE(!residual || (ldr % 8 == 0 && ldr >= N), TDEED_ERR_SHAPE, "tdeed_gemm_scaled_fwd: ldr=%lld", ldr);
+  tdeed_gemm_seg seg{A, lda, 0, K};
+  return gemm_tc_launch(M, N, K, 1, &seg, 1, 0, 0, W, bias, residual, ldr, TDEED_BF16, act, out, ldo, TDEED_BF16, (cudaStream_t)stream,
+                        a_scale, scale_rows);
 }

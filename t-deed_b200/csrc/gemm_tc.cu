@@ -25,6 +25,7 @@ namespace tdeed {
 constexpr int TC_BM = 128, TC_BK = 64, TC_MAX_STAGES = 10;
 constexpr int TC_THREADS = 320;   // producer warp, MMA warp, 8 epilogue warps
 constexpr int TC_THREADS16 = 576; // producer warp, MMA warp, 16 epilogue warps (EPI == 2)
+constexpr int TC_THREADS_SC = TC_THREADS + 128;   // + 4 A-scaling warps (EPI == 3)
 
 struct TcParams {
   long long M;
@@ -50,6 +51,10 @@ struct TcParams {
   int staged;     // 1: outputs go through the smem staging tile (coalesced stores); 0: row pieces straight from registers
   int fast;       // 1: specialised epilogue (bf16 out / bf16 residual, act none|relu): whole-row residual prefetch, pipelined TMEM loads
   int debug;   // TDEED_GEMM_DEBUG (dev only): 1 = skip global stores, 2 = skip TMEM loads, 4 = skip the MMAs
+  // A-operand scaling (squeeze-excite fused into conv3, EPI == 3): A[m, k] *= a_scale[m / scale_rows][k] while the k-block sits
+  // in shared memory, between the TMA load and the MMA
+  const float* a_scale;
+  int scale_rows, scale_ld, K;
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -230,8 +235,11 @@ struct TileCoord { int mt, nt; };
 // EPI 2: the same straight-line epilogue on SIXTEEN warps (four per TMEM lane group, each taking every fourth 16-column piece;
 // direct stores only).  The 8-warp epilogue issues one instruction per ~14 cycles and warp (a latency chain TMEM -> bias ->
 // residual -> pack -> store with two warps per scheduler); twice the warps hide twice the latency.
+// EPI 3: EPI 1 plus four "scaler" warps between the TMA producer and the MMA issuer: they multiply every A k-block by the
+// per-(frame, channel) squeeze-excite gate in shared memory (one row per thread, fp32 multiply, round-to-nearest bf16 — the same
+// arithmetic as the stand-alone se_scale pass, which cost one read + one write of the whole activation per block).
 template <int EPI>
-__global__ void __launch_bounds__(EPI == 2 ? TC_THREADS16 : TC_THREADS, 1)
+__global__ void __launch_bounds__(EPI == 2 ? TC_THREADS16 : (EPI == 3 ? TC_THREADS_SC : TC_THREADS), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                const __grid_constant__ CUtensorMap map_w, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -246,13 +254,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
   uint8_t* ring = smem + (p.w_res ? p.w_res_bytes : 0u);
   const uint32_t stage_bytes = p.w_res ? a_stage_bytes : a_stage_bytes + ((w_stage_bytes + 1023u) & ~1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)p.num_stages * stage_bytes);
+  constexpr int EPIK = (EPI == 3) ? 1 : EPI;            // epilogue flavour
   uint64_t* w_bar = bars + 2 * TC_MAX_STAGES + 5;
+  uint64_t* scaled_bar = bars + 2 * TC_MAX_STAGES + 6;   // [TC_MAX_STAGES] A k-block scaled in place (128 scaler threads)
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + TC_MAX_STAGES;
   uint64_t* tmem_full_bar = bars + 2 * TC_MAX_STAGES;        // [2]
   uint64_t* tmem_empty_bar = bars + 2 * TC_MAX_STAGES + 2;   // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_MAX_STAGES + 4);
-  float* s_bias = reinterpret_cast<float*>(bars + 2 * TC_MAX_STAGES + 6);   // [n_tiles * block_n], zero padded
+  float* s_bias = reinterpret_cast<float*>(bars + 3 * TC_MAX_STAGES + 6);   // [n_tiles * block_n], zero padded
   long long* s_rowm_base = reinterpret_cast<long long*>(s_bias + p.n_tiles * p.block_n);       // [2][128] global row of a tile row
   uint8_t* s_out_base = reinterpret_cast<uint8_t*>(s_rowm_base + 2 * TC_BM);                     // [out_bufs][128][block_n*esz + 16]
 
@@ -268,6 +278,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
     for (int s = 0; s < p.num_stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&scaled_bar[s], 128);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
@@ -337,7 +348,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       for (int kb = 0; kb < total_kb; ++kb, ++it) {
         const int stage = it % p.num_stages;
         const uint32_t round = it / p.num_stages;
-        mbar_wait(&full_bar[stage], round & 1u);
+        mbar_wait(EPI == 3 ? &scaled_bar[stage] : &full_bar[stage], round & 1u);
         tcgen05_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(ring + (size_t)stage * stage_bytes);
@@ -353,6 +364,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
           if (kb == total_kb - 1) umma_commit(&tmem_full_bar[acc]);
         }
         __syncwarp();
+      }
+    }
+  } else if (EPI == 3 && warp >= 10) {
+    // ===== A scaler (4 warps, thread = tile row): SE gate applied to the k-block in shared memory =====
+    const int r = threadIdx.x - 320;                         // 0..127
+    const uint32_t row_off = (uint32_t)r * 128u;
+    const uint32_t sw = (uint32_t)(r & 7);                   // 128B swizzle: 16-byte chunk c of row r lives at chunk c ^ (r % 8)
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile / p.n_tiles;
+      long long m = (long long)mt * TC_BM + r;
+      if (m >= p.M) m = p.M - 1;                             // rows past the end are TMA zero fill: any finite gate does
+      const float* gate = p.a_scale + (size_t)(m / p.scale_rows) * p.scale_ld;
+      for (int kb = 0; kb < total_kb; ++kb, ++it) {
+        const int stage = it % p.num_stages;
+        const uint32_t round = it / p.num_stages;
+        const int k0 = kb * TC_BK;
+        // gate values first (L1 / L2 hits: the 128 rows of a tile belong to at most a handful of frames)
+        float4 g[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+          g[q] = (k0 + 4 * q < p.K) ? __ldg(reinterpret_cast<const float4*>(gate + k0) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        mbar_wait(&full_bar[stage], round & 1u);
+        const uint32_t base = smem_u32(ring + (size_t)stage * stage_bytes) + row_off;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          if (k0 + 8 * c >= p.K) break;                      // K tail: zero-filled chunks stay zero
+          const uint32_t addr = base + (((uint32_t)c ^ sw) << 4);
+          uint4 v = lds128(addr);
+          const float4 ga = g[2 * c], gb = g[2 * c + 1];
+          uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+          const float gs[8] = {ga.x, ga.y, ga.z, ga.w, gb.x, gb.y, gb.z, gb.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            w4[q] = pack_bf16x2(__uint_as_float(w4[q] << 16) * gs[2 * q], __uint_as_float(w4[q] & 0xffff0000u) * gs[2 * q + 1]);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w4[0]), "r"(w4[1]), "r"(w4[2]), "r"(w4[3]) : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA's async-proxy reads
+        mbar_arrive(&scaled_bar[stage]);
       }
     }
   } else {
@@ -397,7 +447,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant
       }
       if (half == 0) s_rowm[r] = row_ok ? m : -1;           // global row of every tile row (or -1), for phase 2
       uint8_t* srow = s_out + r * pitch;
-      if constexpr (EPI == 1) {
+      if constexpr (EPIK == 1) {
         if (p.staged && p.out_bufs == 1 && j > 0) epi_bar_sync();   // single staging tile: previous phase 2 must have drained
         if (p.staged) epi_fast_tile<true>(p, &tmem_full_bar[acc], (j >> 1) & 1u, tmem_row, half, ncols, n0, m, row_ok, s_bias, smem_u32(srow));
         else epi_fast_tile<false>(p, &tmem_full_bar[acc], (j >> 1) & 1u, tmem_row, half, ncols, n0, m, row_ok, s_bias, 0u);
@@ -566,7 +616,7 @@ static int make_map_2d(CUtensorMap* map, const void* base, long long rows, long 
 
 int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* segs, int gstride, int gh, int gw,
                    const void* W, const float* bias, const void* residual, long long ldr, int res_dtype, int act,
-                   void* out, long long ldo, int out_dtype, cudaStream_t st) {
+                   void* out, long long ldo, int out_dtype, cudaStream_t st, const float* a_scale, int scale_rows) {
   TDEED_REQUIRE(M > 0 && M < (1LL << 31) - TC_BM, TDEED_ERR_SHAPE, "gemm_tc: M=%lld out of range", M);
   TDEED_REQUIRE(N % 8 == 0 && K % 8 == 0, TDEED_ERR_SHAPE, "gemm_tc: N=%d, K=%d must be multiples of 8", N, K);
   TDEED_REQUIRE(!residual || res_dtype == out_dtype, TDEED_ERR_UNSUPPORTED,
@@ -575,6 +625,13 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
   p.M = M; p.N = N; p.nseg = nseg;
   p.bias = bias; p.residual = residual; p.ldr = ldr; p.res_dtype = res_dtype; p.act = act;
   p.out = out; p.ldo = ldo; p.out_dtype = out_dtype;
+  p.a_scale = a_scale; p.scale_rows = scale_rows; p.scale_ld = K; p.K = K;
+  if (a_scale) {
+    TDEED_REQUIRE(scale_rows > 0 && nseg == 1 && segs[0].col0 == 0 && gstride <= 1 && out_dtype == TDEED_BF16 &&
+                  (act == TDEED_ACT_NONE || act == TDEED_ACT_RELU) && (reinterpret_cast<uintptr_t>(a_scale) & 15) == 0,
+                  TDEED_ERR_UNSUPPORTED,
+                  "gemm_tc: the A-scale prologue needs one un-gathered segment starting at column 0, bf16 output, act none|relu");
+  }
 
   // M tiling
   long long frames = 0;
@@ -603,6 +660,9 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
     if (nb == block_n) break;
     block_n = nb;
   }
+  // (r2 negative result: narrower n-tiles for the N = K = 368 layers — a 98 KB W slice and a 6-stage instead of a 3-stage A
+  // ring — made them SLOWER, 160 -> 180 us and 281 -> 387 us with the A-scale prologue: the third pass over A from L2 and the
+  // extra tiles cost more than the deeper ring buys.)
   p.n_tiles = ceil_div(N, block_n);
   p.block_n = block_n;
   uint32_t cols = 32;
@@ -679,7 +739,7 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
   p.staged = force_staged ? atoi(force_staged) : (!direct_wins && residual == nullptr && N >= 96 ? 1 : 0);
   if (p.w_res && big_slice) p.staged = 0;
   const size_t stage_out_bytes = p.staged ? (size_t)TC_BM * ((size_t)block_n * (out_dtype == TDEED_F32 ? 4 : 2) + 16) : 0;
-  const size_t fixed = 1024 + p.w_res_bytes + (2 * TC_MAX_STAGES + 6) * sizeof(uint64_t) + bias_bytes + 2 * TC_BM * sizeof(long long) + stage_out_bytes;
+  const size_t fixed = 1024 + p.w_res_bytes + (3 * TC_MAX_STAGES + 6) * sizeof(uint64_t) + bias_bytes + 2 * TC_BM * sizeof(long long) + stage_out_bytes;
   TDEED_REQUIRE(fixed + 2 * stage_bytes <= 227 * 1024, TDEED_ERR_UNSUPPORTED, "gemm_tc: N=%d too wide for the bias staging area", N);
   // a second output staging tile saves one CTA-wide barrier per tile; take it when >= 3 ring stages still fit
   p.out_bufs = (fixed + stage_out_bytes + 3 * stage_bytes <= 227 * 1024) ? 2 : 1;
@@ -692,6 +752,7 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     TDEED_REQUIRE(e == cudaSuccess, TDEED_ERR_CUDA, "gemm_tc: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     attr_set = true;
   }
@@ -705,6 +766,11 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
             M, N, K, nseg, p.gather, residual != nullptr, act, block_n, p.n_tiles, p.w_res, stages, p.staged, p.out_bufs, p.fast, grid, smem);
   static int epi16_env = -1;
   if (epi16_env < 0) { const char* e = tdeed::dev_env("TDEED_GEMM_EPI16"); epi16_env = e ? atoi(e) : 0; }
+  if (a_scale) {
+    TDEED_REQUIRE(p.fast, TDEED_ERR_UNSUPPORTED, "gemm_tc: the A-scale prologue needs the specialised bf16 epilogue (N tile <= 256)");
+    gemm_tc_kernel<3><<<grid, TC_THREADS_SC, smem, st>>>(maps[0], maps[1], maps[2], p);
+    return check_launch("tdeed_gemm_scaled_fwd(tcgen05)");
+  }
   if (p.fast && !p.staged && epi16_env) gemm_tc_kernel<2><<<grid, TC_THREADS16, smem, st>>>(maps[0], maps[1], maps[2], p);
   else if (p.fast) gemm_tc_kernel<1><<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], p);
   else gemm_tc_kernel<0><<<grid, TC_THREADS, smem, st>>>(maps[0], maps[1], maps[2], p);

@@ -212,7 +212,7 @@ static size_t part_floats(int c) {
 extern "C" long long tdeed_se_workspace_floats(int n, int c) { return 2LL * n * c; }
 
 static int se_forward(int dtype, const void* x, void* out, int n, int hw, int c, int rd, const float* w1, const float* b1,
-                      const float* w2, const float* b2, float* workspace, void* stream) {
+                      const float* w2, const float* b2, float* workspace, void* stream, bool apply = true) {
   using namespace tdeed;
   TDEED_REQUIRE(x && w1 && b1 && w2 && b2 && workspace, TDEED_ERR_SHAPE, "tdeed_se_fwd: null pointer");
   TDEED_REQUIRE(n > 0 && hw > 0 && c > 0 && c % 8 == 0 && c <= 2048 && rd > 0 && rd <= 1024, TDEED_ERR_SHAPE,
@@ -235,7 +235,7 @@ static int se_forward(int dtype, const void* x, void* out, int n, int hw, int c,
   int rc = check_launch("tdeed_se_fwd(mean)");
   if (rc) return rc;
   rc = se_fc_dispatch(mean, n, c, rd, w1, b1, w2, b2, scale, st);
-  if (rc) return rc;
+  if (rc || !apply) return rc;
   if (dtype == TDEED_BF16)
     se_scale_kernel<__nv_bfloat16><<<scale_grid, SE_THREADS, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, total8, hw * (c / 8), c / 8, c, scale);
   else
@@ -246,6 +246,13 @@ static int se_forward(int dtype, const void* x, void* out, int n, int hw, int c,
 extern "C" int tdeed_se_fwd(int dtype, void* x, int n, int hw, int c, int rd, const float* w1, const float* b1,
                             const float* w2, const float* b2, float* workspace, void* stream) {
   return se_forward(dtype, x, x, n, hw, c, rd, w1, b1, w2, b2, workspace, stream);
+}
+
+// gate only: mean + fc; the per-(frame, channel) gate lands in workspace[n*c, 2*n*c) and is applied by the consumer
+// (tdeed_gemm_scaled_fwd folds it into conv3's A operand: no read-modify-write pass over the activation)
+extern "C" int tdeed_se_gate_fwd(int dtype, const void* x, int n, int hw, int c, int rd, const float* w1, const float* b1,
+                                 const float* w2, const float* b2, float* workspace, void* stream) {
+  return se_forward(dtype, x, nullptr, n, hw, c, rd, w1, b1, w2, b2, workspace, stream, false);
 }
 
 // training: out-of-place (the unscaled activation is needed by the backward pass); workspace keeps the per-frame means

@@ -56,6 +56,8 @@ SIGNATURES = {
     'tdeed_conv3x3g_tc_fwd': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp]),
     'tdeed_se_workspace_floats': (c_ll, [c_int, c_int]),
     'tdeed_se_fwd': (c_int, [c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'tdeed_se_gate_fwd': (c_int, [c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    'tdeed_gemm_scaled_fwd': (c_int, [c_ll, c_int, c_int, c_vp, c_ll, c_vp, c_int, c_vp, c_vp, c_vp, c_ll, c_int, c_vp, c_ll, c_vp]),
     'tdeed_gsf_workspace_floats': (c_ll, [c_int, c_int, c_int, c_int, c_int]),
     'tdeed_gsf_fwd': (c_int, [c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
                               c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),

@@ -94,6 +94,7 @@ class InferenceEngine:
         self.conv3_tc = True             # bf16: grouped 3x3 conv on tcgen05
         self.fuse_ds0 = True             # bf16: s1.b1 shortcut conv as a second K-segment of conv3's GEMM
         self.stem_v2 = True              # bf16 + uint8 frames: raw-pixel shifted-descriptor stem (stem_tc2.cu)
+        self.fuse_se = True              # bf16: SE gate folded into conv3's A operand (stages 3-4)
         self._graphs = {}
         self.load_state(state)
 
@@ -355,8 +356,19 @@ class InferenceEngine:
         else:
             a2 = self._op('conv3x3g', 2.0 * mo * cout * 9 * blk['gw'], (m + mo) * cout * es + cout * 9 * blk['gw'] * 4,
                           ops.conv3x3g, a1, blk['w2'], blk['b2'], blk['gw'], stride)
-        self._op('se', 4.0 * n * cout * blk['se_w1'].shape[0], 2 * mo * cout * es,
-                 ops.se_, a2, blk['se_w1'], blk['se_b1'], blk['se_w2'], blk['se_b2'])
+        # squeeze-excite.  K > 64 layers on the tcgen05 path (stages 3-4): only the gate is computed here (mean + fc) and conv3's
+        # GEMM applies it to its A operand in shared memory — no read-modify-write pass over a2.  Elsewhere: in place.
+        # (measured, 57-clip batch: N = K = 152 conv3 222 + 117 us (se_scale) -> 260 us fused; N = K = 368: 176 + 72 -> 281 us, a
+        # loss — two n-tiles scale every A block twice behind a 3-stage ring — so the fold is taken for one-n-tile layers only)
+        fold_se = (self.fuse_se and adt == torch.bfloat16 and self.gemm_backend in (L.GEMM_AUTO, L.GEMM_TCGEN05) and 64 < cout <= 256
+                   and cout % 8 == 0 and not (a1_fused is not None and 'w3d' in blk and self.fuse_ds0))
+        gate = None
+        if fold_se:
+            gate = self._op('se', 4.0 * n * cout * blk['se_w1'].shape[0], mo * cout * es,
+                            ops.se_gate, a2, blk['se_w1'], blk['se_b1'], blk['se_w2'], blk['se_b2'], _n=2)
+        else:
+            self._op('se', 4.0 * n * cout * blk['se_w1'].shape[0], 2 * mo * cout * es,
+                     ops.se_, a2, blk['se_w1'], blk['se_b1'], blk['se_w2'], blk['se_b2'], _n=3)
         if a1_fused is not None and 'w3d' in blk and self.fuse_ds0:
             x = self._gemm([(a2.view(mo, cout), cout, 0, cout), (x_sub.view(mo, 32), 32, 0, 32)], blk['w3d'], blk['b3d'],
                            label='conv1x1', act=L.ACT_RELU, rows=mo).view(n, oh, ow, cout)
@@ -369,8 +381,14 @@ class InferenceEngine:
                                  gather=(stride, h, w) if stride > 1 else None)
             else:
                 res = x.view(mo, cout)
-            x = self._gemm([(a2.view(mo, cout), cout, 0, cout)], blk['w3'], blk['b3'], label='conv1x1', residual=res,
-                           act=L.ACT_RELU, rows=mo).view(n, oh, ow, cout)
+            if gate is not None:
+                es3 = blk['w3'].element_size()
+                x = self._op('conv1x1', 2.0 * mo * cout * cout, (mo * cout * 3 + cout * cout) * es3,
+                             ops.gemm_scaled, a2.view(mo, cout), gate, oh * ow, blk['w3'], blk['b3'], residual=res,
+                             act=L.ACT_RELU).view(n, oh, ow, cout)
+            else:
+                x = self._gemm([(a2.view(mo, cout), cout, 0, cout)], blk['w3'], blk['b3'], label='conv1x1', residual=res,
+                               act=L.ACT_RELU, rows=mo).view(n, oh, ow, cout)
         if taps is not None:
             taps['s%d.b%d' % (self._stage_of(bi))] = x
         return x

@@ -139,6 +139,30 @@ def se_(x, w1, b1, w2, b2):
     return x
 
 
+def se_gate(x, w1, b1, w2, b2):
+    """Squeeze-excite gate of x NHWC (n,h,w,c): returns the fp32 gate [n, c] (x is NOT modified); the consumer applies it
+    (gemm_scaled)."""
+    n, h, w, c = x.shape
+    ws = torch.empty(int(L.load().tdeed_se_workspace_floats(n, c)), dtype=torch.float32, device=x.device)
+    L.check(L.load().tdeed_se_gate_fwd(L.dtype_code(x.dtype), L.ptr(x), n, h * w, c, w1.shape[0], L.ptr(w1), L.ptr(b1),
+                                       L.ptr(w2), L.ptr(b2), L.ptr(ws), L.stream()), 'se_gate')
+    return ws[n * c:].view(n, c)
+
+
+def gemm_scaled(a, gate, rows_per_gate, weight, bias=None, residual=None, act=L.ACT_NONE, out=None):
+    """out[M,N] = act((a * gate[row // rows_per_gate]) @ weight.T + bias + residual): conv3 with the SE gate folded into its
+    A operand (bf16 tcgen05 kernel).  a: [M, K] bf16; gate: [M / rows_per_gate, K] fp32."""
+    m, k = a.shape
+    n_out = weight.shape[0]
+    assert a.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16 and gate.dtype == torch.float32 and gate.is_contiguous()
+    if out is None:
+        out = torch.empty((m, n_out), dtype=torch.bfloat16, device=a.device)
+    L.check(L.load().tdeed_gemm_scaled_fwd(m, n_out, k, L.ptr(a), a.stride(0), L.ptr(gate), rows_per_gate, L.ptr(weight), L.ptr(bias),
+                                           L.ptr(residual), residual.stride(-2) if residual is not None else 0, act, L.ptr(out),
+                                           out.stride(0), L.stream()), 'gemm_scaled')
+    return out
+
+
 def gsf_workspace_floats(clips, clip_len, h, w, fold):
     return int(L.load().tdeed_gsf_workspace_floats(clips, clip_len, h, w, fold))
 

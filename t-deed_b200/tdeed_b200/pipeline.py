@@ -366,12 +366,15 @@ class ThreadedFrameSource:
     the DMA engine.  A torch DataLoader moved the same bytes at ~4 GB/s (worker process -> shm -> pin thread), below what one
     B200 consumes.  A slot is recycled only after the upload that read it has completed (event on `stream`)."""
 
-    def __init__(self, pieces, stream, workers=8, depth=24):
-        import queue
+    def __init__(self, pieces, stream, workers=8, depth=24, slots=None):
+        """slots: a list (kept by the caller across runs) that holds the pinned buffers, so that they are allocated once
+        (cudaHostAlloc of a 400 MB ring costs more than a whole video's inference)."""
         import threading
         self.pieces, self.stream, self.n = pieces, stream, len(pieces)
         self.depth = max(depth, workers + 2)
-        self._slots = [None] * self.depth
+        if slots is not None and len(slots) < self.depth:
+            slots.extend([None] * (self.depth - len(slots)))
+        self._slots = slots if slots is not None else [None] * self.depth
         self._events = [None] * self.depth
         self._done = {}
         self._cv = threading.Condition()

@@ -358,7 +358,7 @@ def _stream_scores(model, dataset, mine, augment, k, dev):
                                                                  flips=(False, True) if augment else (False,), clip_len=T)}
         vi = impl.__dict__['_video_inference'][key]
     # frames are decoded by worker threads straight into pinned buffers (tdeed_b200.pipeline.ThreadedFrameSource)
-    source = ThreadedFrameSource(pieces, vi.stream, workers=STREAM_WORKERS)
+    source = ThreadedFrameSource(pieces, vi.stream, workers=STREAM_WORKERS, slots=vi.__dict__.setdefault('_host_slots', []))
     with torch.no_grad():
         return vi.run(vlist, tqdm(source, total=len(pieces)))
 
@@ -416,6 +416,10 @@ def evaluate(model, dataset, split, classes, save_pred=None, printed=True, test=
             counts[c[0]] = counts.get(c[0], 0) + 1
         mine = shard_videos(counts.items(), rank, ws)
         videos = [v for v in videos if v[0] in mine]
+    if os.environ.get('TDEED_EVAL_TIMING') == '1':
+        import time
+        torch.cuda.synchronize()
+        _t0 = time.perf_counter()
     try:
         if _is_native(model) and _streamable(dataset):
             scores = _stream_scores(model, dataset, mine, augment, k, dev)
@@ -426,9 +430,26 @@ def evaluate(model, dataset, split, classes, save_pred=None, printed=True, test=
     finally:
         if all_clips is not None:
             dataset._clips = all_clips
+    if os.environ.get('TDEED_EVAL_TIMING') == '1':
+        torch.cuda.synchronize()
+        print('[util.eval] %-28s %.1f ms' % ('clip scores (network)', (time.perf_counter() - _t0) * 1e3), file=sys.stderr)
 
+    timing = os.environ.get('TDEED_EVAL_TIMING') == '1'
+    if timing:
+        import time
+        torch.cuda.synchronize()
+        _t = [time.perf_counter()]
+
+        def lap(what):
+            torch.cuda.synchronize()
+            _t.append(time.perf_counter())
+            print('[util.eval] %-28s %.1f ms' % (what, (_t[-1] - _t[-2]) * 1e3), file=sys.stderr)
+    else:
+        def lap(what):
+            pass
     fps = {video: f for video, _, f in videos}
     results = [_VideoEvents(video, fps[video], scores[video], 0.01) for video in sorted(scores)]
+    lap('event extraction')
 
     def gathered(lists):
         return gather_video_results(lists) if ws > 1 else lists
@@ -444,7 +465,9 @@ def evaluate(model, dataset, split, classes, save_pred=None, printed=True, test=
     from util.score import compute_mAPs
     if not test:
         nms = nms_lists(windows[0], 0.10, False)
+        lap('NMS + event lists')
         mAPs, _ = compute_mAPs(dataset.labels, nms, tolerances=tolerances, printed=True)
+        lap('compute_mAPs')
         return np.mean(mAPs)
 
     from util.io import store_json, store_json_snb, store_json_sn

@@ -330,3 +330,44 @@ def test_heads_softmax_scatter(dev):
     d = torch.tensor([[0.5, 1.5, 2.5, -0.5, -1.5, 60.0, -60.0, 0.49]])
     got, ref = ops.softmax_scatter(lg.to(dev), d.to(dev), 3).cpu(), O.scatter_max_probs(lg, d)
     assert torch.equal(got == 0, ref == 0) and float((got - ref).abs().max()) < 1e-6
+
+
+@pytest.mark.parametrize('frames,hw,k,n,with_res', [(40, 49, 368, 368, True), (23, 196, 152, 152, True), (9, 196, 152, 368, False),
+                                                     (7, 30, 96, 88, True), (300, 49, 368, 368, True)])
+def test_gemm_scaled_equals_scale_then_gemm(dev, frames, hw, k, n, with_res):
+    """SE gate folded into conv3's A operand (tdeed_gemm_scaled_fwd) == stand-alone bf16(a * gate) followed by the plain
+    tcgen05 GEMM, BIT FOR BIT (same fp32 multiply, same round-to-nearest bf16, same MMA order)."""
+    from tdeed_b200 import ops, _lib as L
+    g = torch.Generator().manual_seed(frames + k)
+    m = frames * hw
+    a = torch.randn(m, k, generator=g).to(torch.bfloat16).to(dev)
+    gate = torch.rand(frames, k, generator=g).to(dev)
+    w = (torch.randn(n, k, generator=g) / k ** 0.5).to(torch.bfloat16).to(dev)
+    bias = torch.randn(n, generator=g).to(dev)
+    res = torch.randn(m, n, generator=g).to(torch.bfloat16).to(dev) if with_res else None
+    scaled = (a.float() * gate.repeat_interleave(hw, dim=0)).to(torch.bfloat16)
+    want = ops.gemm([(scaled, k, 0, k)], w, bias, residual=res, act=L.ACT_RELU, rows=m, backend=L.GEMM_TCGEN05)
+    got = ops.gemm_scaled(a, gate, hw, w, bias, residual=res, act=L.ACT_RELU)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want), float((got.float() - want.float()).abs().max())
+    ref = torch.relu(scaled.float() @ w.float().t() + bias + (res.float() if with_res else 0))
+    assert rel_err(got.float(), ref) < GEMM_TOL_BF16_OUT
+
+
+def test_engine_fused_se_gate_is_bit_identical_to_in_place_se(dev):
+    from argparse import Namespace
+    from model.model import TDEEDModel
+    cfg = O.Config(feature_arch='rny002_gsf', clip_len=8, n_layers=2, sgp_ks=5, sgp_r=2, num_classes=4, radi_displacement=1, crop_dim=None)
+    args = Namespace(modality='rgb', temporal_arch='ed_sgp_mixer', radi_displacement=1, feature_arch=cfg.feature_arch, clip_len=8,
+                     n_layers=2, sgp_ks=5, sgp_r=2, num_classes=4, crop_dim=None)
+    m = TDEEDModel(device='cuda', args=args)
+    m.load(O.random_state(cfg, 2))
+    m._model.eval()
+    eng = m._model.engine('bf16')
+    frames = torch.randint(0, 256, (3, 8, 3, 64, 96), generator=torch.Generator().manual_seed(1), dtype=torch.uint8).to(dev)
+    eng.fuse_se = True
+    a = [t.clone() if t is not None else None for t in eng.forward(frames)]
+    eng.fuse_se = False
+    b = eng.forward(frames)
+    for x, y in zip(a, b):
+        assert (x is None and y is None) or torch.equal(x, y)
