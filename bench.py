@@ -392,10 +392,18 @@ def main():
         vi.use_graphs = False
         step_device()
         torch.cuda.synchronize()
+        eng.prof = []
         torch.cuda.cudart().cudaProfilerStart()
         step_device()
         torch.cuda.synchronize()
         torch.cuda.cudart().cudaProfilerStop()
+        # launch-ordered family labels of the GEMM launches (one kernel launch per entry): tools/traffic_from_ncu.py joins them
+        # with ncu's per-launch DRAM bytes
+        os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+        json.dump({'precision': args.precision, 'clips_per_batch': B, 'path': args.path, 'clips_per_step': n_clips,
+                   'gemm_launches': [(lab, nb) for lab, _, nb, _, _ in eng.prof if lab in ('conv1x1', 'conv1x1_ds', 'sgp_gemm')],
+                   'all_ops': [(lab, nb) for lab, _, nb, _, _ in eng.prof]},
+                  open(os.path.join(ROOT, 'gpurun_out', 'profile_step_labels.json'), 'w'))
         return
     sampler = ClockSampler(local)
     if rank == 0:

@@ -242,16 +242,28 @@ sgp_mix_kernel(const float* __restrict__ x, int t_in, int T, int C, int ks, int 
   for (int k = tr; k < ks; k += SG_RG) s_wp[k * SG_CB + cl] = cok ? w.psi_w[(size_t)c * ks + k] : 0.f;
   if (tr == 0) s_phi[cl] = cok ? phi_gate(colpart + (size_t)b * nrb * C, nrb, C, c, T, lnw, lnb, w.gfc_w[c], w.gfc_b[c]) : 0.f;
   __syncthreads();
-  for (int r = tr; r < rows; r += SG_RG) {
-    const int ws = s_ws[r], we = s_we[r];
-    float ln = 0.f;
-    if (cok && we > ws) {
-      float xv = xb[(size_t)ws * C + c];
-      for (int q = ws + 1; q < we; ++q) xv = fmaxf(xv, xb[(size_t)q * C + c]);
-      ln = fmaf((xv - s_rm[r]) * s_rr[r], lnw, lnb);
-      if (r >= h && r < h + SG_TT) s_xp[(r - h) * SG_CB + cl] = xv;
+  // (32-bit offsets: a clip has < 2^31 elements.  The first version of this loop — 64-bit row * C products and the generic
+  // pooling loop unrolled by the compiler — was 385 SASS instructions per row and 3/4 of the kernel's issue slots: ncu r2.)
+  {
+    const float* xc = xb + c;
+    float* dst = s_ln + tr * SG_CB + cl;
+#pragma unroll 2
+    for (int r = tr; r < rows; r += SG_RG, dst += SG_RG * SG_CB) {
+      const int ws = s_ws[r], nw = s_we[r] - ws;
+      float ln = 0.f;
+      if (cok && nw > 0) {
+        const float* px = xc + ws * C;
+        float xv = px[0];
+        if (nw > 1) {
+          xv = fmaxf(xv, px[C]);
+#pragma unroll 1
+          for (int q = 2; q < nw; ++q) xv = fmaxf(xv, px[q * C]);
+        }
+        ln = fmaf((xv - s_rm[r]) * s_rr[r], lnw, lnb);
+        if (r >= h && r < h + SG_TT) s_xp[(r - h) * SG_CB + cl] = xv;
+      }
+      *dst = ln;
     }
-    s_ln[r * SG_CB + cl] = ln;
   }
   __syncthreads();
 
@@ -262,7 +274,10 @@ sgp_mix_kernel(const float* __restrict__ x, int t_in, int T, int C, int ks, int 
   for (int r = 0; r < SG_RT; ++r) { am[r] = bm; ap[r] = bp; }
   dw_window(s_ln + (size_t)rl * SG_CB + cl, s_wm + cl, up, am);                       // taps t-h .. t+h
   dw_window(s_ln + (size_t)(rl + h - hp) * SG_CB + cl, s_wp + cl, ks, ap);            // taps t-hp .. t+hp
-  double dsum = 0.0, dsq = 0.0;
+  float* yb = y + (size_t)b * T * C;
+  // GroupNorm partials: fp32 over the thread's 8 rows, double from there on (fp64 issue is scarce on this part: per-element
+  // double arithmetic made the whole kernel FP64-bound — 250 issue slots per element, ncu r2)
+  float fsum = 0.f, fsq = 0.f;
   if (cok) {
     const float fcw = w.fc_w[c], fcb = w.fc_b[c], phi = s_phi[cl];
 #pragma unroll
@@ -271,14 +286,14 @@ sgp_mix_kernel(const float* __restrict__ x, int t_in, int T, int C, int ks, int 
       if (t < T) {
         const float ln = s_ln[(size_t)(h + rl + r) * SG_CB + cl];
         const float yv = s_xp[(rl + r) * SG_CB + cl] + (fmaf(fcw, ln, fcb) * phi + am[r] * ap[r] + ln);
-        y[((size_t)b * T + t) * C + c] = yv;
-        dsum += (double)yv;
-        dsq += (double)yv * (double)yv;
+        yb[t * C + c] = yv;
+        fsum += yv;
+        fsq = fmaf(yv, yv, fsq);
       }
     }
   }
-  s_gn[(tr * SG_CB + cl) * 2] = dsum;
-  s_gn[(tr * SG_CB + cl) * 2 + 1] = dsq;
+  s_gn[(tr * SG_CB + cl) * 2] = (double)fsum;
+  s_gn[(tr * SG_CB + cl) * 2 + 1] = (double)fsq;
   __syncthreads();
   if (tr == 0 && cok) {
     double a = 0.0, q = 0.0;
@@ -430,19 +445,24 @@ sgp_mixer_kernel(const float* __restrict__ xc, const float* __restrict__ skip, i
   if (tr == 0) s_phi[cl] = cok ? phi_gate(colpart_z + (size_t)b * nrb_z * C, nrb_z, C, c, T, l1w, l1b, w.gfc1_w[c], w.gfc1_b[c]) : 0.f;
   if (tr == 1) s_phi[SG_CB + cl] = cok ? phi_gate(colpart_x + (size_t)b * nrb_x * C, nrb_x, C, c, T, l2w, l2b, w.gfc2_w[c], w.gfc2_b[c]) : 0.f;
   __syncthreads();
-  for (int r = tr; r < rows; r += SG_RG) {
-    const int i0 = s_i0[r];
-    float zv = 0.f, uv = 0.f;
-    if (cok && i0 >= 0) {
-      const int t = t0 - h + r;
-      zv = fmaf((zb[(size_t)t * C + c] - s_zm[r]) * s_zr[r], l1w, l1b);
-      const float a0 = fmaf((xb[(size_t)i0 * C + c] - s_x0m[r]) * s_x0r[r], l2w, l2b);
-      const float a1 = fmaf((xb[(size_t)s_i1[r] * C + c] - s_x1m[r]) * s_x1r[r], l2w, l2b);
-      const float l1 = s_l1[r];
-      uv = (1.f - l1) * a0 + l1 * a1;
+  {
+    const float* zc = zb + c;
+    const float* xcc = xb + c;
+#pragma unroll 2
+    for (int r = tr; r < rows; r += SG_RG) {
+      const int i0 = s_i0[r];
+      float zv = 0.f, uv = 0.f;
+      if (cok && i0 >= 0) {
+        const int t = t0 - h + r;
+        zv = fmaf((zc[t * C] - s_zm[r]) * s_zr[r], l1w, l1b);
+        const float a0 = fmaf((xcc[i0 * C] - s_x0m[r]) * s_x0r[r], l2w, l2b);
+        const float a1 = fmaf((xcc[s_i1[r] * C] - s_x1m[r]) * s_x1r[r], l2w, l2b);
+        const float l1 = s_l1[r];
+        uv = (1.f - l1) * a0 + l1 * a1;
+      }
+      s_z[r * SG_CB + cl] = zv;
+      s_u[r * SG_CB + cl] = uv;
     }
-    s_z[r * SG_CB + cl] = zv;
-    s_u[r * SG_CB + cl] = uv;
   }
   __syncthreads();
 
@@ -502,19 +522,20 @@ sgp_gnpart_kernel(const float* __restrict__ x, int T, int C, double* __restrict_
   const int b = blockIdx.z, c0 = blockIdx.y * SG_CB, t0 = blockIdx.x * SG_TT;
   const int cl = threadIdx.x % SG_CB, tr = threadIdx.x / SG_CB;
   const int c = c0 + cl;
-  double a = 0.0, q = 0.0;
+  float a = 0.f, q = 0.f;
   if (c < C) {
+#pragma unroll
     for (int r = 0; r < SG_RT; ++r) {
       const int t = t0 + tr * SG_RT + r;
       if (t < T) {
-        const double v = (double)x[((size_t)b * T + t) * C + c];
+        const float v = x[((size_t)b * T + t) * C + c];
         a += v;
-        q += v * v;
+        q = fmaf(v, v, q);
       }
     }
   }
-  s_gn[(tr * SG_CB + cl) * 2] = a;
-  s_gn[(tr * SG_CB + cl) * 2 + 1] = q;
+  s_gn[(tr * SG_CB + cl) * 2] = (double)a;
+  s_gn[(tr * SG_CB + cl) * 2 + 1] = (double)q;
   __syncthreads();
   if (tr == 0 && c < C) {
     double sa = 0.0, sq = 0.0;

@@ -37,8 +37,9 @@ def main():
         f['dram_bytes_per_launch'] = (f['dram_read_bytes'] + f['dram_write_bytes']) / f['launches']
         f['alg_bytes_per_launch'] = f['alg_bytes'] / f['launches']
     json.dump(dict(source='ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum --clock-control none over one eager batch '
-                          '(tools/profile_step.py), FigureSkatingComp_small %s' % meta['precision'],
-                   clips_per_batch=meta['clips_per_batch'], families=fam), open(out, 'w'), indent=1)
+                          '(bench.py --ncu-step: one 169-clip video), FigureSkatingComp_small %s' % meta['precision'],
+                   clips_per_batch=meta['clips_per_batch'], path=meta.get('path', 'engine'), clips_per_step=meta.get('clips_per_step'),
+                   families=fam), open(out, 'w'), indent=1)
     for k, f in fam.items():
         print(k, f['launches'], 'dram/launch %.1f MB' % (f['dram_bytes_per_launch'] / 1e6), 'alg/launch %.1f MB' % (f['alg_bytes_per_launch'] / 1e6))
 
