@@ -36,6 +36,7 @@ struct C3TParams {
   int min_off, npos, npos_pad;
   int nchunks_real, pairs_total, pairs_blk;
   uint32_t tmem_cols;
+  int wide_st;               // output rows are 32-byte aligned (C * 2 % 32 == 0): 256-bit stores
 };
 
 __device__ __forceinline__ uint32_t c3_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -261,11 +262,11 @@ conv3x3g_tc_kernel(const C3TParams p) {
       for (int pp = 0; pp < np; pp += 2) {
         c3_ld_wait();
         if (pp + 1 < np) c3_ld16_nowait(tmem_lane + (uint32_t)(pp + 1) * 16u, vb);
-        epi_fast_chunk<false, false>(va, zero4, zero4, s_bias, pp * 16, ncols, lo, 0u, grow);
+        epi_fast_chunk<false, false>(va, zero4, zero4, s_bias, pp * 16, ncols, lo, 0u, grow, p.wide_st != 0);
         if (pp + 1 < np) {
           c3_ld_wait();
           if (pp + 2 < np) c3_ld16_nowait(tmem_lane + (uint32_t)(pp + 2) * 16u, va);
-          epi_fast_chunk<false, false>(vb, zero4, zero4, s_bias, (pp + 1) * 16, ncols, lo, 0u, grow);
+          epi_fast_chunk<false, false>(vb, zero4, zero4, s_bias, (pp + 1) * 16, ncols, lo, 0u, grow, p.wide_st != 0);
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -324,6 +325,7 @@ static int conv3x3g_tc_run(const void* in, int n, int h, int w, int c, int strid
   TDEED_REQUIRE(nt < (1LL << 31), TDEED_ERR_SHAPE, "tdeed_conv3x3g_tc_fwd: too many tiles");
   p.ntiles = (int)nt;
   p.nchunks_real = c / 8;
+  p.wide_st = ((c * 2) % 32 == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0) ? 1 : 0;
   p.pairs_total = (c + 15) / 16;
   // channel pairs per CTA: at most 8 (128 channels), fewer when the staged window of a wide frame would not fit
   const size_t per_pair = (size_t)9 * 512 + 2 * (size_t)p.nplanes * 2 * p.npos_pad * 16 + 64;     // two input buffers

@@ -13,14 +13,28 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   return v;
 }
 
+// 256-bit global store / load (sm_100: STG.E.ENL2.256 / LDG.E.ENL2.256); the address must be 32-byte aligned
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
+               "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+
 // One 16-column accumulator piece of one row -> + bias (+ bf16 residual), clamp at `lo` (0 = ReLU, -inf = none), bf16, store.
 // Straight-line code (no runtime dtype / activation switches), so the 8-column groups interleave in the schedule.
+// wide (kernel-uniform): every row piece is 32-byte aligned (row pitch and column origin multiples of 32 B): the 16 columns
+// leave as ONE 256-bit store — half the store instructions and L2 write requests of the two 16-byte row pieces.
 template <bool STAGED, bool HAS_RES = true>
 __device__ __forceinline__ void epi_fast_chunk(const uint32_t (&acc)[16], const uint4& r0, const uint4& r1, const float* __restrict__ bias,
-                                               int c0, int ncols, float lo, uint32_t srow_addr, __nv_bfloat16* grow) {
+                                               int c0, int ncols, float lo, uint32_t srow_addr, __nv_bfloat16* grow, bool wide = false) {
+  uint4 o2[2];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int cl = c0 + 8 * h;
+    o2[h] = make_uint4(0u, 0u, 0u, 0u);
     if (cl < ncols) {
       const float4 b0 = *reinterpret_cast<const float4*>(bias + cl);
       const float4 b1 = *reinterpret_cast<const float4*>(bias + cl + 4);
@@ -43,10 +57,12 @@ __device__ __forceinline__ void epi_fast_chunk(const uint32_t (&acc)[16], const 
       o.y = pack_bf16x2(fmaxf(v[2], lo), fmaxf(v[3], lo));
       o.z = pack_bf16x2(fmaxf(v[4], lo), fmaxf(v[5], lo));
       o.w = pack_bf16x2(fmaxf(v[6], lo), fmaxf(v[7], lo));
+      o2[h] = o;
       if (STAGED) sts128(srow_addr + (uint32_t)cl * 2u, o);
-      else if (grow) *reinterpret_cast<uint4*>(grow + cl) = o;
+      else if (grow && !(wide && c0 + 16 <= ncols)) *reinterpret_cast<uint4*>(grow + cl) = o;
     }
   }
+  if (!STAGED && wide && grow && c0 + 16 <= ncols) stg256(grow + c0, o2[0], o2[1]);
 }
 
 }  // namespace tdeed

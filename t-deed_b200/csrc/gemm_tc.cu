@@ -55,6 +55,8 @@ struct TcParams {
   // in shared memory, between the TMA load and the MMA
   const float* a_scale;
   int scale_rows, scale_ld, K;
+  int wide_ld;   // 1: residual row pieces are 32-byte aligned: 256-bit loads
+  int wide_st;   // 1: output row pieces are 32-byte aligned (ldo * 2 and the base multiples of 32): 256-bit stores
 };
 
 // ---------------------------------------------------------------- PTX wrappers
@@ -152,11 +154,17 @@ __device__ __forceinline__ void epi_fast_tile(const TcParams& p, uint64_t* full_
   uint4 rres[2][4];
   const bool has_res = p.residual != nullptr && row_ok;
   const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + m * p.ldr + n0;
+  const bool wide_ld = p.wide_ld != 0;
   auto load_res = [&](uint4 (&dst)[4], int c0) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      dst[q] = make_uint4(0u, 0u, 0u, 0u);
-      if (has_res && c0 + 8 * q < ncols) dst[q] = *reinterpret_cast<const uint4*>(rp + c0 + 8 * q);
+    for (int q = 0; q < 4; q += 2) {
+      dst[q] = dst[q + 1] = make_uint4(0u, 0u, 0u, 0u);
+      if (wide_ld && has_res && c0 + 8 * q + 16 <= ncols) {
+        ldg256(rp + c0 + 8 * q, dst[q], dst[q + 1]);
+      } else {
+        if (has_res && c0 + 8 * q < ncols) dst[q] = *reinterpret_cast<const uint4*>(rp + c0 + 8 * q);
+        if (has_res && c0 + 8 * q + 8 < ncols) dst[q + 1] = *reinterpret_cast<const uint4*>(rp + c0 + 8 * q + 8);
+      }
     }
   };
   load_res(rres[0], half * 32);
@@ -178,11 +186,11 @@ __device__ __forceinline__ void epi_fast_tile(const TcParams& p, uint64_t* full_
       tmem_ld_wait();
       if (s & 1) {
         if (s < 7 && cn < ncols) tmem_ld16(tmem_row + (uint32_t)cn, va);
-        epi_fast_chunk<STAGED>(vb, rres[k & 1][2], rres[k & 1][3], bias, c0, ncols, lo, srow_addr, grow);
+        epi_fast_chunk<STAGED>(vb, rres[k & 1][2], rres[k & 1][3], bias, c0, ncols, lo, srow_addr, grow, p.wide_st != 0);
         if (k < 2) load_res(rres[k & 1], c0 - 16 + 128);
       } else {
         if (cn < ncols) tmem_ld16(tmem_row + (uint32_t)cn, vb);
-        epi_fast_chunk<STAGED>(va, rres[k & 1][0], rres[k & 1][1], bias, c0, ncols, lo, srow_addr, grow);
+        epi_fast_chunk<STAGED>(va, rres[k & 1][0], rres[k & 1][1], bias, c0, ncols, lo, srow_addr, grow, p.wide_st != 0);
       }
     }
   }
@@ -195,11 +203,14 @@ __device__ __forceinline__ void epi_fast16_tile(const TcParams& p, uint64_t* ful
   const bool has_res = p.residual != nullptr && row_ok;
   const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.residual) + m * p.ldr + n0;
   uint4 r0[2], r1[2];
+  const bool wide_ld = p.wide_ld != 0;
   auto load_res = [&](uint4 (&dst)[2], int c0) {
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      dst[q] = make_uint4(0u, 0u, 0u, 0u);
-      if (has_res && c0 + 8 * q < ncols) dst[q] = *reinterpret_cast<const uint4*>(rp + c0 + 8 * q);
+    dst[0] = dst[1] = make_uint4(0u, 0u, 0u, 0u);
+    if (wide_ld && has_res && c0 + 16 <= ncols) {
+      ldg256(rp + c0, dst[0], dst[1]);
+    } else {
+      if (has_res && c0 < ncols) dst[0] = *reinterpret_cast<const uint4*>(rp + c0);
+      if (has_res && c0 + 8 < ncols) dst[1] = *reinterpret_cast<const uint4*>(rp + c0 + 8);
     }
   };
   load_res(r0, quarter * 16);
@@ -217,11 +228,11 @@ __device__ __forceinline__ void epi_fast16_tile(const TcParams& p, uint64_t* ful
       if (k & 1) {
         if (k < 3) load_res(r0, c0 + 64);
         tmem_ld_wait();
-        epi_fast_chunk<false>(v, r1[0], r1[1], bias, c0, ncols, lo, 0u, grow);
+        epi_fast_chunk<false>(v, r1[0], r1[1], bias, c0, ncols, lo, 0u, grow, p.wide_st != 0);
       } else {
         if (k < 3) load_res(r1, c0 + 64);
         tmem_ld_wait();
-        epi_fast_chunk<false>(v, r0[0], r0[1], bias, c0, ncols, lo, 0u, grow);
+        epi_fast_chunk<false>(v, r0[0], r0[1], bias, c0, ncols, lo, 0u, grow, p.wide_st != 0);
       }
     }
   }
@@ -626,6 +637,8 @@ int gemm_tc_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* se
   p.bias = bias; p.residual = residual; p.ldr = ldr; p.res_dtype = res_dtype; p.act = act;
   p.out = out; p.ldo = ldo; p.out_dtype = out_dtype;
   p.a_scale = a_scale; p.scale_rows = scale_rows; p.scale_ld = K; p.K = K;
+  p.wide_ld = (residual && res_dtype == TDEED_BF16 && (ldr * 2) % 32 == 0 && (reinterpret_cast<uintptr_t>(residual) & 31) == 0) ? 1 : 0;
+  p.wide_st = (out_dtype == TDEED_BF16 && (ldo * 2) % 32 == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0) ? 1 : 0;
   if (a_scale) {
     TDEED_REQUIRE(scale_rows > 0 && nseg == 1 && segs[0].col0 == 0 && gstride <= 1 && out_dtype == TDEED_BF16 &&
                   (act == TDEED_ACT_NONE || act == TDEED_ACT_RELU) && (reinterpret_cast<uintptr_t>(a_scale) & 15) == 0,

@@ -43,6 +43,7 @@ struct ThinParams {
   int out_dtype;
   uint32_t tmem_cols;
   int nacc_log2;   // log2 of the number of TMEM accumulators (2..8): thin tiles are cheap, the MMA warp may run that far ahead
+  int wide_st; // output rows 32-byte aligned: 256-bit stores
   int fast;    // specialised bf16 epilogue (act none|relu): pipelined TMEM loads, cross-tile residual prefetch
   int mma_pair; // staged tiles the MMA warp handles per proxy fence (1..4)
   int split;   // fast && N <= 32: the two epilogue warp halves take alternate tiles (otherwise half of them would idle)
@@ -308,11 +309,11 @@ gemm_thin_kernel(const ThinParams p) {
             th_ld_wait();
             if (s & 1) {
               if (s < 7 && cn < p.N) th_ld16_nowait(tmem_row + (uint32_t)cn, va);
-              epi_fast_chunk<false>(vb, rres[k & 1][2], rres[k & 1][3], s_bias, c0, p.N, lo, 0u, grow);
+              epi_fast_chunk<false>(vb, rres[k & 1][2], rres[k & 1][3], s_bias, c0, p.N, lo, 0u, grow, p.wide_st != 0);
               if (k >= 1 && k < 2) load_res(rres[k & 1], m, c0 - 16 + 128);       // chunk 3 (rres[1]); chunk 2 is loaded below
             } else {
               if (cn < p.N) th_ld16_nowait(tmem_row + (uint32_t)cn, vb);
-              epi_fast_chunk<false>(va, rres[k & 1][0], rres[k & 1][1], s_bias, c0, p.N, lo, 0u, grow);
+              epi_fast_chunk<false>(va, rres[k & 1][0], rres[k & 1][1], s_bias, c0, p.N, lo, 0u, grow, p.wide_st != 0);
             }
           }
           if (s == 1 && cbase + 128 < p.N) load_res(rres[0], m, cbase + 128);    // chunk 2 of this tile
@@ -455,6 +456,7 @@ int gemm_thin_launch(long long M, int N, int K, int nseg, const tdeed_gemm_seg* 
   static int fast_env = -1;
   if (fast_env < 0) { const char* e = tdeed::dev_env("TDEED_GEMM_FAST_EPI"); fast_env = e ? atoi(e) : 1; }
   p.fast = (fast_env && out_dtype == TDEED_BF16 && (act == TDEED_ACT_NONE || act == TDEED_ACT_RELU)) ? 1 : 0;
+  p.wide_st = (out_dtype == TDEED_BF16 && (ldo * 2) % 32 == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0) ? 1 : 0;
   p.split = (p.fast && N <= 32) ? 1 : 0;
   static int pair_env = -1;
   if (pair_env < 0) { const char* e = tdeed::dev_env("TDEED_THIN_MMA_PAIR"); pair_env = e ? atoi(e) : 2; }

@@ -21,6 +21,7 @@
 // concat with the untouched channels of x (tdeed_gemm_fwd segments).
 //
 // workspace layout (floats): gate [N*hw*2] | sums [N*fold*2] (y, r) | wgt [N*fold] | Q [N*hw*6]
+#include <type_traits>
 #include "common.cuh"
 
 namespace tdeed {
@@ -221,7 +222,8 @@ gsf_gate_kernel(const T* __restrict__ x, int clip_len, int hw, int c, int fold, 
 // ---- kernel 3: GSF fusion weights.  One CTA per frame, one thread per channel. ----
 __global__ void __launch_bounds__(GS_THREADS)
 gsf_weight_kernel(const float* __restrict__ sums, int clip_len, int hw, int fold, const float* __restrict__ cc_w,
-                  const float* __restrict__ cc_b, float* __restrict__ wgt) {
+                  const float* __restrict__ cc_b, float* __restrict__ wgt, int RB) {
+  // sums: [frame][RB row blocks][fold][2]; the row-block partials (tensor-core gate kernel) are added in block order
   const int f = blockIdx.x;
   const int t = f % clip_len;
   const int half = fold / 2;
@@ -238,9 +240,13 @@ gsf_weight_kernel(const float* __restrict__ sums, int clip_len, int hw, int fold
         if (tt < 0 || tt >= clip_len) continue;
         // plane 0: mean of the SHIFTED y at time tt (= y at tt+1 for g=0, tt-1 for g=1, zero outside the clip)
         const int ts = (g == 0) ? tt + 1 : tt - 1;
-        float ym = 0.f;
-        if (ts >= 0 && ts < clip_len) ym = sums[(((size_t)(f - t + ts)) * fold + g * half + cc) * 2] * inv;
-        const float rm = sums[(((size_t)(f - t + tt)) * fold + g * half + cc) * 2 + 1] * inv;
+        float ym = 0.f, rm = 0.f;
+        for (int r = 0; r < RB; ++r) {
+          if (ts >= 0 && ts < clip_len) ym += sums[((((size_t)(f - t + ts)) * RB + r) * fold + g * half + cc) * 2];
+          rm += sums[((((size_t)(f - t + tt)) * RB + r) * fold + g * half + cc) * 2 + 1];
+        }
+        ym *= inv;
+        rm *= inv;
         a = fmaf(wk[(dc + 1) * 3 + (dt + 1)], ym, a);
         a = fmaf(wk[9 + (dc + 1) * 3 + (dt + 1)], rm, a);
       }
@@ -300,6 +306,358 @@ gsf_blend_kernel(const T* __restrict__ x, int clip_len, int hw, int c, int fold,
   store8(out + (size_t)fp * ld_out + o8 * 8, o);
 }
 
+// ---- kernels 1+2 fused on tensor cores (bf16 inference): gate = tanh(conv3d(relu(bn(x)))) + the per-channel sums of y and r ----
+// The 3x3x3 gate convolution as an implicit GEMM on mma.sync m16n8k16 (bf16 operands, fp32 accumulate):
+//   rows   p' : the positions of the CTA's row block INCLUDING the two halo columns (R x (w+2)), 16 per MMA
+//   K         : the fold channels (padded to 16) of z = relu(bn(x)), staged pixel-major in shared memory (pitch = K*2+16 bytes:
+//               ldmatrix rows of consecutive positions fall into distinct 16-byte bank groups)
+//   N = 8     : (group g, horizontal tap dx) -> 6 columns; the weights of the other group's channels are zero
+//   P_dx[p']  = sum over (source frame dt, vertical tap dy, channel) of W[g][ch][dt][dy][dx] * z[t+dt-1][p' + dy*(w+2)][ch]
+// so the temporal and vertical taps are A-operand address offsets into the halo tile and only the horizontal tap is left as a
+// shift-add of three neighbouring P columns: gate[g][y][x] = tanh(b[g] + sum_dx P_dx[y*(w+2) + x + dx][g*3+dx]).
+// One CTA owns FT consecutive frames of a clip x R rows: the FT+2 staged frames are shared by its outputs (the CUDA-core
+// gsf_q_kernel + gsf_gate_kernel pair ran at 187/260/397 us for the rny002 layers, L1/issue-bound; no Q round trip here).
+constexpr int GT_THREADS = 256;                // 512 threads doubled the per-thread set-up work: 244M vs 164M instructions, slower
+constexpr int GT_SMEM_BUDGET = 110 * 1024;     // two CTAs per SM
+
+__device__ __forceinline__ void gt_ldmatrix_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void gt_mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// B fragments of the gate conv, one uint2 per (dt, dy, k-step, lane): [k = s*16 + (lane%4)*2 + {0,1} (+8)][n = lane/4]
+__global__ void gsf_pack_w_kernel(const float* __restrict__ w3d, int fold, int ks, uint2* __restrict__ wB) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 9 * ks * 32) return;
+  const int lane = idx & 31, s = (idx >> 5) % ks, tap = (idx >> 5) / ks;      // tap = dt*3 + dy
+  const int n = lane >> 2, kb = s * 16 + (lane & 3) * 2;
+  const int half = fold >> 1;
+  float v[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int ch = kb + (q & 1) + (q >> 1) * 8;
+    v[q] = 0.f;
+    if (n < 6 && ch < fold) {
+      const int g = n / 3, dx = n - g * 3;
+      if ((ch >= half ? 1 : 0) == g) v[q] = w3d[(size_t)ch * 27 + tap * 3 + dx];   // [g][ci][kt][dy][dx], ch = g*half + ci
+    }
+  }
+  wB[idx] = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+}
+
+constexpr int GT_NI = 8;                       // staged pieces per thread and frame (register-resident offsets)
+
+// KS = k-steps (fold padded to 16 channels per step); KS = 0: run-time `ks`
+template <int KS>
+__global__ void __launch_bounds__(GT_THREADS, 2)
+gsf_gate_tc_kernel(const __nv_bfloat16* __restrict__ x, int clip_len, int h, int w, int c, int fold, int ks_rt, int R, int FT, int MT,
+                   int z_bytes, const float* __restrict__ bn_scale, const float* __restrict__ bn_shift, const uint2* __restrict__ wB,
+                   const float* __restrict__ b3d, float* __restrict__ gate, float* __restrict__ sums_part, int RB) {
+  extern __shared__ __align__(128) unsigned char gt_smem[];
+  const int ks = KS ? KS : ks_rt;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wp = w + 2, hpx = (R + 2) * wp, hw = h * w;
+  const int foldp = ks * 16, pitch = foldp * 2 + 16, nchunk = foldp >> 3;
+  uint2* s_wB = reinterpret_cast<uint2*>(gt_smem);
+  unsigned char* s_z = gt_smem + 9 * ks * 256;
+  float* s_P = reinterpret_cast<float*>(s_z + z_bytes);
+  float2* s_gate = reinterpret_cast<float2*>(s_P + FT * MT * 128);
+  const int rb = blockIdx.x, b = blockIdx.z;
+  const int y0 = rb * R, t0 = blockIdx.y * FT;
+  const int nfo = min(FT, clip_len - t0);
+  const int rows = min(R, h - y0);
+  const size_t f0 = (size_t)b * clip_len + t0;          // first output frame
+  const uint32_t z_addr = (uint32_t)__cvta_generic_to_shared(s_z);
+  const uint32_t frame_bytes = (uint32_t)(hpx * pitch);
+
+  // ---- stage frames t0-1 .. t0+nfo, rows y0-1 .. y0+R, columns -1 .. w: raw x by cp.async (every 16-byte piece of the CTA is in
+  //      flight at once), zeros outside the image / the clip, then z = relu(bn(x)) in place on the pieces that hold pixels.
+  //      A thread visits the same <= GT_NI halo positions in every frame: their global offsets are computed once. ----
+  const int k = tid % nchunk, rl = tid / nchunk, rpp = GT_THREADS / nchunk;
+  const int ch0 = k * 8;
+  const bool chunk_ok = ch0 + 8 <= c;
+  unsigned gmask = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) gmask |= (unsigned)(ch0 + j >= (fold >> 1) ? 1 : 0) << j;
+  int off[GT_NI];                                       // element offset of the piece inside a frame; -1: zero padding; -2: none
+  const uint32_t zt = z_addr + (uint32_t)(rl * pitch + k * 16);
+  const uint32_t step = (uint32_t)(rpp * pitch);
+  if (rl < rpp) {
+    {
+      const int step_y = rpp / wp, step_x = rpp - step_y * wp;
+      int hy = rl / wp, hx = rl - hy * wp;
+#pragma unroll
+      for (int i = 0; i < GT_NI; ++i) {
+        const int py = y0 - 1 + hy, px = hx - 1;
+        off[i] = rl + i * rpp >= hpx ? -2 : ((chunk_ok && py >= 0 && py < h && px >= 0 && px < w) ? (py * w + px) * c + ch0 : -1);
+        hy += step_y; hx += step_x;
+        if (hx >= wp) { hx -= wp; ++hy; }
+      }
+    }
+    for (int fr = 0; fr < nfo + 2; ++fr) {
+      const int t = t0 - 1 + fr;
+      const bool fvalid = t >= 0 && t < clip_len;
+      const __nv_bfloat16* xf = x + ((size_t)b * clip_len + (fvalid ? t : 0)) * hw * c;
+      const uint32_t zf = zt + (uint32_t)fr * frame_bytes;
+#pragma unroll
+      for (int i = 0; i < GT_NI; ++i) {
+        if (off[i] >= 0 && fvalid) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(zf + (uint32_t)i * step), "l"(xf + off[i]) : "memory");
+        } else if (off[i] >= -1) {
+          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(zf + (uint32_t)i * step), "r"(0u) : "memory");
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  {                                                     // the packed weights ride in a second group of the same wait
+    const uint32_t wb_addr = (uint32_t)__cvta_generic_to_shared(s_wB);
+    for (int i = tid; i < 9 * ks * 16; i += GT_THREADS)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(wb_addr + (uint32_t)i * 16u), "l"(reinterpret_cast<const uint4*>(wB) + i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = ch0 + j;
+    sc[j] = ch < fold ? bn_scale[ch] : 0.f;              // pad channels: z = relu(0 * x + 0) = 0
+    sh[j] = ch < fold ? bn_shift[ch] : 0.f;
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");     // every thread: the weight pieces of the idle tail threads too
+  if (rl < rpp) {
+    for (int fr = 0; fr < nfo + 2; ++fr) {
+      const int t = t0 - 1 + fr;
+      if (t < 0 || t >= clip_len) continue;
+      const uint32_t zf = zt + (uint32_t)fr * frame_bytes;
+#pragma unroll
+      for (int i = 0; i < GT_NI; ++i) {
+        if (off[i] >= 0) {                               // this thread's own copy: visible after wait_group
+          uint32_t wv[4], o[4];
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(wv[0]), "=r"(wv[1]), "=r"(wv[2]), "=r"(wv[3]) : "r"(zf + (uint32_t)i * step));
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float lo = fmaxf(fmaf(__uint_as_float(wv[q] << 16), sc[2 * q], sh[2 * q]), 0.f);
+            const float hi = fmaxf(fmaf(__uint_as_float(wv[q] & 0xffff0000u), sc[2 * q + 1], sh[2 * q + 1]), 0.f);
+            o[q] = pack_bf16x2(lo, hi);
+          }
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(zf + (uint32_t)i * step), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+        }
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- implicit GEMM: a warp per (output frame, 16-position tile) ----
+  {
+    const uint32_t b_addr = (uint32_t)__cvta_generic_to_shared(s_wB) + (uint32_t)lane * 8u;
+    const uint32_t dy_bytes = (uint32_t)(wp * pitch);
+    for (int item = warp; item < nfo * MT; item += GT_THREADS / 32) {
+      const int fo = item / MT, mt = item - fo * MT;
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint32_t a_base = z_addr + (uint32_t)fo * frame_bytes + (uint32_t)((mt * 16 + (lane & 15)) * pitch) + (uint32_t)(lane >> 4) * 16u;
+#pragma unroll
+      for (int dt = 0; dt < 3; ++dt) {
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+          const uint32_t a_addr = a_base + (uint32_t)dt * frame_bytes + (uint32_t)dy * dy_bytes;
+          const uint32_t bq = b_addr + (uint32_t)((dt * 3 + dy) * ks) * 256u;
+          if (KS) {
+#pragma unroll
+            for (int s2 = 0; s2 < KS; ++s2) {
+              uint32_t a[4], b0, b1;
+              gt_ldmatrix_x4(a_addr + (uint32_t)s2 * 32u, a);
+              asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(bq + (uint32_t)s2 * 256u));
+              gt_mma16816(acc, a, b0, b1);
+            }
+          } else {
+#pragma unroll 2
+            for (int s2 = 0; s2 < ks; ++s2) {
+              uint32_t a[4], b0, b1;
+              gt_ldmatrix_x4(a_addr + (uint32_t)s2 * 32u, a);
+              asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(b0), "=r"(b1) : "r"(bq + (uint32_t)s2 * 256u));
+              gt_mma16816(acc, a, b0, b1);
+            }
+          }
+        }
+      }
+      float* P = s_P + item * 128 + (lane >> 2) * 8 + (lane & 3) * 2;
+      *reinterpret_cast<float2*>(P) = make_float2(acc[0], acc[1]);
+      *reinterpret_cast<float2*>(P + 64) = make_float2(acc[2], acc[3]);
+    }
+  }
+  __syncthreads();
+
+  // ---- gate = tanh(bias + horizontal shift-add) ----
+  {
+    const float bias0 = b3d[0], bias1 = b3d[1];
+    const int npx = rows * w;
+    for (int i = tid; i < nfo * npx; i += GT_THREADS) {
+      const int fo = i / npx, rem = i - fo * npx;
+      const int y = rem / w, xx = rem - y * w;
+      const float* P = s_P + fo * MT * 128 + (y * wp + xx) * 8;
+      const float a0 = bias0 + P[0] + P[8 + 1] + P[16 + 2];
+      const float a1 = bias1 + P[3] + P[8 + 4] + P[16 + 5];
+      const float2 g = make_float2(tanhf(a0), tanhf(a1));
+      *reinterpret_cast<float2*>(gate + ((f0 + fo) * hw + (size_t)y0 * w + rem) * 2) = g;
+      s_gate[fo * R * w + rem] = g;
+    }
+  }
+  __syncthreads();
+
+  // ---- spatial sums of y = gate*x and of x per (frame, channel) -> (sum y, sum r = sum x - sum y): a thread owns (frame, 8 channels,
+  //      pixel slice), the S slices of an output are added in a fixed order ----
+  {
+    float* s_part = reinterpret_cast<float*>(s_z);        // [nfo * S][foldp][2] (the z tile is dead)
+    const int npx = rows * w;
+    const int slots = nfo * nchunk;
+    const int S = GT_THREADS / slots;                     // >= 1: host keeps FT * nchunk <= GT_THREADS
+    const int slot = tid / S, sl = tid - slot * S;
+    if (slot < slots) {
+      const int fo = slot / nchunk, kk = slot - fo * nchunk;
+      const int c0 = kk * 8;
+      float sy[8], sx[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sy[j] = sx[j] = 0.f;
+      if (c0 + 8 <= c) {
+        const int half = fold >> 1;
+        const __nv_bfloat16* xf = x + ((f0 + fo) * hw + (size_t)y0 * w) * c + c0;
+        const float2* gs = s_gate + fo * R * w;
+        const bool lo_only = c0 + 8 <= half, hi_only = c0 >= half;
+        for (int p = sl; p < npx; p += 2 * S) {           // two pixels per round: both loads in flight
+          const int p1 = p + S;
+          const uint4 r0 = *reinterpret_cast<const uint4*>(xf + (uint32_t)(p * c));
+          uint4 r1 = make_uint4(0u, 0u, 0u, 0u);
+          float2 g1 = make_float2(0.f, 0.f);
+          if (p1 < npx) { r1 = *reinterpret_cast<const uint4*>(xf + (uint32_t)(p1 * c)); g1 = gs[p1]; }
+          const float2 g0 = gs[p];
+          const uint32_t w0[4] = {r0.x, r0.y, r0.z, r0.w}, w1[4] = {r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float v0 = (j & 1) ? __uint_as_float(w0[j >> 1] & 0xffff0000u) : __uint_as_float(w0[j >> 1] << 16);
+            const float v1 = (j & 1) ? __uint_as_float(w1[j >> 1] & 0xffff0000u) : __uint_as_float(w1[j >> 1] << 16);
+            const bool hi = hi_only || (!lo_only && c0 + j >= half);
+            sy[j] = fmaf(hi ? g0.y : g0.x, v0, sy[j]);
+            sx[j] += v0;
+            sy[j] = fmaf(hi ? g1.y : g1.x, v1, sy[j]);      // zeros when p1 is past the block
+            sx[j] += v1;
+          }
+        }
+      }
+      float2* dst = reinterpret_cast<float2*>(s_part) + (fo * S + sl) * foldp + c0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dst[j] = make_float2(sy[j], sx[j] - sy[j]);
+    }
+    __syncthreads();
+    // outputs (frame, channel, {y, r}); G threads (a power of two: contiguous lanes of one warp) add strided slices, then a shuffle tree
+    const int nout = nfo * fold * 2;
+    int G = 1;
+    while (G < 32 && G * 2 * nout <= GT_THREADS && G * 2 <= S) G *= 2;
+    for (int o0 = 0; o0 < nout * G; o0 += GT_THREADS) {
+      const int og = o0 + tid;
+      const int o = og / G, sub = og - o * G;
+      const int fo = o / (fold * 2), i = o - fo * (fold * 2);
+      float a = 0.f;
+      if (o < nout) {
+        const float* sp = s_part + fo * S * foldp * 2 + i;
+        const int stride = foldp * 2;
+#pragma unroll 4
+        for (int q = sub; q < S; q += G) a += sp[q * stride];
+      }
+      for (int sh2 = 1; sh2 < G; sh2 <<= 1) a += __shfl_xor_sync(0xffffffffu, a, sh2);
+      if (o < nout && sub == 0) sums_part[(((f0 + fo) * RB + rb) * fold) * 2 + i] = a;
+    }
+  }
+}
+
+// ---- kernel 4b (bf16 inference): blend + channel interleave on 16-byte pieces.  One CTA per `subs` tiles of GSB_ROWS (frame, pixel) rows ----
+// A thread owns 8 consecutive INPUT channels (the same 8 for every row it visits, so the interleaved output positions and the
+// group tests are computed once): per row one 16-byte load of x[t] and of the shifted neighbour frame(s), eight blends, eight
+// 2-byte stores into the CTA's [rows][ld_out] shared-memory tile; the tile (a contiguous piece of `out`) leaves with coalesced
+// 16-byte stores.  (gsf_blend_kernel walks the OUTPUT channels with 2-byte global loads and index arithmetic per channel:
+// ~500 instructions per 8 channels, instruction-bound at ~10x the time the bytes need.)
+constexpr int GSB_ROWS = 128;
+__global__ void __launch_bounds__(GS_THREADS)
+gsf_blend8_kernel(const __nv_bfloat16* __restrict__ x, int clip_len, int hw, int c, int fold, int mode, unsigned rows_total, int subs,
+                  const float* __restrict__ gate, const float* __restrict__ wgt, __nv_bfloat16* __restrict__ out, int ld_out) {
+  extern __shared__ __align__(16) unsigned char gsb_smem[];
+  __nv_bfloat16* s_out = reinterpret_cast<__nv_bfloat16*>(gsb_smem);                 // [GSB_ROWS][ld_out]
+  const int half = fold >> 1, quarter = fold >> 2;
+  const int nchunk = ld_out >> 3;
+  const int rpp = GS_THREADS / nchunk;                    // rows per pass
+  const int k = threadIdx.x % nchunk, rl = threadIdx.x / nchunk;
+  const int ch0 = k * 8;
+  // per-thread constants: output position of each of the 8 channels, its group
+  int jo[8];
+  unsigned gmask = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = ch0 + j;
+    const int g = ch >= half ? 1 : 0;
+    const int ci = ch - g * half;
+    const int k2 = ci >= quarter ? 1 : 0;
+    jo[j] = ch < fold ? g * half + 2 * (ci - k2 * quarter) + k2 : ch;    // out[2i+k] = in[k*quarter + i]; pad columns keep their place
+    gmask |= (unsigned)g << j;
+  }
+  const bool lo_grp = ch0 < half, hi_grp = ch0 + 7 >= half;
+  const int nvalid = min(8, fold - ch0);                  // channels >= fold are pad columns (written as zeros)
+  const unsigned fstride = (unsigned)hw * (unsigned)c;    // host: hw * c and frames * hw < 2^31
+  for (int sub = 0; sub < subs; ++sub) {
+    const unsigned r0 = ((unsigned)blockIdx.x * (unsigned)subs + sub) * GSB_ROWS;
+    if (r0 >= rows_total) break;
+    const int nrows = (int)min((unsigned)GSB_ROWS, rows_total - r0);
+    if (sub) __syncthreads();                             // the previous tile has left shared memory
+    if (rl < rpp) {
+      const unsigned r = r0 + rl;
+      int f = (int)(r / (unsigned)hw);
+      int p = (int)(r - (unsigned)f * (unsigned)hw);
+      int t = f % clip_len;
+      for (int row = rl; row < nrows; row += rpp) {
+        const unsigned fp = (unsigned)f * (unsigned)hw + (unsigned)p;
+        const __nv_bfloat16* xt = x + (size_t)fp * c + ch0;
+        const float* gt = gate + (size_t)fp * 2;
+        const bool has_next = t + 1 < clip_len, has_prev = t > 0;
+        float xv[8], xn[8], xp[8], wv[8];
+        load8(xt, xv);
+        const float2 g01 = *reinterpret_cast<const float2*>(gt);
+        float gn = 0.f, gp = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) xn[j] = xp[j] = wv[j] = 0.f;
+        if (lo_grp && has_next) { load8(xt + fstride, xn); gn = gt[2 * hw]; }
+        if (hi_grp && has_prev) { load8(xt - fstride, xp); gp = gt[1 - 2 * hw]; }
+        if (mode == TDEED_SHIFT_GSF) {
+          const float* wp = wgt + (size_t)f * fold + ch0;   // 16-byte aligned: fold % 4 == 0
+          const float4 w0 = *reinterpret_cast<const float4*>(wp);
+          wv[0] = w0.x; wv[1] = w0.y; wv[2] = w0.z; wv[3] = w0.w;
+          if (nvalid > 4) {
+            const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
+            wv[4] = w1.x; wv[5] = w1.y; wv[6] = w1.z; wv[7] = w1.w;
+          }
+        }
+        __nv_bfloat16* so = s_out + row * ld_out;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool g1 = (gmask >> j) & 1u;
+          const float r_ = xv[j] - (g1 ? g01.y : g01.x) * xv[j];
+          const float ys = g1 ? gp * xp[j] : gn * xn[j];
+          float v = mode == TDEED_SHIFT_GSF ? ys * wv[j] + r_ * (1.f - wv[j]) : ys + r_;
+          if (j >= nvalid) v = 0.f;                         // pad columns: the GEMM multiplies them by zero weights
+          so[jo[j]] = __float2bfloat16_rn(v);
+        }
+        p += rpp;
+        while (p >= hw) { p -= hw; ++f; if (++t == clip_len) t = 0; }
+      }
+    }
+    __syncthreads();
+    const uint4* src = reinterpret_cast<const uint4*>(s_out);
+    uint4* dst = reinterpret_cast<uint4*>(out + (size_t)r0 * ld_out);
+    for (int i = threadIdx.x; i < nrows * nchunk; i += GS_THREADS) dst[i] = src[i];
+  }
+}
+
 template <typename T>
 static int launch_gsf(int mode, const void* x, int clips, int clip_len, int h, int w, int c, int fold,
                       const float* bn_scale, const float* bn_shift, const float* w3d, const float* b3d,
@@ -312,6 +670,71 @@ static int launch_gsf(int mode, const void* x, int clips, int clip_len, int h, i
   float* Q = wgt + (size_t)n * fold;
   Q += (4 - ((Q - ws) & 3)) & 3;                       // 16-byte align (float2 stores need 8)
 
+  int RB = 1;                 // row blocks whose partial sums the weight kernel adds (tensor-core gate kernel only)
+  const float* sums_in = sums;
+  bool gate_done = false;
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    // tensor-core gate kernel (inference): plan the row block R and the frames per CTA FT inside the shared-memory budget
+    const int ks = (fold + 15) / 16, foldp = ks * 16, pitch = foldp * 2 + 16, wp = w + 2;
+    const int rpp = GT_THREADS / (foldp / 8);
+    int R = 0, FT = 0, MT = 0;
+    size_t z_bytes = 0, smem_tc = 0;
+    auto plan = [&](int rb, int ft) {
+      const int r = ceil_div(h, rb), mt = ceil_div(r * wp, 16);
+      size_t zb = ((size_t)(ft + 2) * (r + 2) * wp + 16) * pitch;
+      const size_t part = (size_t)GT_THREADS * 64;             // [FT * S slices][foldp][2] floats, FT * S * (foldp / 8) <= GT_THREADS
+      if (ft * (foldp / 8) > GT_THREADS) return false;
+      if (zb < part) zb = part;
+      zb = (zb + 15) / 16 * 16;
+      const size_t total = (size_t)9 * ks * 256 + zb + (size_t)ft * mt * 512 + (size_t)ft * r * w * 8;
+      if (total > (size_t)GT_SMEM_BUDGET || ceil_div((r + 2) * wp, rpp) > GT_NI) return false;
+      RB = ceil_div(h, r); R = r; FT = ft; MT = mt; z_bytes = zb; smem_tc = total;
+      return true;
+    };
+    bool ok = false;
+    if (!copy_tail && foldp <= 8 * GT_THREADS && clip_len >= 1 && (long long)hw * c < (1ll << 31)) {
+      for (int minft = 2; minft >= 1 && !ok; --minft)
+        for (int rb = 1; rb <= h && !ok; ++rb)
+          for (int ft = (clip_len < 4 ? clip_len : 4); ft >= minft && !ok; --ft) ok = plan(rb, ft);
+    }
+    // the partial sums of RB > 1 row blocks live in the (otherwise unused) Q region, the packed weights behind it.  The choice
+    // of the path must not depend on the number of clips: a batch and its clips one by one give bit-identical results.
+    if (ok && (RB == 1 || (size_t)RB * fold * 2 <= (size_t)hw * 6) && ceil_div(clip_len, FT) <= 65535 && clips <= 65535) {
+      uint2* wB = reinterpret_cast<uint2*>(Q + ((size_t)n * hw * 6 + 3) / 4 * 4);
+      float* sums_part = RB > 1 ? Q : sums;
+      gsf_pack_w_kernel<<<ceil_div(9 * ks * 32, 128), 128, 0, st>>>(w3d, fold, ks, wB);
+      int rc0 = check_launch("tdeed_gsf_fwd(pack)");
+      if (rc0) return rc0;
+      void (*kern)(const __nv_bfloat16*, int, int, int, int, int, int, int, int, int, int, const float*, const float*, const uint2*,
+                   const float*, float*, float*, int) = gsf_gate_tc_kernel<0>;
+      int kidx = 0;
+      switch (ks) {                                      // the RegNetY-200MF / 800MF fold widths get unrolled k-loops
+        case 1: kern = gsf_gate_tc_kernel<1>; kidx = 1; break;
+        case 2: kern = gsf_gate_tc_kernel<2>; kidx = 2; break;
+        case 3: kern = gsf_gate_tc_kernel<3>; kidx = 3; break;
+        case 5: kern = gsf_gate_tc_kernel<5>; kidx = 4; break;
+        case 6: kern = gsf_gate_tc_kernel<6>; kidx = 5; break;
+        case 12: kern = gsf_gate_tc_kernel<12>; kidx = 6; break;
+        default: break;
+      }
+      static bool tc_set[7] = {false, false, false, false, false, false, false};
+      if (!tc_set[kidx]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BUDGET);
+        TDEED_REQUIRE(e == cudaSuccess, TDEED_ERR_CUDA, "tdeed_gsf_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        tc_set[kidx] = true;
+      }
+      kern<<<dim3((unsigned)RB, (unsigned)ceil_div(clip_len, FT), (unsigned)clips), GT_THREADS, smem_tc, st>>>(
+          (const __nv_bfloat16*)x, clip_len, h, w, c, fold, ks, R, FT, MT, (int)z_bytes, bn_scale, bn_shift, wB, b3d, gate, sums_part, RB);
+      rc0 = check_launch("tdeed_gsf_fwd(gate_tc)");
+      if (rc0) return rc0;
+      sums_in = sums_part;
+      gate_done = true;
+    } else {
+      RB = 1;
+    }
+  }
+  int rc = 0;
+  if (!gate_done) {
   // kernel 1: rows per CTA so that the staged z tile fits the shared-memory budget
   const size_t w_bytes = (size_t)9 * fold * 16;
   int rows = h;
@@ -334,17 +757,29 @@ static int launch_gsf(int mode, const void* x, int clips, int clip_len, int h, i
       nsl *= 2;
   }
   kq<<<dim3(ceil_div(h, rows), n), GS_THREADS, smem_q, st>>>((const T*)x, h, w, c, fold, rows, nsl, bn_scale, bn_shift, w3d, Q);
-  int rc = check_launch("tdeed_gsf_fwd(q)");
+  rc = check_launch("tdeed_gsf_fwd(q)");
   if (rc) return rc;
 
   const int SEG = GS_THREADS / fold > 0 ? GS_THREADS / fold : 1;
   gsf_gate_kernel<T><<<n, GS_THREADS, (size_t)SEG * fold * 2 * sizeof(float), st>>>((const T*)x, clip_len, hw, c, fold, b3d, Q, gate, sums);
   rc = check_launch("tdeed_gsf_fwd(gate)");
   if (rc) return rc;
+  }
   if (mode == TDEED_SHIFT_GSF) {
-    gsf_weight_kernel<<<n, fold < GS_THREADS ? ((fold + 31) / 32 * 32) : GS_THREADS, 0, st>>>(sums, clip_len, hw, fold, cc_w, cc_b, wgt);
+    gsf_weight_kernel<<<n, fold < GS_THREADS ? ((fold + 31) / 32 * 32) : GS_THREADS, 0, st>>>(sums_in, clip_len, hw, fold, cc_w, cc_b, wgt, RB);
     rc = check_launch("tdeed_gsf_fwd(weights)");
     if (rc) return rc;
+  }
+  if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+    if (!copy_tail && ld_out == (fold + 7) / 8 * 8 && (size_t)GSB_ROWS * ld_out * 2 <= 48 * 1024 && (long long)n * hw < (1ll << 31) && (long long)hw * c < (1ll << 31)) {
+      // tiles per CTA: the per-thread set-up is amortised over several tiles as long as ~12 CTAs per SM remain
+      const unsigned rows_total = (unsigned)((long long)n * hw);
+      const long long tiles = ceil_div_ll((long long)rows_total, GSB_ROWS);
+      const int subs = (int)(tiles / 2000 < 1 ? 1 : (tiles / 2000 > 8 ? 8 : tiles / 2000));
+      gsf_blend8_kernel<<<(unsigned)ceil_div_ll(tiles, subs), GS_THREADS, (size_t)GSB_ROWS * ld_out * 2, st>>>(
+          (const __nv_bfloat16*)x, clip_len, hw, c, fold, mode, rows_total, subs, gate, wgt, (__nv_bfloat16*)out, ld_out);
+      return check_launch("tdeed_gsf_fwd(blend8)");
+    }
   }
   const long long total = (long long)n * hw * (ld_out / 8);
   gsf_blend_kernel<T><<<dim3((unsigned)n, (unsigned)ceil_div(hw * (ld_out / 8), GS_THREADS)), GS_THREADS, 0, st>>>(
@@ -356,7 +791,8 @@ static int launch_gsf(int mode, const void* x, int clips, int clip_len, int h, i
 
 extern "C" long long tdeed_gsf_workspace_floats(int clips, int clip_len, int h, int w, int fold) {
   const long long n = (long long)clips * clip_len;
-  return n * h * w * 2 + n * fold * 2 + n * fold + 4 + n * h * w * 6;
+  // gate | sums | fusion weights | Q maps (or row-block partial sums) | packed bf16 conv3d weights of the tensor-core gate kernel
+  return n * h * w * 2 + n * fold * 2 + n * fold + 4 + n * h * w * 6 + 4 + 9ll * ((fold + 15) / 16) * 64;
 }
 
 static int gsf_dispatch(int dtype, int mode, const void* x, int clips, int clip_len, int h, int w, int c, int fold,

@@ -245,12 +245,18 @@ def test_se_and_pool(dev, c, rd, hw):
 
 
 @pytest.mark.parametrize('mode', ['gsf', 'gsm'])
-@pytest.mark.parametrize('fold,c,hw', [(16, 56, (6, 5)), (40, 152, (4, 4)), (92, 368, (3, 2)), (192, 768, (2, 3))])
-def test_gate_shift(dev, mode, fold, c, hw):
+@pytest.mark.parametrize('fold,c,hw,dtype', [(16, 56, (6, 5), 'f32'), (40, 152, (4, 4), 'f32'), (92, 368, (3, 2), 'f32'), (192, 768, (2, 3), 'f32'),
+                                             # bf16 activations (the inference engine's path): the real layer shapes of rny002 / rny008
+                                             (12, 56, (28, 50), 'bf16'), (36, 152, (14, 25), 'bf16'), (92, 368, (7, 13), 'bf16'),
+                                             (32, 128, (9, 7), 'bf16'), (80, 320, (5, 6), 'bf16'), (192, 768, (2, 3), 'bf16'),
+                                             (4, 16, (3, 3), 'bf16')])
+def test_gate_shift(dev, mode, fold, c, hw, dtype):
     from tdeed_b200 import _lib as L, ops
     g = torch.Generator().manual_seed(4)
     clips, T = 2, 5
     x = torch.randn(clips * T, c, *hw, generator=g)
+    if dtype == 'bf16':
+        x = x.bfloat16().float()
     sd = {'g.bn.weight': torch.rand(fold, generator=g) + 0.5, 'g.bn.bias': torch.randn(fold, generator=g) * 0.1,
           'g.bn.running_mean': torch.randn(fold, generator=g) * 0.1, 'g.bn.running_var': torch.rand(fold, generator=g) + 0.5,
           'g.conv3D.weight': torch.randn(2, fold // 2, 3, 3, 3, generator=g) / math.sqrt(27 * fold / 2),
@@ -267,6 +273,15 @@ def test_gate_shift(dev, mode, fold, c, hw):
     xh = _nhwc(x).to(dev)
     ld = (fold + 7) // 8 * 8
     ws = torch.empty(ops.gsf_workspace_floats(clips, T, hw[0], hw[1], fold), dtype=torch.float32, device=dev)
+    if dtype == 'bf16':
+        # pad columns are poisoned: the kernel must write them as zeros (the 1x1 conv reads them against zero weights)
+        out = torch.full((clips * T * hw[0] * hw[1], ld), float('nan'), device=dev, dtype=torch.bfloat16)
+        ops.gsf(xh.bfloat16(), clips, T, fold, L.SHIFT_GSF if mode == 'gsf' else L.SHIFT_GSM, p, ws, out)
+        assert bool((out[:, fold:] == 0).all())
+        got = out[:, :fold].float().reshape(clips * T, hw[0], hw[1], fold).permute(0, 3, 1, 2)
+        # bf16 output rounding (2^-9) dominates; the gate conv runs on bf16 tensor-core operands with fp32 accumulation
+        assert rel_err(got, ref) < 6e-3
+        return
     out = torch.zeros(clips * T * hw[0] * hw[1], ld, device=dev)
     ops.gsf(xh, clips, T, fold, L.SHIFT_GSF if mode == 'gsf' else L.SHIFT_GSM, p, ws, out)
     got = out[:, :fold].reshape(clips * T, hw[0], hw[1], fold).permute(0, 3, 1, 2)
