@@ -151,6 +151,15 @@ int tdeed_gsf_fwd(int dtype, int mode, const void* x, int clips, int clip_len, i
                   const float* bn_scale, const float* bn_shift, const float* conv3d_w, const float* conv3d_b,
                   const float* cc_w, const float* cc_b, float* workspace,
                   void* out, int ld_out, void* stream);
+/* Same, but out[:, ch] holds the result for INPUT channel ch (no interleave).  The interleave is a fixed channel permutation in
+ * front of the block's 1x1 convolution, so a caller that owns that convolution's weight permutes its columns once instead:
+ * out_natural[:, ch] == out_interleaved[:, tdeed_gsf_interleaved_position(fold, ch)].  (The bf16 kernel then stores 16 bytes
+ * per thread straight from registers.) */
+int tdeed_gsf_fwd_natural(int dtype, int mode, const void* x, int clips, int clip_len, int h, int w, int c, int fold,
+                          const float* bn_scale, const float* bn_shift, const float* conv3d_w, const float* conv3d_b,
+                          const float* cc_w, const float* cc_b, float* workspace,
+                          void* out, int ld_out, void* stream);
+int tdeed_gsf_interleaved_position(int fold, int ch);
 
 /* (6) global average pool + positional encoding: feat[f, :] = mean_hw(x[f]) + temp_enc[f % clip_len, :]
  * (timm head global_pool, model/model.py:133-137).  x: NHWC [n, hw, c]; temp_enc fp32 [clip_len, c];

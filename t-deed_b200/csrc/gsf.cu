@@ -27,6 +27,10 @@
 namespace tdeed {
 
 constexpr int GS_THREADS = 256;
+
+// the blend arithmetic, spelled with explicit roundings so that every blend kernel gives the same bits
+__device__ __forceinline__ float gs_resid(float x, float g) { return __fmaf_rn(-g, x, x); }                    // r = x - g*x
+__device__ __forceinline__ float gs_fuse(float ys, float r, float w) { return __fmaf_rn(ys, w, __fmul_rn(r, __fsub_rn(1.f, w))); }
 constexpr int GS_Q_SMEM_BUDGET = 96 * 1024;
 
 // ---- kernel 1: Q maps.  grid (row_blocks, frames) ----
@@ -260,7 +264,7 @@ template <typename T>
 __global__ void __launch_bounds__(GS_THREADS)
 gsf_blend_kernel(const T* __restrict__ x, int clip_len, int hw, int c, int fold, int mode,
                  const float* __restrict__ gate, const float* __restrict__ wgt, T* __restrict__ out, int ld_out,
-                 long long total, int copy_tail) {
+                 long long total, int copy_tail, int natural) {
   // grid (frames, pixel-octet blocks): the frame index is the block's, one 32-bit division per thread (the former flat index
   // cost four 64-bit divisions per thread plus one division per output channel: more than half of the kernel's instructions)
   const int o8n = ld_out / 8;
@@ -287,17 +291,17 @@ gsf_blend_kernel(const T* __restrict__ x, int clip_len, int hw, int c, int fold,
     float v = 0.f;
     if (jo < fold) {
       const int g = jo >= half ? 1 : 0, jj = jo - g * half;       // jo < fold = 2 * half
-      const int ch = g * half + (jj & 1) * quarter + (jj >> 1);   // out[2i+k] = in[k*quarter + i]
+      const int ch = natural ? jo : g * half + (jj & 1) * quarter + (jj >> 1);   // out[2i+k] = in[k*quarter + i]
       const float xv = Elem<T>::ld(xt + ch);
-      const float r = xv - (g == 0 ? g0 : g1) * xv;
+      const float r = gs_resid(xv, g == 0 ? g0 : g1);
       float ys = 0.f;
-      if (g == 0) { if (has_next) ys = gn * Elem<T>::ld(xn + ch); }
-      else { if (has_prev) ys = gp * Elem<T>::ld(xp + ch); }
+      if (g == 0) { if (has_next) ys = __fmul_rn(gn, Elem<T>::ld(xn + ch)); }
+      else { if (has_prev) ys = __fmul_rn(gp, Elem<T>::ld(xp + ch)); }
       if (mode == TDEED_SHIFT_GSF) {
         const float wv = wgt[(size_t)f * fold + ch];
-        v = ys * wv + r * (1.f - wv);
+        v = gs_fuse(ys, r, wv);
       } else {
-        v = ys + r;
+        v = __fadd_rn(ys, r);
       }
     }
     else if (copy_tail && jo < c) v = Elem<T>::ld(xt + jo);   // training: materialise the concat [gs(x[:, :fold]) | x[:, fold:]]
@@ -641,9 +645,9 @@ gsf_blend8_kernel(const __nv_bfloat16* __restrict__ x, int clip_len, int hw, int
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const bool g1 = (gmask >> j) & 1u;
-          const float r_ = xv[j] - (g1 ? g01.y : g01.x) * xv[j];
-          const float ys = g1 ? gp * xp[j] : gn * xn[j];
-          float v = mode == TDEED_SHIFT_GSF ? ys * wv[j] + r_ * (1.f - wv[j]) : ys + r_;
+          const float r_ = gs_resid(xv[j], g1 ? g01.y : g01.x);
+          const float ys = g1 ? __fmul_rn(gp, xp[j]) : __fmul_rn(gn, xn[j]);
+          float v = mode == TDEED_SHIFT_GSF ? gs_fuse(ys, r_, wv[j]) : __fadd_rn(ys, r_);
           if (j >= nvalid) v = 0.f;                         // pad columns: the GEMM multiplies them by zero weights
           so[jo[j]] = __float2bfloat16_rn(v);
         }
@@ -658,10 +662,65 @@ gsf_blend8_kernel(const __nv_bfloat16* __restrict__ x, int clip_len, int hw, int
   }
 }
 
+// ---- kernel 4c (bf16 inference, natural channel order): out[:, ch] = blend of input channel ch.  The reference's channel
+// interleave (out[2i+k] = in[k*quarter + i]) is a fixed permutation in front of a 1x1 convolution: the caller folds it into the
+// columns of that convolution's weight, and a thread's 8 input channels leave as one 16-byte store (no shared-memory tile,
+// no per-channel output positions). ----
+__global__ void __launch_bounds__(GS_THREADS)
+gsf_blend8n_kernel(const __nv_bfloat16* __restrict__ x, int clip_len, int hw, int c, int fold, int mode, unsigned rows_total, int iters,
+                   const float* __restrict__ gate, const float* __restrict__ wgt, __nv_bfloat16* __restrict__ out, int ld_out) {
+  const int nchunk = ld_out >> 3, rpp = GS_THREADS / nchunk;
+  const int k = threadIdx.x % nchunk, rl = threadIdx.x / nchunk;
+  if (rl >= rpp) return;
+  const int ch0 = k * 8, half = fold >> 1;
+  const bool lo_grp = ch0 < half, hi_grp = ch0 + 7 >= half;
+  const int nvalid = min(8, fold - ch0);                  // channels >= fold are pad columns (written as zeros)
+  unsigned r = blockIdx.x * (unsigned)(rpp * iters) + rl; // row = frame * hw + pixel (host: frames * hw, hw * c < 2^31)
+  if (r >= rows_total) return;
+  int f = (int)(r / (unsigned)hw);
+  int p = (int)(r - (unsigned)f * (unsigned)hw);
+  int t = f % clip_len;
+  const unsigned fstride = (unsigned)hw * (unsigned)c;
+  for (int it = 0; it < iters && r < rows_total; ++it, r += rpp) {
+    const __nv_bfloat16* xt = x + (size_t)r * c + ch0;
+    const float* gt = gate + (size_t)r * 2;
+    const bool has_next = t + 1 < clip_len, has_prev = t > 0;
+    float xv[8], xn[8], xp[8], wv[8];
+    load8(xt, xv);
+    const float2 g01 = *reinterpret_cast<const float2*>(gt);
+    float gn = 0.f, gp = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { xn[j] = xp[j] = 0.f; wv[j] = 1.f; }
+    if (lo_grp && has_next) { load8(xt + fstride, xn); gn = gt[2 * hw]; }
+    if (hi_grp && has_prev) { load8(xt - fstride, xp); gp = gt[1 - 2 * hw]; }
+    if (mode == TDEED_SHIFT_GSF) {
+      const float* wp = wgt + (size_t)f * fold + ch0;     // 16-byte aligned: fold % 4 == 0
+      const float4 w0 = *reinterpret_cast<const float4*>(wp);
+      wv[0] = w0.x; wv[1] = w0.y; wv[2] = w0.z; wv[3] = w0.w;
+      if (nvalid > 4) {
+        const float4 w1 = *reinterpret_cast<const float4*>(wp + 4);
+        wv[4] = w1.x; wv[5] = w1.y; wv[6] = w1.z; wv[7] = w1.w;
+      }
+    }
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const bool g1 = !lo_grp || (hi_grp && ch0 + j >= half);
+      const float r_ = gs_resid(xv[j], g1 ? g01.y : g01.x);
+      const float ys = g1 ? __fmul_rn(gp, xp[j]) : __fmul_rn(gn, xn[j]);
+      v[j] = mode == TDEED_SHIFT_GSF ? gs_fuse(ys, r_, wv[j]) : __fadd_rn(ys, r_);
+      if (j >= nvalid) v[j] = 0.f;                        // pad columns: the GEMM multiplies them by zero weights
+    }
+    store8(out + (size_t)r * ld_out + ch0, v);
+    p += rpp;
+    while (p >= hw) { p -= hw; ++f; if (++t == clip_len) t = 0; }
+  }
+}
+
 template <typename T>
 static int launch_gsf(int mode, const void* x, int clips, int clip_len, int h, int w, int c, int fold,
                       const float* bn_scale, const float* bn_shift, const float* w3d, const float* b3d,
-                      const float* cc_w, const float* cc_b, float* ws, void* out, int ld_out, int copy_tail, cudaStream_t st) {
+                      const float* cc_w, const float* cc_b, float* ws, void* out, int ld_out, int copy_tail, int natural, cudaStream_t st) {
   const int n = clips * clip_len, hw = h * w;
   TDEED_REQUIRE(n <= 65535, TDEED_ERR_UNSUPPORTED, "tdeed_gsf_fwd: %d frames per call (the Q-map kernel puts frames on grid.y: at most 65535; split the batch)", n);
   float* gate = ws;
@@ -771,7 +830,15 @@ static int launch_gsf(int mode, const void* x, int clips, int clip_len, int h, i
     if (rc) return rc;
   }
   if constexpr (std::is_same<T, __nv_bfloat16>::value) {
-    if (!copy_tail && ld_out == (fold + 7) / 8 * 8 && (size_t)GSB_ROWS * ld_out * 2 <= 48 * 1024 && (long long)n * hw < (1ll << 31) && (long long)hw * c < (1ll << 31)) {
+    if (natural && !copy_tail && ld_out == (fold + 7) / 8 * 8 && ld_out <= 8 * GS_THREADS && (long long)n * hw < (1ll << 31) &&
+        (long long)hw * c < (1ll << 31)) {
+      const unsigned rows_total = (unsigned)((long long)n * hw);
+      const int rpp = GS_THREADS / (ld_out / 8), iters = 4;
+      gsf_blend8n_kernel<<<(unsigned)ceil_div_ll((long long)rows_total, (long long)rpp * iters), GS_THREADS, 0, st>>>(
+          (const __nv_bfloat16*)x, clip_len, hw, c, fold, mode, rows_total, iters, gate, wgt, (__nv_bfloat16*)out, ld_out);
+      return check_launch("tdeed_gsf_fwd(blend8n)");
+    }
+    if (!natural && !copy_tail && ld_out == (fold + 7) / 8 * 8 && (size_t)GSB_ROWS * ld_out * 2 <= 48 * 1024 && (long long)n * hw < (1ll << 31) && (long long)hw * c < (1ll << 31)) {
       // tiles per CTA: the per-thread set-up is amortised over several tiles as long as ~12 CTAs per SM remain
       const unsigned rows_total = (unsigned)((long long)n * hw);
       const long long tiles = ceil_div_ll((long long)rows_total, GSB_ROWS);
@@ -783,7 +850,7 @@ static int launch_gsf(int mode, const void* x, int clips, int clip_len, int h, i
   }
   const long long total = (long long)n * hw * (ld_out / 8);
   gsf_blend_kernel<T><<<dim3((unsigned)n, (unsigned)ceil_div(hw * (ld_out / 8), GS_THREADS)), GS_THREADS, 0, st>>>(
-      (const T*)x, clip_len, hw, c, fold, mode, gate, wgt, (T*)out, ld_out, total, copy_tail);
+      (const T*)x, clip_len, hw, c, fold, mode, gate, wgt, (T*)out, ld_out, total, copy_tail, natural);
   return check_launch("tdeed_gsf_fwd(blend)");
 }
 
@@ -798,7 +865,7 @@ extern "C" long long tdeed_gsf_workspace_floats(int clips, int clip_len, int h, 
 static int gsf_dispatch(int dtype, int mode, const void* x, int clips, int clip_len, int h, int w, int c, int fold,
                         const float* bn_scale, const float* bn_shift, const float* conv3d_w, const float* conv3d_b,
                         const float* cc_w, const float* cc_b, float* workspace, void* out, int ld_out, int copy_tail,
-                        void* stream) {
+                        int natural, void* stream) {
   using namespace tdeed;
   TDEED_REQUIRE(x && bn_scale && bn_shift && conv3d_w && conv3d_b && workspace && out, TDEED_ERR_SHAPE,
                 "tdeed_gsf_fwd: null pointer");
@@ -810,10 +877,10 @@ static int gsf_dispatch(int dtype, int mode, const void* x, int clips, int clip_
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == TDEED_BF16)
     return launch_gsf<__nv_bfloat16>(mode, x, clips, clip_len, h, w, c, fold, bn_scale, bn_shift, conv3d_w, conv3d_b,
-                                     cc_w, cc_b, workspace, out, ld_out, copy_tail, st);
+                                     cc_w, cc_b, workspace, out, ld_out, copy_tail, natural, st);
   if (dtype == TDEED_F32)
     return launch_gsf<float>(mode, x, clips, clip_len, h, w, c, fold, bn_scale, bn_shift, conv3d_w, conv3d_b, cc_w, cc_b,
-                             workspace, out, ld_out, copy_tail, st);
+                             workspace, out, ld_out, copy_tail, natural, st);
   set_error("tdeed_gsf_fwd: dtype %d", dtype);
   return TDEED_ERR_UNSUPPORTED;
 }
@@ -823,7 +890,24 @@ extern "C" int tdeed_gsf_fwd(int dtype, int mode, const void* x, int clips, int 
                              const float* cc_w, const float* cc_b, float* workspace, void* out, int ld_out,
                              void* stream) {
   return gsf_dispatch(dtype, mode, x, clips, clip_len, h, w, c, fold, bn_scale, bn_shift, conv3d_w, conv3d_b, cc_w, cc_b,
-                      workspace, out, ld_out, 0, stream);
+                      workspace, out, ld_out, 0, 0, stream);
+}
+
+// same, but out[:, ch] holds input channel ch (no interleave): the caller permutes the columns of the following 1x1 convolution
+// with tdeed_gsf_interleaved_position (out_natural[:, ch] == out_interleaved[:, position(ch)]).
+extern "C" int tdeed_gsf_fwd_natural(int dtype, int mode, const void* x, int clips, int clip_len, int h, int w, int c, int fold,
+                                     const float* bn_scale, const float* bn_shift, const float* conv3d_w, const float* conv3d_b,
+                                     const float* cc_w, const float* cc_b, float* workspace, void* out, int ld_out,
+                                     void* stream) {
+  return gsf_dispatch(dtype, mode, x, clips, clip_len, h, w, c, fold, bn_scale, bn_shift, conv3d_w, conv3d_b, cc_w, cc_b,
+                      workspace, out, ld_out, 0, 1, stream);
+}
+
+extern "C" int tdeed_gsf_interleaved_position(int fold, int ch) {
+  const int half = fold / 2, quarter = fold / 4;
+  if (ch < 0 || ch >= fold || fold % 4) return -1;
+  const int g = ch >= half ? 1 : 0, ci = ch - g * half, k2 = ci >= quarter ? 1 : 0;
+  return g * half + 2 * (ci - k2 * quarter) + k2;         // model/impl/gsf.py:84-92: out[2i+k] = in[k*quarter + i]
 }
 
 // training: writes the full concat y = [gs(x[:, :fold]) | x[:, fold:]] as [frames*h*w, c] (model/shift.py:89-93); the
@@ -832,5 +916,5 @@ extern "C" int tdeed_gsf_cat_fwd(int dtype, int mode, const void* x, int clips, 
                                  const float* bn_scale, const float* bn_shift, const float* conv3d_w, const float* conv3d_b,
                                  const float* cc_w, const float* cc_b, float* workspace, void* out, void* stream) {
   return gsf_dispatch(dtype, mode, x, clips, clip_len, h, w, c, fold, bn_scale, bn_shift, conv3d_w, conv3d_b, cc_w, cc_b,
-                      workspace, out, c, 1, stream);
+                      workspace, out, c, 1, 0, stream);
 }

@@ -61,6 +61,9 @@ SIGNATURES = {
     'tdeed_gsf_workspace_floats': (c_ll, [c_int, c_int, c_int, c_int, c_int]),
     'tdeed_gsf_fwd': (c_int, [c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
                               c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
+    'tdeed_gsf_fwd_natural': (c_int, [c_int, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
+                                      c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
+    'tdeed_gsf_interleaved_position': (c_int, [c_int, c_int]),
     'tdeed_pool_posenc_fwd': (c_int, [c_int, c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     'tdeed_sgp_mix_workspace_floats': (c_ll, [c_int, c_int, c_int]),
     'tdeed_sgp_mix_fwd': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(SgpWeights), c_vp, c_vp,

@@ -129,7 +129,9 @@ class InferenceEngine:
                 fd = fold_dim(cin)
                 fdp, xs = _round8(fd), fd // 8 * 8
                 wp = torch.zeros((cout, fdp + cin - xs), dtype=torch.float32, device=dev)
-                wp[:, :fd] = w1[:, :fd]
+                # the gate-shift kernel writes its channels in input order (ops.gsf natural=True): the reference's channel
+                # interleave (model/impl/gsf.py:84-92) becomes a column permutation of this weight
+                wp[:, :fd] = w1[:, ops.gsf_interleaved_positions(fd)]
                 wp[:, fdp + (fd - xs):] = w1[:, fd:]
                 w1 = wp
                 b['x_start'] = xs
@@ -342,8 +344,8 @@ class InferenceEngine:
                 ws = torch.empty(ops.gsf_workspace_floats(b, t, h, w, fd), dtype=torch.float32, device=x.device)
                 gso = torch.empty((m, _round8(fd)), dtype=adt, device=x.device)
                 self._op('gsf', 2.0 * m * 27 * fd, m * fd * es * 2, ops.gsf, x, b, t, fd,
-                         L.SHIFT_GSF if cfg.shift_mode == 'gsf' else L.SHIFT_GSM, gs, ws, gso,
-                         _n=3 if cfg.shift_mode == 'gsf' else 2)
+                         L.SHIFT_GSF if cfg.shift_mode == 'gsf' else L.SHIFT_GSM, gs, ws, gso, natural=True,
+                         _n=4 if cfg.shift_mode == 'gsf' else 3)
                 segs = [(gso, gso.shape[1], 0, gso.shape[1]), (x, cin, blk['x_start'], cin - blk['x_start'])]
             else:
                 segs = [(x, cin, 0, cin)]

@@ -167,13 +167,21 @@ def gsf_workspace_floats(clips, clip_len, h, w, fold):
     return int(L.load().tdeed_gsf_workspace_floats(clips, clip_len, h, w, fold))
 
 
-def gsf(x, clips, clip_len, fold, mode, p, workspace, out):
-    """x NHWC (clips*clip_len, h, w, c) -> out (N*h*w, ld_out) holding the gate-shifted fold channels."""
+def gsf_interleaved_positions(fold):
+    """position[ch] of input channel ch in the reference's interleaved output (model/impl/gsf.py:84-92)."""
+    lib = L.load()
+    return [int(lib.tdeed_gsf_interleaved_position(fold, ch)) for ch in range(fold)]
+
+
+def gsf(x, clips, clip_len, fold, mode, p, workspace, out, natural=False):
+    """x NHWC (clips*clip_len, h, w, c) -> out (N*h*w, ld_out) holding the gate-shifted fold channels (natural=True: in input
+    channel order, the interleave left to the weight columns of the following 1x1 conv)."""
     n, h, w, c = x.shape
-    L.check(L.load().tdeed_gsf_fwd(L.dtype_code(x.dtype), mode, L.ptr(x), clips, clip_len, h, w, c, fold,
-                                   L.ptr(p['bn_scale']), L.ptr(p['bn_shift']), L.ptr(p['w3d']), L.ptr(p['b3d']),
-                                   L.ptr(p.get('cc_w')), L.ptr(p.get('cc_b')), L.ptr(workspace), L.ptr(out),
-                                   out.shape[-1], L.stream()), 'gsf')
+    fn = L.load().tdeed_gsf_fwd_natural if natural else L.load().tdeed_gsf_fwd
+    L.check(fn(L.dtype_code(x.dtype), mode, L.ptr(x), clips, clip_len, h, w, c, fold,
+               L.ptr(p['bn_scale']), L.ptr(p['bn_shift']), L.ptr(p['w3d']), L.ptr(p['b3d']),
+               L.ptr(p.get('cc_w')), L.ptr(p.get('cc_b')), L.ptr(workspace), L.ptr(out),
+               out.shape[-1], L.stream()), 'gsf')
     return out
 
 

@@ -281,11 +281,20 @@ def test_gate_shift(dev, mode, fold, c, hw, dtype):
         got = out[:, :fold].float().reshape(clips * T, hw[0], hw[1], fold).permute(0, 3, 1, 2)
         # bf16 output rounding (2^-9) dominates; the gate conv runs on bf16 tensor-core operands with fp32 accumulation
         assert rel_err(got, ref) < 6e-3
+        # natural channel order (the engine's call): the same values at the un-interleaved positions, bit for bit
+        nat = torch.full_like(out, float('nan'))
+        ops.gsf(xh.bfloat16(), clips, T, fold, L.SHIFT_GSF if mode == 'gsf' else L.SHIFT_GSM, p, ws, nat, natural=True)
+        pos = ops.gsf_interleaved_positions(fold)
+        assert sorted(pos) == list(range(fold))
+        assert torch.equal(nat[:, :fold], out[:, pos]) and bool((nat[:, fold:] == 0).all())
         return
     out = torch.zeros(clips * T * hw[0] * hw[1], ld, device=dev)
     ops.gsf(xh, clips, T, fold, L.SHIFT_GSF if mode == 'gsf' else L.SHIFT_GSM, p, ws, out)
     got = out[:, :fold].reshape(clips * T, hw[0], hw[1], fold).permute(0, 3, 1, 2)
     assert rel_err(got, ref) < 2e-5
+    nat = torch.zeros_like(out)
+    ops.gsf(xh, clips, T, fold, L.SHIFT_GSF if mode == 'gsf' else L.SHIFT_GSM, p, ws, nat, natural=True)
+    assert torch.equal(nat[:, :fold], out[:, ops.gsf_interleaved_positions(fold)])
 
 
 @pytest.mark.parametrize('c,t_in,t_out,ks,r', [(368, 25, 25, 7, 4), (368, 25, 13, 5, 4), (768, 100, 50, 9, 4), (368, 13, 7, 11, 2),

@@ -45,7 +45,7 @@ if 'se' in what:
         t = timeit(lambda: ops.se_(x, w1, b1, w2, b2))
         print('se   n=%d hw=%d c=%d rd=%d: %.1f us total (mean+fc+scale), %.2f TB/s on 3 passes' % (n, hw, c, rd, t, 3 * x.numel() * 2 / t / 1e6), flush=True)
 if 'gsf' in what:
-    shapes = ((28, 56, 12), (14, 152, 36), (7, 368, 92))
+    shapes = ((28, 56, 16), (14, 152, 40), (7, 368, 92))
     if os.environ.get('GSF_SHAPE'):
         shapes = (shapes[int(os.environ['GSF_SHAPE'])],)
     for (h, c, fold) in shapes:
@@ -56,5 +56,5 @@ if 'gsf' in what:
                  cc_w=torch.randn(36, device=dev) * 0.2, cc_b=torch.randn(2, device=dev) * 0.1)
         ws = torch.empty(ops.gsf_workspace_floats(b, t_, h, h, fold), dtype=torch.float32, device=dev)
         out = torch.empty((b * t_ * h * h, (fold + 7) // 8 * 8), dtype=torch.bfloat16, device=dev)
-        t = timeit(lambda: ops.gsf(x, b, t_, fold, L.SHIFT_GSF, p, ws, out))
+        t = timeit(lambda: ops.gsf(x, b, t_, fold, L.SHIFT_GSF, p, ws, out, natural=True))
         print('gsf  %dx%dx%d fold=%d: %.1f us (q+gate+weight+blend)' % (h, h, c, fold, t), flush=True)
