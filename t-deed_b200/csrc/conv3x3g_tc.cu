@@ -331,6 +331,15 @@ static int conv3x3g_tc_run(const void* in, int n, int h, int w, int c, int strid
   const size_t per_pair = (size_t)9 * 512 + 2 * (size_t)p.nplanes * 2 * p.npos_pad * 16 + 64;     // two input buffers
   int max_pairs = (int)((200 * 1024 - 2 * (size_t)p.npos * p.nplanes * sizeof(int)) / per_pair);
   if (max_pairs > C3T_MAX_PAIRS) max_pairs = C3T_MAX_PAIRS;
+  // Wide layers run better as several narrow channel blocks (more CTAs per SM: the staging / MMA / epilogue stages of more tiles
+  // overlap) than as 128-channel blocks.  Measured on B200 at 5700 frames (us, max pairs 8 / 6 / 4 / 3 / 2):
+  //   stride 1   7x7x368 : 191 / 148 / 148 / 153 / 161     14x14x320: 690 / 612 / 537 / 580 / 577     7x7x768: 385 / 330 / 328 / 330 / 365
+  //              14x14x152: 321 / 320 / 336 / 381 / 445    28x28x128: 227 / 243 / 242 / 293 / 258  (narrow layers: keep 8)
+  //   stride 2  14x14x368: 438 /  -  / 354 / 312 / 336     28x28x152: 682 / - / - / 598 / 761       14x14x768: 977 / - / 766 / 702 / 731
+  //              56x56x128: 485 / - / - / 514 / 508  (<= 8 pairs: keep 8)
+  // The choice depends on the layer only (never on the frame count): a batch and its clips one by one run the same kernel.
+  if (stride == 1 && p.pairs_total >= 16 && max_pairs > 4) max_pairs = 4;
+  if (stride == 2 && p.pairs_total >= 10 && max_pairs > 3) max_pairs = 3;
   static int pairs_env = -1;
   if (pairs_env < 0) { const char* e = tdeed::dev_env("TDEED_C3_MAX_PAIRS"); pairs_env = e ? atoi(e) : 0; }
   if (pairs_env > 0 && max_pairs > pairs_env) max_pairs = pairs_env;
