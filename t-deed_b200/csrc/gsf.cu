@@ -353,7 +353,7 @@ __global__ void gsf_pack_w_kernel(const float* __restrict__ w3d, int fold, int k
   wB[idx] = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
 }
 
-constexpr int GT_NI = 8;                       // staged pieces per thread and frame (register-resident offsets)
+constexpr int GT_NI = 32;                      // halo positions per thread (one validity bit each)
 
 // KS = k-steps (fold padded to 16 channels per step); KS = 0: run-time `ks`
 template <int KS>
@@ -387,34 +387,30 @@ gsf_gate_tc_kernel(const __nv_bfloat16* __restrict__ x, int clip_len, int h, int
   unsigned gmask = 0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) gmask |= (unsigned)(ch0 + j >= (fold >> 1) ? 1 : 0) << j;
-  int off[GT_NI];                                       // element offset of the piece inside a frame; -1: zero padding; -2: none
   const uint32_t zt = z_addr + (uint32_t)(rl * pitch + k * 16);
   const uint32_t step = (uint32_t)(rpp * pitch);
+  const int step_y = rpp / wp, step_x = rpp - step_y * wp;
+  const int nfr = nfo + 2;
+  unsigned fmask = 0;                                   // staged frames that lie inside the clip
+  for (int fr = 0; fr < nfr; ++fr) fmask |= (unsigned)(t0 - 1 + fr >= 0 && t0 - 1 + fr < clip_len ? 1 : 0) << fr;
+  unsigned vmask = 0;                                   // this thread's halo positions (<= 32) that hold a pixel
   if (rl < rpp) {
-    {
-      const int step_y = rpp / wp, step_x = rpp - step_y * wp;
-      int hy = rl / wp, hx = rl - hy * wp;
-#pragma unroll
-      for (int i = 0; i < GT_NI; ++i) {
-        const int py = y0 - 1 + hy, px = hx - 1;
-        off[i] = rl + i * rpp >= hpx ? -2 : ((chunk_ok && py >= 0 && py < h && px >= 0 && px < w) ? (py * w + px) * c + ch0 : -1);
-        hy += step_y; hx += step_x;
-        if (hx >= wp) { hx -= wp; ++hy; }
+    const __nv_bfloat16* xc = x + ((size_t)b * clip_len + t0 - 1) * hw * c + ch0;     // frame fr: xc + fr * hw * c (fmask-guarded)
+    int hy = rl / wp, hx = rl - hy * wp, i = 0;
+    uint32_t zp = zt;
+    for (int hp = rl; hp < hpx; hp += rpp, ++i, zp += step) {
+      const int py = y0 - 1 + hy, px = hx - 1;
+      const bool pv = chunk_ok && py >= 0 && py < h && px >= 0 && px < w;
+      vmask |= (unsigned)(pv ? 1 : 0) << i;
+      const __nv_bfloat16* src = xc + (pv ? (py * w + px) * c : 0);
+      uint32_t zq = zp;
+      for (int fr = 0; fr < nfr; ++fr, zq += frame_bytes, src += (size_t)hw * c) {
+        const bool in = pv && ((fmask >> fr) & 1u);     // src-size 0 = zero fill: one instruction, no divergent branch
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(zq), "l"(in ? (const void*)src : (const void*)x),
+                     "r"(in ? 16 : 0) : "memory");
       }
-    }
-    for (int fr = 0; fr < nfo + 2; ++fr) {
-      const int t = t0 - 1 + fr;
-      const bool fvalid = t >= 0 && t < clip_len;
-      const __nv_bfloat16* xf = x + ((size_t)b * clip_len + (fvalid ? t : 0)) * hw * c;
-      const uint32_t zf = zt + (uint32_t)fr * frame_bytes;
-#pragma unroll
-      for (int i = 0; i < GT_NI; ++i) {
-        if (off[i] >= 0 && fvalid) {
-          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(zf + (uint32_t)i * step), "l"(xf + off[i]) : "memory");
-        } else if (off[i] >= -1) {
-          asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(zf + (uint32_t)i * step), "r"(0u) : "memory");
-        }
-      }
+      hy += step_y; hx += step_x;
+      if (hx >= wp) { hx -= wp; ++hy; }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   }
@@ -432,24 +428,22 @@ gsf_gate_tc_kernel(const __nv_bfloat16* __restrict__ x, int clip_len, int h, int
     sh[j] = ch < fold ? bn_shift[ch] : 0.f;
   }
   asm volatile("cp.async.wait_group 0;" ::: "memory");     // every thread: the weight pieces of the idle tail threads too
-  if (rl < rpp) {
-    for (int fr = 0; fr < nfo + 2; ++fr) {
-      const int t = t0 - 1 + fr;
-      if (t < 0 || t >= clip_len) continue;
-      const uint32_t zf = zt + (uint32_t)fr * frame_bytes;
+  {
+    uint32_t zp = zt;
+    for (unsigned m = vmask; m; m >>= 1, zp += step) {
+      if (!(m & 1u)) continue;
+      uint32_t zq = zp;
+      for (unsigned fm = fmask; fm; fm >>= 1, zq += frame_bytes) {
+        if (!(fm & 1u)) continue;                         // this thread's own copies: visible after wait_group
+        uint32_t wv[4], o[4];
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(wv[0]), "=r"(wv[1]), "=r"(wv[2]), "=r"(wv[3]) : "r"(zq));
 #pragma unroll
-      for (int i = 0; i < GT_NI; ++i) {
-        if (off[i] >= 0) {                               // this thread's own copy: visible after wait_group
-          uint32_t wv[4], o[4];
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(wv[0]), "=r"(wv[1]), "=r"(wv[2]), "=r"(wv[3]) : "r"(zf + (uint32_t)i * step));
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float lo = fmaxf(fmaf(__uint_as_float(wv[q] << 16), sc[2 * q], sh[2 * q]), 0.f);
-            const float hi = fmaxf(fmaf(__uint_as_float(wv[q] & 0xffff0000u), sc[2 * q + 1], sh[2 * q + 1]), 0.f);
-            o[q] = pack_bf16x2(lo, hi);
-          }
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(zf + (uint32_t)i * step), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
+        for (int q = 0; q < 4; ++q) {
+          const float lo = fmaxf(fmaf(__uint_as_float(wv[q] << 16), sc[2 * q], sh[2 * q]), 0.f);
+          const float hi = fmaxf(fmaf(__uint_as_float(wv[q] & 0xffff0000u), sc[2 * q + 1], sh[2 * q + 1]), 0.f);
+          o[q] = pack_bf16x2(lo, hi);
         }
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(zq), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
       }
     }
   }
