@@ -13,6 +13,13 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   return v;
 }
 
+// two floats -> bf16x2 with ReLU in the conversion: max(x, 0) then round-to-nearest, the same values as fmaxf + cvt
+__device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
 // 256-bit global store / load (sm_100: STG.E.ENL2.256 / LDG.E.ENL2.256); the address must be 32-byte aligned
 __device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x),
@@ -53,10 +60,17 @@ __device__ __forceinline__ void epi_fast_chunk(const uint32_t (&acc)[16], const 
         }
       }
       uint4 o;
-      o.x = pack_bf16x2(fmaxf(v[0], lo), fmaxf(v[1], lo));
-      o.y = pack_bf16x2(fmaxf(v[2], lo), fmaxf(v[3], lo));
-      o.z = pack_bf16x2(fmaxf(v[4], lo), fmaxf(v[5], lo));
-      o.w = pack_bf16x2(fmaxf(v[6], lo), fmaxf(v[7], lo));
+      if (lo == 0.f) {                        // ReLU rides on the conversion (F2FP.RELU): no separate max per element
+        o.x = pack_bf16x2_relu(v[0], v[1]);
+        o.y = pack_bf16x2_relu(v[2], v[3]);
+        o.z = pack_bf16x2_relu(v[4], v[5]);
+        o.w = pack_bf16x2_relu(v[6], v[7]);
+      } else {
+        o.x = pack_bf16x2(fmaxf(v[0], lo), fmaxf(v[1], lo));
+        o.y = pack_bf16x2(fmaxf(v[2], lo), fmaxf(v[3], lo));
+        o.z = pack_bf16x2(fmaxf(v[4], lo), fmaxf(v[5], lo));
+        o.w = pack_bf16x2(fmaxf(v[6], lo), fmaxf(v[7], lo));
+      }
       o2[h] = o;
       if (STAGED) sts128(srow_addr + (uint32_t)cl * 2u, o);
       else if (grow && !(wide && c0 + 16 <= ncols)) *reinterpret_cast<uint4*>(grow + cl) = o;

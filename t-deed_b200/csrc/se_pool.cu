@@ -79,10 +79,10 @@ __device__ __forceinline__ float reduce_scatter(float (&acc)[F], int lane) {
   return acc[0];                                 // sum over the warp for frame (lane % F)
 }
 
-constexpr int SE_FC_THREADS = 512;
+constexpr int SE_FC_THREADS = 384;
 
 template <int F>
-__global__ void __launch_bounds__(SE_FC_THREADS, (F <= 16 ? 2 : 1))
+__global__ void __launch_bounds__(SE_FC_THREADS, (F <= 16 ? 3 : 1))
 se_fc_kernel(const float* __restrict__ mean, int n, int c, int rd, const float* __restrict__ w1,
              const float* __restrict__ b1, const float* __restrict__ w2t, const float* __restrict__ b2,
              float* __restrict__ scale) {

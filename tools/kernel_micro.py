@@ -42,6 +42,8 @@ if 'se' in what:
         b1 = torch.randn(rd, device=dev) * 0.1
         w2 = torch.randn(rd, c, device=dev) * 0.1
         b2 = torch.randn(c, device=dev) * 0.1
+        tg = timeit(lambda: ops.se_gate(x, w1, b1, w2, b2))
+        print('se_gate n=%d hw=%d c=%d rd=%d: %.1f us (mean+fc)' % (n, hw, c, rd, tg), flush=True)
         t = timeit(lambda: ops.se_(x, w1, b1, w2, b2))
         print('se   n=%d hw=%d c=%d rd=%d: %.1f us total (mean+fc+scale), %.2f TB/s on 3 passes' % (n, hw, c, rd, t, 3 * x.numel() * 2 / t / 1e6), flush=True)
 if 'gsf' in what:
