@@ -69,6 +69,50 @@ class EngineConfig:
             prev = w
 
 
+PAD_LIMIT = 1.07      # 56 -> 64 (stage 2, +14 % bytes) was measured too: no gain
+
+
+def padded_width(w):
+    """bf16 rows of `w` channels are w*2 bytes; the GEMM / grouped-conv epilogues store 32 bytes per instruction when every row
+    starts on a 32-byte boundary (w % 16 == 0).  Widths that miss it by <= 7 % are zero-padded (RegNetY-200MF stage 3: 152 -> 160,
+    +5 % bytes, conv1 GEMM 218 -> 145 us per 57-clip batch); the pad channels carry exact zeros through the whole block."""
+    wp = (w + 15) // 16 * 16
+    return wp if wp != w and wp <= PAD_LIMIT * w else w
+
+
+def _pad_to(t, shape, fill=0.0):
+    out = torch.full(shape, fill, dtype=t.dtype)
+    out[tuple(slice(0, n) for n in t.shape)] = t
+    return out
+
+
+def pad_block_state(sd, p, cin, cout, cin_p, cout_p, shifted):
+    """Zero-pad the tensors of bottleneck `p` from (cin, cout) to (cin_p, cout_p) channels: padded output channels get zero
+    weights, zero BN scale / shift (weight 0, bias 0, mean 0, var 1) and zero SE columns, padded input channels zero columns."""
+    if (cin, cout) == (cin_p, cout_p):
+        return
+
+    def bn(q, n):
+        for k, fill in (('weight', 0.0), ('bias', 0.0), ('running_mean', 0.0), ('running_var', 1.0)):
+            sd[q + '.' + k] = _pad_to(sd[q + '.' + k], (n,), fill)
+
+    c1 = p + ('.conv1.net' if shifted else '.conv1')
+    sd[c1 + '.conv.weight'] = _pad_to(sd[c1 + '.conv.weight'], (cout_p, cin_p, 1, 1))
+    bn(c1 + '.bn', cout_p)
+    w2 = sd[p + '.conv2.conv.weight']
+    sd[p + '.conv2.conv.weight'] = _pad_to(w2, (cout_p,) + tuple(w2.shape[1:]))
+    bn(p + '.conv2.bn', cout_p)
+    rd = sd[p + '.se.fc1.weight'].shape[0]
+    sd[p + '.se.fc1.weight'] = _pad_to(sd[p + '.se.fc1.weight'], (rd, cout_p, 1, 1))
+    sd[p + '.se.fc2.weight'] = _pad_to(sd[p + '.se.fc2.weight'], (cout_p, rd, 1, 1))
+    sd[p + '.se.fc2.bias'] = _pad_to(sd[p + '.se.fc2.bias'], (cout_p,))
+    sd[p + '.conv3.conv.weight'] = _pad_to(sd[p + '.conv3.conv.weight'], (cout_p, cout_p, 1, 1))
+    bn(p + '.conv3.bn', cout_p)
+    if (p + '.downsample.conv.weight') in sd:
+        sd[p + '.downsample.conv.weight'] = _pad_to(sd[p + '.downsample.conv.weight'], (cout_p, cin_p, 1, 1))
+        bn(p + '.downsample.bn', cout_p)
+
+
 def _bn_fold(sd, p, eps=1e-5):
     scale = sd[p + '.weight'].float() / torch.sqrt(sd[p + '.running_var'].float() + eps)
     shift = sd[p + '.bias'].float() - sd[p + '.running_mean'].float() * scale
@@ -117,7 +161,16 @@ class InferenceEngine:
         W['stem2_wimg'], W['stem2_b0'], W['stem2_pad'] = ops.stem_tc2_weights(W['stem_w'], W['stem_b'])   # raw-pixel stem (stem_tc2.cu)
         gw = REGNET[cfg.backbone]['group_width']
         blocks = []
+        feat = cfg.feat_dim
         for p, cin, cout, stride, shifted in cfg.blocks():
+            fd_real = fold_dim(cin)
+            if adt == torch.bfloat16:
+                # 32-byte aligned activation rows for the inner stages (the last stage's width is the feature dimension)
+                cin_p = padded_width(cin) if cin != 32 else cin
+                cout_p = padded_width(cout) if cout != feat else cout
+                assert fold_dim(cin_p) == fd_real or not shifted
+                pad_block_state(sd, p, cin, cout, cin_p, cout_p, shifted)
+                cin, cout = cin_p, cout_p
             b = dict(cin=cin, cout=cout, stride=stride, shifted=shifted, gw=gw)
             c1 = p + ('.conv1.net' if shifted else '.conv1')
             sc, sh = _bn_fold(sd, c1 + '.bn')
@@ -126,7 +179,7 @@ class InferenceEngine:
                 # K layout of the virtual concat [gate-shift out (fold, padded to 8) | x[:, xs:]]: TMA box origins
                 # must be 16-byte aligned, so the x segment starts at the multiple of 8 below `fold`; the few
                 # overlapped channels / pad columns get zero weights.
-                fd = fold_dim(cin)
+                fd = fd_real
                 fdp, xs = _round8(fd), fd // 8 * 8
                 wp = torch.zeros((cout, fdp + cin - xs), dtype=torch.float32, device=dev)
                 # the gate-shift kernel writes its channels in input order (ops.gsf natural=True): the reference's channel
@@ -156,7 +209,7 @@ class InferenceEngine:
                 b['bd'] = f32(sh)
             if shifted:
                 g = p + '.conv1.gs'
-                fd = fold_dim(cin)
+                fd = fd_real
                 sc, sh = _bn_fold(sd, g + '.bn')
                 gs = dict(fold=fd, bn_scale=f32(sc), bn_shift=f32(sh), w3d=f32(sd[g + '.conv3D.weight'].reshape(-1)),
                           b3d=f32(sd[g + '.conv3D.bias']))

@@ -15,6 +15,14 @@ CASES = [('K368 lda368', 368, 0, 368, 256, 256, 0), ('K368 lda384', 384, 0, 368,
          ('K368 lda368 N368', 368, 0, 368, 368, 368, 0), ('K384 lda384 N384 ldo384', 384, 0, 384, 384, 384, 0),
          ('K384 lda384 N368 ldo384', 384, 0, 384, 368, 384, 0),
          ('K368 lda368 N368 res', 368, 0, 368, 368, 368, 368), ('K384 lda384 N384 res ld384', 384, 0, 384, 384, 384, 384)]
+M3 = 5700 * 196
+CASES3 = [('s3 K152 lda152 N152 res', 152, 0, 152, 152, 152, 152), ('s3 K128 lda152 N152 res', 152, 0, 128, 152, 152, 152),
+          ('s3 K192 lda192 N152 res', 192, 0, 192, 152, 152, 152), ('s3 K152 lda152 N152', 152, 0, 152, 152, 152, 0),
+          ('s3 K128 lda152 N152', 152, 0, 128, 152, 152, 0), ('s3 K192 lda192 N152', 192, 0, 192, 152, 152, 0),
+          ('s3 K64 lda152 N152', 152, 0, 64, 152, 152, 0), ('s3 K160 lda160 N160', 160, 0, 160, 160, 160, 0),
+          ('s3 K160 lda160 N160 res', 160, 0, 160, 160, 160, 160), ('s3 K152 N152 ldo160', 152, 0, 152, 152, 160, 0), ('s3 K152 N128', 152, 0, 152, 128, 128, 0), ('s3 K152 N64', 152, 0, 152, 64, 64, 0)]
+if os.environ.get('S3'):
+    CASES, M4 = CASES3, M3
 for name, lda, col0, k, n, ldo, ldr in CASES:
     a = torch.randn(M4, lda, device=dev).to(torch.bfloat16)
     w = torch.randn(n, k, device=dev).to(torch.bfloat16)
