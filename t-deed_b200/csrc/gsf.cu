@@ -21,6 +21,7 @@
 // concat with the untouched channels of x (tdeed_gemm_fwd segments).
 //
 // workspace layout (floats): gate [N*hw*2] | sums [N*fold*2] (y, r) | wgt [N*fold] | Q [N*hw*6]
+#include <cstdlib>
 #include <type_traits>
 #include "common.cuh"
 
@@ -732,6 +733,13 @@ static int launch_gsf(int mode, const void* x, int clips, int clip_len, int h, i
     const int rpp = GT_THREADS / (foldp / 8);
     int R = 0, FT = 0, MT = 0;
     size_t z_bytes = 0, smem_tc = 0;
+    static int gt_budget = -1, gt_ftmax = 4;
+    if (gt_budget < 0) {
+      const char* e1 = tdeed::dev_env("TDEED_GT_BUDGET_KB");
+      const char* e2 = tdeed::dev_env("TDEED_GT_FTMAX");
+      gt_budget = e1 ? atoi(e1) * 1024 : GT_SMEM_BUDGET;
+      gt_ftmax = e2 ? atoi(e2) : 4;
+    }
     auto plan = [&](int rb, int ft) {
       const int r = ceil_div(h, rb), mt = ceil_div(r * wp, 16);
       size_t zb = ((size_t)(ft + 2) * (r + 2) * wp + 16) * pitch;
@@ -740,7 +748,7 @@ static int launch_gsf(int mode, const void* x, int clips, int clip_len, int h, i
       if (zb < part) zb = part;
       zb = (zb + 15) / 16 * 16;
       const size_t total = (size_t)9 * ks * 256 + zb + (size_t)ft * mt * 512 + (size_t)ft * r * w * 8;
-      if (total > (size_t)GT_SMEM_BUDGET || ceil_div((r + 2) * wp, rpp) > GT_NI) return false;
+      if (total > (size_t)gt_budget || ceil_div((r + 2) * wp, rpp) > GT_NI) return false;
       RB = ceil_div(h, r); R = r; FT = ft; MT = mt; z_bytes = zb; smem_tc = total;
       return true;
     };
@@ -748,12 +756,13 @@ static int launch_gsf(int mode, const void* x, int clips, int clip_len, int h, i
     if (!copy_tail && foldp <= 8 * GT_THREADS && clip_len >= 1 && (long long)hw * c < (1ll << 31)) {
       for (int minft = 2; minft >= 1 && !ok; --minft)
         for (int rb = 1; rb <= h && !ok; ++rb)
-          for (int ft = (clip_len < 4 ? clip_len : 4); ft >= minft && !ok; --ft) ok = plan(rb, ft);
+          for (int ft = (clip_len < gt_ftmax ? clip_len : gt_ftmax); ft >= minft && !ok; --ft) ok = plan(rb, ft);
     }
     // the partial sums of RB > 1 row blocks live in the (otherwise unused) Q region, the packed weights behind it.  The choice
     // of the path must not depend on the number of clips: a batch and its clips one by one give bit-identical results.
     if (ok && (RB == 1 || (size_t)RB * fold * 2 <= (size_t)hw * 6) && ceil_div(clip_len, FT) <= 65535 && clips <= 65535) {
       uint2* wB = reinterpret_cast<uint2*>(Q + ((size_t)n * hw * 6 + 3) / 4 * 4);
+      if (tdeed::dev_env("TDEED_GT_TRACE")) fprintf(stderr, "gate_tc plan: %dx%d fold %d -> RB %d R %d FT %d MT %d smem %zu\n", h, w, fold, RB, R, FT, MT, smem_tc);
       float* sums_part = RB > 1 ? Q : sums;
       gsf_pack_w_kernel<<<ceil_div(9 * ks * 32, 128), 128, 0, st>>>(w3d, fold, ks, wB);
       int rc0 = check_launch("tdeed_gsf_fwd(pack)");
@@ -772,7 +781,7 @@ static int launch_gsf(int mode, const void* x, int clips, int clip_len, int h, i
       }
       static bool tc_set[7] = {false, false, false, false, false, false, false};
       if (!tc_set[kidx]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BUDGET);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         TDEED_REQUIRE(e == cudaSuccess, TDEED_ERR_CUDA, "tdeed_gsf_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         tc_set[kidx] = true;
       }

@@ -91,6 +91,27 @@ def test_golden_bf16(name, golden_dir, dev):
         assert np.abs(probs - g['probs']).max() < BF16_TOL_PROBS
 
 
+def test_padded_stage_width_is_bit_identical(dev, monkeypatch):
+    """The bf16 engine zero-pads RegNetY-200MF's stage 3 from 152 to 160 channels (32-byte activation rows, engine.padded_width):
+    the pad channels carry exact zeros, so the network output must not change by a single bit."""
+    from tdeed_b200 import engine as E
+    cfg = O.Config(feature_arch='rny002_gsf', clip_len=8, n_layers=2, sgp_ks=5, sgp_r=4, num_classes=4,
+                   radi_displacement=2, crop_dim=None)
+    g = torch.Generator().manual_seed(3)
+    frames = torch.randint(0, 256, (2, 8, 3, 64, 96), generator=g, dtype=torch.uint8)
+    assert E.padded_width(152) == 160 and E.padded_width(368) == 368 and E.padded_width(56) == 56
+    m = build(cfg, O.random_state(cfg, 9), dev)
+    widths = [b['cout'] for b in m._model.engine('bf16').W['blocks']]
+    assert 160 in widths and 152 not in widths
+    _, p_pad = m.predict(frames, use_amp=True, use_graph=False)
+    monkeypatch.setattr(E, 'PAD_LIMIT', 1.0)
+    m2 = build(cfg, O.random_state(cfg, 9), dev)
+    widths2 = [b['cout'] for b in m2._model.engine('bf16').W['blocks']]
+    assert 152 in widths2 and 160 not in widths2
+    _, p_ref = m2.predict(frames, use_amp=True, use_graph=False)
+    assert np.array_equal(p_pad, p_ref)
+
+
 def test_graph_replay_matches_eager_and_tracks_weight_updates(dev):
     cfg = O.Config(feature_arch='rny002_gsf', clip_len=8, n_layers=2, sgp_ks=5, sgp_r=4, num_classes=4,
                    radi_displacement=2, crop_dim=32)
