@@ -156,7 +156,9 @@ int tdeed_linear_fwd(const float* x, int M, int C, const float* W, const float* 
 int tdeed_linear_bwd_data(const float* dout, int ldd, int M, int C, const float* W, int N, const float* add, float* dx,
                           void* stream);
 /* F.cross_entropy(weight=class_weight) with int64 class targets (weighted mean) or probability targets (mean over rows)
- * + F.mse_loss(displ, labelD).mean()  (model/model.py:308-319).  loss_out fp32 [3] = total, CE, MSE. */
+ * + F.mse_loss(displ, labelD).mean()  (model/model.py:308-319).  loss_out fp32 [3] = total, CE, MSE.
+ * An int64 target outside [0, K) (its head's range in the two-head variant) makes torch raise; the kernels never index out of
+ * bounds (the label is clamped) and report it as a NaN loss (total and CE). */
 int tdeed_ce_mse_loss(const float* logits, int M, int K, int ld_logits, const long long* target_hard,
                       const float* target_soft, const float* class_weight, const float* displ, const float* labelD,
                       float* loss_out, float* dlogits, float* ddispl, void* stream);

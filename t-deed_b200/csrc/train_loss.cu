@@ -84,6 +84,7 @@ ce_mse_loss_kernel(const float* __restrict__ logits, int M, int K, int ld, const
                    float* __restrict__ ddispl) {
   __shared__ float s_red[32];
   float lsum = 0.f, wsum = 0.f, msum = 0.f;
+  int bad = 0;                                   // a hard label outside [0, K): F.cross_entropy raises; here the loss becomes NaN
   for (int m = threadIdx.x; m < M; m += 256) {
     const float* z = logits + (size_t)m * ld;
     float mx = z[0];
@@ -92,7 +93,9 @@ ce_mse_loss_kernel(const float* __restrict__ logits, int M, int K, int ld, const
     for (int j = 0; j < K; ++j) se += expf(z[j] - mx);
     const float lse = mx + logf(se);
     if (hard) {
-      const int y = (int)hard[m];
+      const long long yl = hard[m];
+      bad |= (yl < 0 || yl >= K) ? 1 : 0;
+      const int y = (int)min(max(yl, 0ll), (long long)K - 1);       // never index out of bounds
       const float w = cw ? cw[y] : 1.f;
       lsum += w * (lse - z[y]);
       wsum += w;
@@ -110,8 +113,9 @@ ce_mse_loss_kernel(const float* __restrict__ logits, int M, int K, int ld, const
   wsum = block_sum(wsum, s_red);
   msum = block_sum(msum, s_red);
   const float denom = hard ? wsum : (float)M;
+  const int any_bad = __syncthreads_or(bad);
   if (threadIdx.x == 0) {
-    const float ce = lsum / denom, mse = displ ? msum / (float)M : 0.f;
+    const float ce = any_bad ? __int_as_float(0x7fc00000) : lsum / denom, mse = displ ? msum / (float)M : 0.f;
     out[0] = ce + mse;
     out[1] = ce;
     out[2] = mse;
@@ -124,7 +128,7 @@ ce_mse_loss_kernel(const float* __restrict__ logits, int M, int K, int ld, const
     for (int j = 0; j < K; ++j) se += expf(z[j] - mx);
     const float inv = 1.f / se;
     if (hard) {
-      const int y = (int)hard[m];
+      const int y = (int)min(max(hard[m], 0ll), (long long)K - 1);
       const float w = (cw ? cw[y] : 1.f) / denom;
       for (int j = 0; j < K; ++j) dlogits[(size_t)m * K + j] = w * (expf(z[j] - mx) * inv - (j == y ? 1.f : 0.f));
     } else {
@@ -149,6 +153,7 @@ ce_mse_loss_2h_kernel(const float* __restrict__ logits, int B, int T, int n1, in
   __shared__ float s_red[32];
   const int K = n1 + n2, M = B * T;
   float total = 0.f;
+  int bad = 0;                                   // a hard label outside its head's range: the loss becomes NaN (torch raises)
   for (int b = 0; b < B; ++b) {
     const int ds = dataset[b];
     const int c0 = ds == 2 ? n1 : 0, k = ds == 2 ? n2 : n1;
@@ -163,7 +168,9 @@ ce_mse_loss_2h_kernel(const float* __restrict__ logits, int B, int T, int n1, in
         for (int j = 0; j < k; ++j) se += expf(z[j] - mx);
         const float lse = mx + logf(se);
         if (hard) {
-          const int y = (int)hard[m] - c0;
+          const long long yl = hard[m] - c0;
+          bad |= (yl < 0 || yl >= k) ? 1 : 0;
+          const int y = (int)min(max(yl, 0ll), (long long)k - 1);
           const float w = cw ? cw[y] : 1.f;
           lsum += w * (lse - z[y]);
           wsum += w;
@@ -190,7 +197,7 @@ ce_mse_loss_2h_kernel(const float* __restrict__ logits, int B, int T, int n1, in
       for (int j = 0; j < k; ++j) se += expf(z[j] - mx);
       const float inv = 1.f / se;
       if (hard) {
-        const int y = (int)hard[m] - c0;
+        const int y = (int)min(max(hard[m] - c0, 0ll), (long long)k - 1);
         const float w = (cw ? cw[y] : 1.f) / denom;
         for (int j = 0; j < k; ++j) dz[c0 + j] = w * (expf(z[j] - mx) * inv - (j == y ? 1.f : 0.f));
       } else {
@@ -210,6 +217,8 @@ ce_mse_loss_2h_kernel(const float* __restrict__ logits, int B, int T, int n1, in
     }
   }
   msum = block_sum(msum, s_red);
+  const int any_bad = __syncthreads_or(bad);
+  if (any_bad) total = __int_as_float(0x7fc00000);
   if (threadIdx.x == 0) {
     const float mse = displ ? msum / (float)M : 0.f;
     out[0] = total + mse;

@@ -443,6 +443,32 @@ def test_loss_and_heads(soft, K, displ):
     assert rel(T().colsum(dlogits), br.grad) < 1e-4
 
 
+def test_loss_flags_out_of_range_labels():
+    """F.cross_entropy raises on a target outside [0, K); the fused loss must not read out of bounds and poisons the loss (NaN)."""
+    g = torch.Generator(device=DEV).manual_seed(3)
+    M, K = 64, 5
+    logits = torch.randn((M, K), device=DEV, generator=g)
+    cw = torch.ones(K, device=DEV)
+    t = torch.randint(0, K, (M,), device=DEV, generator=g)
+    loss, dl, _ = T().ce_mse_loss(logits, t, None, cw, None, None)
+    assert bool(torch.isfinite(loss).all())
+    for bad in (K, -1, 10 ** 9):
+        tb = t.clone()
+        tb[17] = bad
+        loss, dl, _ = T().ce_mse_loss(logits, tb, None, cw, None, None)
+        assert bool(torch.isnan(loss[0])) and bool(torch.isnan(loss[1])) and bool(torch.isfinite(dl).all())
+    # two heads: a dataset-2 label that was not shifted by n1 (update_labels_2heads skipped) is out of its head's range
+    B, Tn, n1, n2 = 2, 16, 3, 4
+    lg = torch.randn((B * Tn, n1 + n2), device=DEV, generator=g)
+    ds = torch.tensor([1, 2], dtype=torch.int32, device=DEV)
+    hard = torch.cat([torch.randint(0, n1, (Tn,), device=DEV, generator=g), n1 + torch.randint(0, n2, (Tn,), device=DEV, generator=g)])
+    loss, _, _ = T().ce_mse_loss_2heads(lg, B, Tn, n1, n2, ds, hard, None, torch.ones(n1 + n2, device=DEV), None, None)
+    assert bool(torch.isfinite(loss).all())
+    hard[Tn + 3] = 1                                      # dataset 2, label < n1
+    loss, _, _ = T().ce_mse_loss_2heads(lg, B, Tn, n1, n2, ds, hard, None, torch.ones(n1 + n2, device=DEV), None, None)
+    assert bool(torch.isnan(loss[0]))
+
+
 def test_dropout_and_adamw():
     g = torch.Generator(device=DEV).manual_seed(9)
     x = torch.randn((400, 368), device=DEV, generator=g)
