@@ -62,10 +62,12 @@ if 'gsf' in what:
         print('gsf  %dx%dx%d fold=%d: %.1f us (q+gate+weight+blend)' % (h, h, c, fold, t), flush=True)
 if 'c3' in what:
     # grouped 3x3 conv (tcgen05) at the layer shapes of one 57-clip batch (upper) and one 1425-frame chunk (lower)
-    shapes = ((N, 14, 152, 8, 1), (N, 7, 368, 8, 1), (N, 28, 152, 8, 2), (N, 14, 368, 8, 2), (1425, 56, 56, 8, 2), (1425, 112, 24, 8, 2))
+    shapes = ((N, 14, 160, 8, 1), (N, 7, 368, 8, 1), (N, 28, 152, 8, 2), (N, 14, 368, 8, 2), (1425, 56, 56, 8, 2), (1425, 112, 24, 8, 2))
     if os.environ.get('C3_FAMILY') == 'rny008':
         shapes = ((N, 14, 320, 16, 1), (N, 7, 768, 16, 1), (N, 28, 320, 16, 2), (N, 14, 768, 16, 2), (1425, 28, 128, 16, 1),
                   (1425, 56, 128, 16, 2), (1425, 112, 64, 16, 2))
+    if os.environ.get('C3_SHAPE'):
+        shapes = (shapes[int(os.environ['C3_SHAPE'])],)
     for (n, h, c, gw, stride) in shapes:
         x = torch.randn(n, h, h, c, device=dev).to(torch.bfloat16)
         wimg = ops.conv3_weight_image(torch.randn(c, gw, 3, 3, device=dev) * 0.1, gw)
