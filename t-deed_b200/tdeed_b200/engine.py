@@ -560,6 +560,17 @@ class InferenceEngine:
         key = ('lower', frames.data_ptr(), tuple(frames.shape), frames.dtype, bool(flip), crop)
         return self.graphed(key, lambda: self.lower(frames, flip=flip, crop=crop))
 
+    def upper_feat_graphed(self, x, b, t):
+        """upper() alone on a static clip-major feature buffer: the pooled per-frame features (b*t, feat_dim) fp32."""
+        key = ('upper_feat', x.data_ptr(), tuple(x.shape), b, t)
+        return self.graphed(key, lambda: self.upper(x, b, t))
+
+    def temporal_heads_graphed(self, feat, b, t):
+        """temporal() + heads() on a static (b*t, feat_dim) feature buffer — the clips of several backbone batches at once: the
+        temporal stack is a few dozen small launches whose time barely depends on b."""
+        key = ('temporal', feat.data_ptr(), b, t)
+        return self.graphed(key, lambda: self.heads(self.temporal(feat.view(b, t, self.cfg.feat_dim))))
+
     def upper_graphed(self, x, b, t):
         """upper() + temporal() + heads() on a static clip-major feature buffer x (b*t, h, w, c)."""
         key = ('upper', x.data_ptr(), tuple(x.shape), b, t)

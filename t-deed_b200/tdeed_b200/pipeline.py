@@ -167,7 +167,8 @@ class VideoInference:
     PCIe four times.  Here the frames of all videos form ONE stream: unique frames are uploaded once into one of two
     `frames_per_chunk`-frame device buffers (side stream, overlapping the kernels of the previous chunk), run through
     InferenceEngine.lower() once (twice with the flipped TTA view) and filed into a ring of per-frame features in HBM; clip
-    batches are gathered from the ring (tdeed_gather_rows) and finished by upper() + temporal() + heads().  Frames before 0 /
+    batches are gathered from the ring (tdeed_gather_rows), finished by upper(), and the temporal stack + heads run over the
+    pooled features of a few batches at once.  Frames before 0 /
     past the end of a video read the features of the all-zero frame, exactly what the reference's zero padding
     (dataset/frame.py:622-625) produces.  Results are bit-identical to per-clip execution (tests/test_gpu_video.py): no
     kernel of the lower part mixes frames, and clip order == accumulation order.
@@ -178,11 +179,14 @@ class VideoInference:
     """
 
     def __init__(self, engine, in_hw, clips_per_batch=57, frames_per_chunk=None, flips=(False,), clip_len=None,
-                 upload_crop=True):
+                 upload_crop=True, temporal_batches=None):
         self.eng = engine
         self.dev = engine.device
         self.T = clip_len or engine.cfg.clip_len
         self.B = clips_per_batch
+        # The temporal stack + heads run once per `temporal_batches` backbone batches (their pooled features wait in a stash):
+        # ~40 small launches whose time barely depends on the number of clips (3 x 57 clips: 3.5 -> ~2 ms per video).
+        self.temporal_batches = temporal_batches or max(1, min(8, 171 // self.B))
         self.N = frames_per_chunk or max(self.T, self.B * max(1, self.T // 4))
         self.flips = tuple(flips)
         self.K = engine.cfg.num_classes + 1
@@ -219,6 +223,8 @@ class VideoInference:
         if self.ring is None:
             self.ring = [torch.empty((self.W_slots,) + tuple(f.shape), dtype=f.dtype, device=self.dev) for f in pad]
             self.xg = [torch.empty((self.B * self.T,) + tuple(f.shape), dtype=f.dtype, device=self.dev) for f in pad]
+            self.stash = [torch.empty((self.temporal_batches * self.B * self.T, eng.cfg.feat_dim), dtype=torch.float32, device=self.dev)
+                          for _ in pad]
             self.pad = pad
         else:                       # new weights (engine.load_state): same buffers (graphs may be keyed on them), new contents
             for dst, f in zip(self.pad, pad):
@@ -311,6 +317,7 @@ class VideoInference:
         scores = {name: VideoScores(vlen, K, self.dev) for name, vlen, _ in videos}
         chunks = iter(chunks)
         self.frames_in, self._fill = 0, 0
+        pending = []                                     # batches whose features wait in the stash for the temporal stack
         for lo in range(0, len(clips), B):
             batch = clips[lo:lo + B]
             need = 0
@@ -328,34 +335,47 @@ class VideoInference:
                     self._flush()                # end of the stream: ragged last chunk
                 else:
                     raise RuntimeError('frame stream ended after %d frames; the clip list needs %d' % (self.frames_in, need))
-            outs = []
+            # backbone (stages 3-4) of this batch -> pooled features, parked in slot len(pending) of the feature stash
+            j = len(pending)
             for fi in range(len(self.flips)):
                 ops.gather_clip_rows(self.ring[fi], self.pad[fi], self.xg[fi], T, first, los, his)
+                feat = eng.upper_feat_graphed(self.xg[fi], B, T) if self.use_graphs else eng.upper(self.xg[fi], B, T)
+                self.stash[fi][j * B * T:(j + 1) * B * T].copy_(feat)
+                self.launches += 2
+            pending.append((lo, batch))
+            if len(pending) < self.temporal_batches and lo + B < len(clips):
+                continue
+            # temporal stack + heads once for all parked batches (clip results do not depend on the batch they ride in)
+            k = len(pending)
+            outs = []
+            for fi in range(len(self.flips)):
+                fview = self.stash[fi][:k * B * T]
                 if self.use_graphs:
-                    _, _, probs = eng.upper_graphed(self.xg[fi], B, T)
+                    _, _, probs = eng.temporal_heads_graphed(fview, k * B, T)
                 else:
-                    _, _, probs = eng.heads(eng.temporal(eng.upper(self.xg[fi], B, T).view(B, T, eng.cfg.feat_dim)))
+                    _, _, probs = eng.heads(eng.temporal(fview.view(k * B, T, eng.cfg.feat_dim)))
                 outs.append(probs)
-                self.launches += 1
-            nb = len(batch)
-            if tta:     # the reference adds plain then flipped view clip by clip (util/eval.py:321-349): keep that order
-                probs = torch.stack(outs, dim=1)[:nb].reshape(nb * len(outs), T, K)
-            else:
-                probs = outs[0][:nb]
             rep = len(outs) if tta else 1
-            bi = 0
-            while bi < nb:                      # clips of one batch may belong to several videos
-                name = batch[bi][0]
-                bj = bi
-                while bj < nb and batch[bj][0] == name:
-                    bj += 1
-                st = [batch[i][2] for i in range(bi, bj) for _ in range(rep)]
-                scores[name].add(probs[bi * rep:bj * rep], st, tta=tta)
-                self.launches += 1
-                if on_video is not None and last_clip[name] == lo + bj - 1:
-                    on_video(name, scores[name])
-                bi = bj
-            self.clips_out += nb
+            for j, (blo, bbatch) in enumerate(pending):
+                nb = len(bbatch)
+                if tta:  # the reference adds plain then flipped view clip by clip (util/eval.py:321-349): keep that order
+                    probs = torch.stack([o[j * B:j * B + nb] for o in outs], dim=1).reshape(nb * len(outs), T, K)
+                else:
+                    probs = outs[0][j * B:j * B + nb]
+                bi = 0
+                while bi < nb:                      # clips of one batch may belong to several videos
+                    name = bbatch[bi][0]
+                    bj = bi
+                    while bj < nb and bbatch[bj][0] == name:
+                        bj += 1
+                    st = [bbatch[i][2] for i in range(bi, bj) for _ in range(rep)]
+                    scores[name].add(probs[bi * rep:bj * rep], st, tta=tta)
+                    self.launches += 1
+                    if on_video is not None and last_clip[name] == blo + bj - 1:
+                        on_video(name, scores[name])
+                    bi = bj
+                self.clips_out += nb
+            pending = []
         return scores
 
 
