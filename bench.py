@@ -246,6 +246,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours')
     ap.add_argument('--clips-per-batch', type=int, default=57)
+    ap.add_argument('--frames-per-chunk', type=int, default=0, help='frames per lower() launch of the video-level engine (default: clips_per_batch * 25)')
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--workload', default='infer', choices=['infer', 'train'],
@@ -317,7 +318,7 @@ def main():
     if per_clip:
         vi = VideoInference(eng, (FRAME_H, FRAME_W), clips_per_batch=B, frames_per_chunk=B * T, flips=(False,))
     else:
-        vi = VideoInference(eng, (FRAME_H, FRAME_W), clips_per_batch=B, frames_per_chunk=B * HOP, flips=(False,))
+        vi = VideoInference(eng, (FRAME_H, FRAME_W), clips_per_batch=B, frames_per_chunk=args.frames_per_chunk or B * HOP, flips=(False,))
 
     def pieces(src, n):
         for lo in range(0, VIDEO_FRAMES, n):
