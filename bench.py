@@ -293,6 +293,7 @@ def main():
     import contextlib
     import io
     with contextlib.redirect_stdout(io.StringIO()):
+        torch.manual_seed(0)             # the conv / linear weights come from torch's default init: the same on every run and rank
         model = TDEEDModel(device='cuda:%d' % local, args=model_args())
     randomize_(model._model, seed=0)
     model._model.eval()

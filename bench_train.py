@@ -160,6 +160,7 @@ def run_train(args, quiet=False):
     prof = _Profiler()
     prof.install()
     with contextlib.redirect_stdout(io.StringIO()):
+        torch.manual_seed(0)             # the conv / linear weights come from torch's default init: the same on every run and rank
         model = TDEEDModel(device='cuda:%d' % local, args=train_args())
     randomize_(model._model, seed=0)                      # same weights on every rank (DP replicas)
     model.train_precision = args.precision
