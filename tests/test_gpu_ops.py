@@ -249,7 +249,9 @@ def test_se_and_pool(dev, c, rd, hw):
                                              # bf16 activations (the inference engine's path): the real layer shapes of rny002 / rny008
                                              (12, 56, (28, 50), 'bf16'), (36, 152, (14, 25), 'bf16'), (92, 368, (7, 13), 'bf16'),
                                              (32, 128, (9, 7), 'bf16'), (80, 320, (5, 6), 'bf16'), (192, 768, (2, 3), 'bf16'),
-                                             (4, 16, (3, 3), 'bf16')])
+                                             (4, 16, (3, 3), 'bf16'),
+                                             # wide frames (SoccerNetBall 448x796 -> 56x100 at stage 3): many row blocks per frame
+                                             (32, 128, (6, 100), 'bf16')])
 def test_gate_shift(dev, mode, fold, c, hw, dtype):
     from tdeed_b200 import _lib as L, ops
     g = torch.Generator().manual_seed(4)

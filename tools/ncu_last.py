@@ -1,3 +1,4 @@
+"""Last (warm) record per (kernel, grid) of an `ncu --csv --metrics ...` log: python tools/ncu_last.py log.csv"""
 import csv,collections,sys
 rows=list(csv.reader(open(sys.argv[1])))
 hdr=None; recs=collections.OrderedDict()

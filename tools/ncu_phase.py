@@ -1,3 +1,5 @@
+"""Instruction / stall-sample share per kernel phase (source lines that start with `// ----`) from the same export as ncu_src.py:
+python tools/ncu_phase.py export.csv path/to/kernel.cu"""
 import csv,sys,re
 rows=list(csv.reader(open(sys.argv[1])))
 src=open(sys.argv[2]).read().split('\n')

@@ -1,3 +1,5 @@
+"""Hot source lines of an `ncu -i rep --page source --csv --print-source cuda,sass` export (share of stall samples and of executed
+instructions per CUDA line): python tools/ncu_src.py export.csv [min_share]"""
 import csv,sys
 rows=list(csv.reader(open(sys.argv[1])))
 thr=float(sys.argv[2]) if len(sys.argv)>2 else 0.012
