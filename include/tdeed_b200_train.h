@@ -137,6 +137,10 @@ int tdeed_cast_f32(const float* in, long long n, void* out, int out_dtype, void*
  * tdeed_aug_gray_mean: mean[n] of the grayscale image (the pivot of adjust_contrast).
  * tdeed_aug_contrast_blur_flip: contrast (pivot mean[frame]) -> 5x5 Gaussian (kernel1d_host: 5 host floats, reflect padding) ->
  * horizontal flip; x and out must not alias. */
+/* mixup of two uint8 clip batches (model/model.py:228-254): out[s, i] = fl32(lam[s][0]) * a[s, i] + fl32(lam[s][1]) * b[s, i],
+ * the reference's arithmetic (two rounded products, one rounded sum) in one pass; a, b: u8 [n_samples, per_sample] (per_sample a
+ * multiple of 16, 16-byte aligned), lam: fp32 [n_samples][2] on the device, out: fp32 [n_samples, per_sample]. */
+int tdeed_mixup_u8(const void* a, const void* b, const float* lam, int n_samples, long long per_sample, float* out, void* stream);
 int tdeed_aug_color(const void* frames, int frames_dtype, float in_scale, int n_frames, int in_h, int in_w, int crop_y,
                     int crop_x, int h, int w, int hue_on, float hue, int sat_on, float sat, int bri_on, float bri,
                     float* out, void* stream);

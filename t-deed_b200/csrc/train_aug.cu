@@ -128,9 +128,43 @@ aug_cbf_kernel(const float* __restrict__ x, int h, int w, long long total, int c
   out[idx] = v;
 }
 
+// mixup of two uint8 clips per sample (model/model.py:228-254 of the reference): out = fl32(l) * a + fl32(1 - l) * b with the
+// reference's three roundings (two products, one sum); 16 pixels per thread (two 16-byte loads, four 16-byte stores)
+__global__ void __launch_bounds__(256)
+mixup_u8_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, const float* __restrict__ lam, long long per_sample16,
+                long long total16, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= total16) return;
+  const long long smp = i / per_sample16;
+  const float la = lam[2 * smp], lb = lam[2 * smp + 1];
+  const uint4 ra = reinterpret_cast<const uint4*>(a)[i], rb = reinterpret_cast<const uint4*>(b)[i];
+  const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w}, wb[4] = {rb.x, rb.y, rb.z, rb.w};
+  float4* o = reinterpret_cast<float4*>(out) + i * 4;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      v[j] = __fadd_rn(__fmul_rn(la, (float)((wa[q] >> (8 * j)) & 0xffu)), __fmul_rn(lb, (float)((wb[q] >> (8 * j)) & 0xffu)));
+    o[q] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 }  // namespace tdeed
 
 using namespace tdeed;
+
+extern "C" int tdeed_mixup_u8(const void* a, const void* b, const float* lam, int n_samples, long long per_sample, float* out,
+                              void* stream) {
+  TDEED_REQUIRE(a && b && lam && out && n_samples > 0 && per_sample > 0 && per_sample % 16 == 0, TDEED_ERR_SHAPE,
+                "tdeed_mixup_u8: n=%d per_sample=%lld (must be a multiple of 16)", n_samples, per_sample);
+  TDEED_REQUIRE(((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(out)) & 15) == 0,
+                TDEED_ERR_SHAPE, "tdeed_mixup_u8: pointers must be 16-byte aligned");
+  const long long total16 = (long long)n_samples * (per_sample / 16);
+  mixup_u8_kernel<<<(unsigned)ceil_div_ll(total16, 256), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)a, (const uint8_t*)b, lam,
+                                                                                         per_sample / 16, total16, out);
+  return check_launch("tdeed_mixup_u8");
+}
 
 extern "C" int tdeed_aug_color(const void* frames, int frames_dtype, float in_scale, int n_frames, int in_h, int in_w, int crop_y,
                                int crop_x, int h, int w, int hue_on, float hue, int sat_on, float sat, int bri_on, float bri,

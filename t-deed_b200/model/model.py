@@ -5,6 +5,7 @@ on sys.path — while Impl.forward runs as hand-written sm_100a kernels (libtdee
 tdeed_b200.InferenceEngine).  There is no PyTorch / CPU fallback: without the built library or a
 CUDA device, forward raises.
 """
+import os
 import random
 from contextlib import nullcontext
 
@@ -426,13 +427,18 @@ class TDEEDModel(BaseRGBModel):
                     # two label adds in the same order — but batched and free of host syncs (the reference's per-clip
                     # `label_dist[i, range(T), label[i]] += l[i]` uploads an index tensor from pageable memory every clip,
                     # which drains the stream)
-                    frame2 = batch['frame2'].to(self.device, non_blocking=True).float()
+                    frame2 = batch['frame2'].to(self.device, non_blocking=True)
                     label2 = batch['label2'].to(self.device, non_blocking=True)
                     nb = frame2.shape[0]
                     l = [random.betavariate(0.2, 0.2) for _ in range(nb)]
                     lam = torch.tensor([[v, 1 - v] for v in l], dtype=torch.float64).float().pin_memory().to(self.device, non_blocking=True)
                     la, lb = lam[:, 0], lam[:, 1]
-                    frame = la.view(nb, 1, 1, 1, 1) * frame.float() + lb.view(nb, 1, 1, 1, 1) * frame2
+                    if (frame.dtype == torch.uint8 and frame2.dtype == torch.uint8 and frame.is_contiguous() and frame2.is_contiguous()
+                            and frame[0].numel() % 16 == 0 and os.environ.get('TDEED_TORCH_MIXUP') != '1'):
+                        from tdeed_b200 import train_ops
+                        frame = train_ops.mixup_u8(frame, frame2, lam)        # one pass over the two uint8 clips (tdeed_mixup_u8)
+                    else:
+                        frame = la.view(nb, 1, 1, 1, 1) * frame.float() + lb.view(nb, 1, 1, 1, 1) * frame2.float()
                     label_dist = torch.zeros((label.shape[0], label.shape[1], self._num_classes), device=self.device)
                     label_dist.scatter_add_(2, label.unsqueeze(2), la.view(nb, 1, 1).expand(-1, label.shape[1], 1).contiguous())
                     label_dist.scatter_add_(2, label2.unsqueeze(2), lb.view(nb, 1, 1).expand(-1, label.shape[1], 1).contiguous())

@@ -140,6 +140,7 @@ SIGNATURES.update({
     'tdeed_cast_f32': (c_int, [c_vp, c_ll, c_vp, c_int, c_vp]),
     'tdeed_aug_color': (c_int, [c_vp, c_int, c_float, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_float,
                                 c_int, c_float, c_vp, c_vp]),
+    'tdeed_mixup_u8': (c_int, [c_vp, c_vp, c_vp, c_int, c_ll, c_vp, c_vp]),
     'tdeed_aug_gray_mean': (c_int, [c_vp, c_int, c_int, c_vp, c_vp]),
     'tdeed_aug_contrast_blur_flip': (c_int, [c_vp, c_int, c_int, c_int, c_int, c_float, c_vp, c_int, ctypes.POINTER(c_float), c_int,
                                              c_vp, c_vp]),

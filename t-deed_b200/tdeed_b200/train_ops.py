@@ -385,6 +385,16 @@ def linear_bwd_data(dout, W, add=None, col0=0, n=None):
     return dx
 
 
+def mixup_u8(a, b, lam):
+    """a, b: uint8 (n, ...) clip batches on the device, lam: fp32 (n, 2) device tensor -> fp32 lam[:,0]*a + lam[:,1]*b (one pass,
+    the reference's roundings: model/model.py:228-254)."""
+    assert a.dtype == torch.uint8 and b.dtype == torch.uint8 and a.shape == b.shape and a.is_contiguous() and b.is_contiguous()
+    assert lam.dtype == torch.float32 and lam.is_contiguous() and tuple(lam.shape) == (a.shape[0], 2)
+    out = torch.empty(a.shape, dtype=torch.float32, device=a.device)
+    L.check(L.load().tdeed_mixup_u8(L.ptr(a), L.ptr(b), L.ptr(lam), a.shape[0], a[0].numel(), L.ptr(out), L.stream()), 'mixup_u8')
+    return out
+
+
 def ce_mse_loss(logits, target_hard, target_soft, class_weight, displ, labelD):
     """logits [M, K] fp32.  -> (loss[3] device tensor, dlogits [M,K], ddispl [M] | None)."""
     M, K = logits.shape

@@ -443,6 +443,16 @@ def test_loss_and_heads(soft, K, displ):
     assert rel(T().colsum(dlogits), br.grad) < 1e-4
 
 
+def test_mixup_u8_matches_the_reference_arithmetic():
+    g = torch.Generator(device=DEV).manual_seed(11)
+    a = torch.randint(0, 256, (3, 4, 3, 16, 24), device=DEV, generator=g, dtype=torch.uint8)
+    b = torch.randint(0, 256, a.shape, device=DEV, generator=g, dtype=torch.uint8)
+    l = torch.tensor([0.3137, 0.9999, 1e-6], dtype=torch.float64)
+    lam = torch.stack([l, 1 - l], dim=1).float().to(DEV)
+    ref = lam[:, 0].view(3, 1, 1, 1, 1) * a.float() + lam[:, 1].view(3, 1, 1, 1, 1) * b.float()      # model/model.py:240-244
+    assert torch.equal(T().mixup_u8(a, b, lam), ref)
+
+
 def test_loss_flags_out_of_range_labels():
     """F.cross_entropy raises on a target outside [0, K); the fused loss must not read out of bounds and poisons the loss (NaN)."""
     g = torch.Generator(device=DEV).manual_seed(3)
