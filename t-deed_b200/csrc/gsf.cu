@@ -334,6 +334,16 @@ __device__ __forceinline__ void gt_mma16816(float (&c)[4], const uint32_t (&a)[4
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// totals of the row-block partial sums (training: the backward pass reads [frame][fold][2]), blocks added in order
+__global__ void gsf_sum_partials_kernel(const float* __restrict__ part, int n_frames, int RB, int per_frame, float* __restrict__ sums) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_frames * per_frame) return;
+  const int f = idx / per_frame, i = idx - f * per_frame;
+  float a = 0.f;
+  for (int r = 0; r < RB; ++r) a += part[((size_t)f * RB + r) * per_frame + i];
+  sums[idx] = a;
+}
+
 // B fragments of the gate conv, one uint2 per (dt, dy, k-step, lane): [k = s*16 + (lane%4)*2 + {0,1} (+8)][n = lane/4]
 __global__ void gsf_pack_w_kernel(const float* __restrict__ w3d, int fold, int ks, uint2* __restrict__ wB) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -753,7 +763,7 @@ static int launch_gsf(int mode, const void* x, int clips, int clip_len, int h, i
       return true;
     };
     bool ok = false;
-    if (!copy_tail && foldp <= 8 * GT_THREADS && clip_len >= 1 && (long long)hw * c < (1ll << 31)) {
+    if (foldp <= 8 * GT_THREADS && clip_len >= 1 && (long long)hw * c < (1ll << 31)) {
       for (int minft = 2; minft >= 1 && !ok; --minft)
         for (int rb = 1; rb <= h && !ok; ++rb)
           for (int ft = (clip_len < gt_ftmax ? clip_len : gt_ftmax); ft >= minft && !ok; --ft) ok = plan(rb, ft);
@@ -789,6 +799,11 @@ static int launch_gsf(int mode, const void* x, int clips, int clip_len, int h, i
           (const __nv_bfloat16*)x, clip_len, h, w, c, fold, ks, R, FT, MT, (int)z_bytes, bn_scale, bn_shift, wB, b3d, gate, sums_part, RB);
       rc0 = check_launch("tdeed_gsf_fwd(gate_tc)");
       if (rc0) return rc0;
+      if (copy_tail && RB > 1) {       // training: tdeed_gsf_bwd reads the per-frame totals
+        gsf_sum_partials_kernel<<<ceil_div(n * fold * 2, GS_THREADS), GS_THREADS, 0, st>>>(sums_part, n, RB, fold * 2, sums);
+        rc0 = check_launch("tdeed_gsf_fwd(sum partials)");
+        if (rc0) return rc0;
+      }
       sums_in = sums_part;
       gate_done = true;
     } else {
