@@ -157,9 +157,101 @@ static int launch_se_fc(const float* mean, int n, int c, int rd, const float* w1
   return check_launch("tdeed_se_fwd(fc)");
 }
 
+// ---- fc1 + ReLU + fc2 + sigmoid on tensor cores (bf16 engine): 16 frames = the 16 rows of mma.sync m16n8k8 TF32 tiles ----
+// The reference runs these two 1x1 convolutions under fp16 autocast (11-bit significands, fp32 accumulate); TF32 operands (11 bits,
+// fp32 accumulate) keep that precision while the CUDA-core kernel above spends 2.7 instructions per FMA.  Means and hidden
+// activations sit in shared memory (row stride = 4 mod 32 words: conflict-free fragment loads), the fp32 weights are read from
+// L2 straight into B fragments (8 rows x 32 contiguous bytes per warp and k-step) and rounded with cvt.rna.tf32.
+constexpr int SE_TC_THREADS = 384;      // 12 warps: rd = 92 is 12 n-tiles of fc1
+
+__device__ __forceinline__ uint32_t se_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void se_mma_tf32(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__host__ __device__ inline int se_tc_stride(int k) { return k + ((4 - (k & 31)) & 31); }     // >= k, = 4 (mod 32)
+
+__global__ void __launch_bounds__(SE_TC_THREADS, 3)
+se_fc_tc_kernel(const float* __restrict__ mean, int n, int c, int rd, const float* __restrict__ w1, const float* __restrict__ b1,
+                const float* __restrict__ w2t, const float* __restrict__ b2, float* __restrict__ scale) {
+  extern __shared__ __align__(16) uint32_t se_tc_smem[];
+  const int rdp = (rd + 7) & ~7;
+  const int sm_ld = se_tc_stride(c), sh_ld = se_tc_stride(rdp);
+  uint32_t* s_mean = se_tc_smem;                       // [16][sm_ld]  tf32
+  uint32_t* s_hid = s_mean + 16 * sm_ld;               // [16][sh_ld]  tf32
+  const int f0 = blockIdx.x * 16;
+  const int nf = min(16, n - f0);
+  for (int i = threadIdx.x; i < 16 * c; i += SE_TC_THREADS) {
+    const int f = i / c, ch = i - f * c;
+    s_mean[f * sm_ld + ch] = se_tf32(f < nf ? mean[(size_t)(f0 + f) * c + ch] : 0.f);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  // fc1: hidden[16][rd] = relu(mean[16][c] . w1[rd][c]^T + b1)
+  for (int n0 = warp * 8; n0 < rdp; n0 += (SE_TC_THREADS / 32) * 8) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const bool nok = n0 + g < rd;
+    const float* wr = w1 + (size_t)(nok ? n0 + g : 0) * c + t;
+    const uint32_t* ar = s_mean + g * sm_ld + t;
+#pragma unroll 4
+    for (int k0 = 0; k0 < c; k0 += 8) {
+      const float w0 = nok ? __ldg(wr + k0) : 0.f, w4 = nok ? __ldg(wr + k0 + 4) : 0.f;
+      se_mma_tf32(acc, ar[k0], ar[8 * sm_ld + k0], ar[k0 + 4], ar[8 * sm_ld + k0 + 4], se_tf32(w0), se_tf32(w4));
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int col = n0 + 2 * t + j;
+      const float bb = col < rd ? b1[col] : 0.f;
+      s_hid[g * sh_ld + col] = col < rd ? se_tf32(fmaxf(acc[j] + bb, 0.f)) : 0u;
+      s_hid[(g + 8) * sh_ld + col] = col < rd ? se_tf32(fmaxf(acc[2 + j] + bb, 0.f)) : 0u;
+    }
+  }
+  __syncthreads();
+  // fc2: scale[16][c] = sigmoid(hidden[16][rd] . w2t[rd][c] + b2)
+  for (int n0 = warp * 8; n0 < c; n0 += (SE_TC_THREADS / 32) * 8) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* wc = w2t + n0 + g;
+    const uint32_t* ar = s_hid + g * sh_ld + t;
+#pragma unroll 4
+    for (int k0 = 0; k0 < rdp; k0 += 8) {
+      const float w0 = k0 + t < rd ? __ldg(wc + (size_t)(k0 + t) * c) : 0.f;
+      const float w4 = k0 + t + 4 < rd ? __ldg(wc + (size_t)(k0 + t + 4) * c) : 0.f;
+      se_mma_tf32(acc, ar[k0], ar[8 * sh_ld + k0], ar[k0 + 4], ar[8 * sh_ld + k0 + 4], se_tf32(w0), se_tf32(w4));
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int col = n0 + 2 * t + j;
+      const float bb = b2[col];
+      if (g < nf) scale[(size_t)(f0 + g) * c + col] = sigmoidf_(acc[j] + bb);
+      if (g + 8 < nf) scale[(size_t)(f0 + g + 8) * c + col] = sigmoidf_(acc[2 + j] + bb);
+    }
+  }
+}
+
+static int launch_se_fc_tc(const float* mean, int n, int c, int rd, const float* w1, const float* b1, const float* w2, const float* b2,
+                           float* scale, cudaStream_t st) {
+  const int rdp = (rd + 7) & ~7;
+  const size_t smem = (size_t)16 * (se_tc_stride(c) + se_tc_stride(rdp)) * sizeof(uint32_t);
+  static size_t set = 48 * 1024;
+  if (smem > set) {
+    cudaError_t e = cudaFuncSetAttribute(se_fc_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    TDEED_REQUIRE(e == cudaSuccess, TDEED_ERR_CUDA, "tdeed_se_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    set = 200 * 1024;
+  }
+  se_fc_tc_kernel<<<ceil_div(n, 16), SE_TC_THREADS, smem, st>>>(mean, n, c, rd, w1, b1, w2, b2, scale);
+  return check_launch("tdeed_se_fwd(fc_tc)");
+}
+
 // frames per CTA: about one wave of CTAs, bounded by shared memory (F * (c + rd) floats)
 static int se_fc_dispatch(const float* mean, int n, int c, int rd, const float* w1, const float* b1, const float* w2, const float* b2,
-                          float* scale, cudaStream_t st) {
+                          float* scale, cudaStream_t st, bool tensor = false) {
+  if (tensor && (size_t)16 * (tdeed::se_tc_stride(c) + tdeed::se_tc_stride((rd + 7) & ~7)) * 4 <= 190 * 1024)
+    return launch_se_fc_tc(mean, n, c, rd, w1, b1, w2, b2, scale, st);
   // 16 frames per 512-thread CTA, two CTAs per SM: 32 warps per SM hide the L2 latency of the weight stream (one 8-warp CTA
   // of 32 frames per SM issued 28 % of the time: ncu r2); 8 frames when there are too few frames to fill the machine
   const int per = ceil_div(n, 2 * kNumSMs);
@@ -212,7 +304,7 @@ static size_t part_floats(int c) {
 extern "C" long long tdeed_se_workspace_floats(int n, int c) { return 2LL * n * c; }
 
 static int se_forward(int dtype, const void* x, void* out, int n, int hw, int c, int rd, const float* w1, const float* b1,
-                      const float* w2, const float* b2, float* workspace, void* stream, bool apply = true) {
+                      const float* w2, const float* b2, float* workspace, void* stream, bool apply = true, bool train = false) {
   using namespace tdeed;
   TDEED_REQUIRE(x && w1 && b1 && w2 && b2 && workspace, TDEED_ERR_SHAPE, "tdeed_se_fwd: null pointer");
   TDEED_REQUIRE(n > 0 && hw > 0 && c > 0 && c % 8 == 0 && c <= 2048 && rd > 0 && rd <= 1024, TDEED_ERR_SHAPE,
@@ -234,7 +326,7 @@ static int se_forward(int dtype, const void* x, void* out, int n, int hw, int c,
   }
   int rc = check_launch("tdeed_se_fwd(mean)");
   if (rc) return rc;
-  rc = se_fc_dispatch(mean, n, c, rd, w1, b1, w2, b2, scale, st);
+  rc = se_fc_dispatch(mean, n, c, rd, w1, b1, w2, b2, scale, st, dtype == TDEED_BF16 && !train);
   if (rc || !apply) return rc;
   if (dtype == TDEED_BF16)
     se_scale_kernel<__nv_bfloat16><<<scale_grid, SE_THREADS, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, total8, hw * (c / 8), c / 8, c, scale);
@@ -260,7 +352,7 @@ extern "C" int tdeed_se_gate_fwd(int dtype, const void* x, int n, int hw, int c,
 extern "C" int tdeed_se_train_fwd(int dtype, const void* x, void* out, int n, int hw, int c, int rd, const float* w1,
                                   const float* b1, const float* w2t, const float* b2, float* workspace, void* stream) {
   TDEED_REQUIRE(out, TDEED_ERR_SHAPE, "tdeed_se_train_fwd: null pointer");
-  return se_forward(dtype, x, out, n, hw, c, rd, w1, b1, w2t, b2, workspace, stream);
+  return se_forward(dtype, x, out, n, hw, c, rd, w1, b1, w2t, b2, workspace, stream, true, true);   // exact fp32 fc: the backward differentiates it
 }
 
 extern "C" int tdeed_pool_posenc_fwd(int dtype, const void* x, int n, int hw, int c, int clip_len,

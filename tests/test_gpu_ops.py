@@ -244,6 +244,25 @@ def test_se_and_pool(dev, c, rd, hw):
     assert rel_err(pooled, x.mean((2, 3)) + te.repeat(2, 1)) < 1e-5
 
 
+@pytest.mark.parametrize('c,rd,hw,n', [(368, 92, (7, 7), 37), (160, 38, (14, 14), 16), (152, 14, (5, 5), 3), (768, 192, (4, 5), 20),
+                                       (24, 8, (9, 7), 33), (56, 6, (6, 6), 17)])
+def test_se_gate_bf16_tensor_core_fc(dev, c, rd, hw, n):
+    """bf16 activations: the two SE 1x1 convolutions run on TF32 tensor-core tiles (11-bit significands, fp32 accumulate — the
+    precision of the reference's fp16 autocast).  The gate must agree with the fp32 computation to ~1e-3, ragged frame counts
+    (n % 16 != 0) and hidden widths that are not multiples of 8 included."""
+    from tdeed_b200 import ops
+    g = torch.Generator().manual_seed(c + rd)
+    x = (torch.randn(n, c, *hw, generator=g) * 2).bfloat16().float()
+    w1, b1 = torch.randn(rd, c, generator=g) / math.sqrt(c), torch.randn(rd, generator=g) * 0.1
+    w2, b2 = torch.randn(c, rd, generator=g) / math.sqrt(rd), torch.randn(c, generator=g) * 0.1
+    s = torch.sigmoid(torch.relu(x.mean((2, 3)) @ w1.t() + b1) @ w2.t() + b2)
+    xh = _nhwc(x).to(dev).bfloat16()
+    gate = ops.se_gate(xh, w1.to(dev), b1.to(dev), w2.t().contiguous().to(dev), b2.to(dev))
+    assert gate.shape == (n, c) and float((gate.cpu() - s).abs().max()) < 2e-3
+    out = ops.se_(xh.clone(), w1.to(dev), b1.to(dev), w2.t().contiguous().to(dev), b2.to(dev))
+    assert torch.equal(out, (xh.float() * gate[:, None, None, :]).bfloat16())       # the scale pass applies exactly that gate
+
+
 @pytest.mark.parametrize('mode', ['gsf', 'gsm'])
 @pytest.mark.parametrize('fold,c,hw,dtype', [(16, 56, (6, 5), 'f32'), (40, 152, (4, 4), 'f32'), (92, 368, (3, 2), 'f32'), (192, 768, (2, 3), 'f32'),
                                              # bf16 activations (the inference engine's path): the real layer shapes of rny002 / rny008
