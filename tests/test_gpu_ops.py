@@ -263,6 +263,22 @@ def test_se_gate_bf16_tensor_core_fc(dev, c, rd, hw, n):
     assert torch.equal(out, (xh.float() * gate[:, None, None, :]).bfloat16())       # the scale pass applies exactly that gate
 
 
+@pytest.mark.parametrize('c,rd,hw', [(368, 92, (7, 7)), (160, 38, (14, 14)), (24, 8, (6, 5))])
+def test_se_gate_bits_do_not_depend_on_the_frame_count(dev, c, rd, hw):
+    """A clip batch must equal its clips one by one: the gate of a frame may not depend on how many frames share the call (16-frame
+    MMA tiles, kernel choices by frame count)."""
+    from tdeed_b200 import ops
+    g = torch.Generator().manual_seed(c)
+    n = 16 * 148 + 23                                   # more than one wave of 16-frame CTAs, ragged last one
+    x = torch.randn(n, hw[0], hw[1], c, generator=g).to(dev).bfloat16()
+    w1, b1 = (torch.randn(rd, c, generator=g) / math.sqrt(c)).to(dev), (torch.randn(rd, generator=g) * 0.1).to(dev)
+    w2t, b2 = (torch.randn(rd, c, generator=g) / math.sqrt(rd)).to(dev), (torch.randn(c, generator=g) * 0.1).to(dev)
+    big = ops.se_gate(x, w1, b1, w2t, b2).clone()
+    for lo, hi in ((0, 16), (100, 137), (n - 23, n)):
+        small = ops.se_gate(x[lo:hi].contiguous(), w1, b1, w2t, b2)
+        assert torch.equal(small, big[lo:hi])
+
+
 @pytest.mark.parametrize('mode', ['gsf', 'gsm'])
 @pytest.mark.parametrize('fold,c,hw,dtype', [(16, 56, (6, 5), 'f32'), (40, 152, (4, 4), 'f32'), (92, 368, (3, 2), 'f32'), (192, 768, (2, 3), 'f32'),
                                              # bf16 activations (the inference engine's path): the real layer shapes of rny002 / rny008
