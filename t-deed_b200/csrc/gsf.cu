@@ -7,7 +7,12 @@
 //   out = shift(y)*w + r*(1-w)   (GSM: shift(y) + r), channel-interleaved
 //   shift: group 0 takes y from t+1 (zero at T-1), group 1 from t-1 (zero at 0); no leakage across clips.
 //
-// Kernel plan (every input frame is read from HBM once per kernel, all reductions in a fixed order):
+// bf16 inference takes the tensor-core path further down: gsf_pack_w_kernel -> gsf_gate_tc_kernel (gate conv as an mma.sync implicit
+// GEMM fused with tanh and the y / x sums) -> gsf_weight_kernel -> gsf_blend8n_kernel / gsf_blend8_kernel (16-byte pieces).  The
+// fp32 exact mode and shapes the tensor-core plan rejects use the CUDA-core kernels below; the training forward uses the
+// tensor-core gate kernel and the CUDA-core blend (it also copies the untouched channels).
+//
+// CUDA-core kernel plan (every input frame is read from HBM once per kernel, all reductions in a fixed order):
 //   1. gsf_q_kernel     per (frame, row block): z = relu(bn(x)) staged channel-major in shared memory, then the
 //                       three temporal slices of the 3x3x3 kernel are applied as 2D convs:
 //                       Q[f][p][3g+kt] = (W3d[g][:, kt] * z[f])[p].  The temporal sum is deferred, so no CTA
