@@ -93,3 +93,42 @@ def test_pretrained_backbone_is_loaded_strictly_or_warned_about(tmp_path, monkey
     torch.save(bad, tmp_path / 'regnety_008.pth')
     with pytest.raises(RuntimeError):                                        # strict: wrong / missing keys raise
         regnet.create_model('regnety_008', pretrained=True)
+
+
+def test_stage_width_padding_keeps_the_network_function():
+    """engine.pad_block_state zero-pads a bottleneck (RegNetY-200MF stage 3: 152 -> 160 channels in the bf16 engine): the original
+    tensors sit unchanged in the leading block, the pad channels get zero weights / BN scale and shift (weight 0, bias 0, mean 0,
+    var 1) / SE columns — checked here on the CPU with the oracle: a padded block maps the same input to the same output."""
+    from tdeed_b200 import engine as E
+    assert E.padded_width(152) == 160 and E.padded_width(368) == 368 and E.padded_width(56) == 56 and E.padded_width(24) == 24
+    assert E.fold_dim(152) == E.fold_dim(160)
+    cfg = O.Config(feature_arch='rny002_gsf', clip_len=4, n_layers=2, sgp_ks=5, sgp_r=2, num_classes=4, radi_displacement=1, crop_dim=None)
+    sd = {k: v.clone() for k, v in O.random_state(cfg, 3).items()}
+    ref = {k: v.clone() for k, v in sd.items()}
+    p = '_features.s3.b2'
+    E.pad_block_state(sd, p, 152, 152, 160, 160, True)
+    w1 = sd[p + '.conv1.net.conv.weight']
+    assert tuple(w1.shape) == (160, 160, 1, 1) and torch.equal(w1[:152, :152], ref[p + '.conv1.net.conv.weight'])
+    assert float(w1[152:].abs().max()) == 0 and float(w1[:, 152:].abs().max()) == 0
+    for q in ('.conv1.net.bn', '.conv2.bn', '.conv3.bn'):
+        assert float(sd[p + q + '.weight'][152:].abs().max()) == 0 and float(sd[p + q + '.bias'][152:].abs().max()) == 0
+        assert float(sd[p + q + '.running_mean'][152:].abs().max()) == 0 and bool((sd[p + q + '.running_var'][152:] == 1).all())
+    assert tuple(sd[p + '.conv2.conv.weight'].shape) == (160, 8, 3, 3) and float(sd[p + '.conv2.conv.weight'][152:].abs().max()) == 0
+    assert tuple(sd[p + '.se.fc1.weight'].shape)[1] == 160 and tuple(sd[p + '.se.fc2.weight'].shape)[0] == 160
+    assert tuple(sd[p + '.conv3.conv.weight'].shape) == (160, 160, 1, 1)
+    # the gate-shift parameters of the block are untouched (the fold width is computed from the real width)
+    for k in ref:
+        if k.startswith(p + '.conv1.gs.'):
+            assert torch.equal(sd[k], ref[k])
+    # function check with plain torch ops on the padded vs original tensors: conv1 -> bn -> relu of a zero-padded input
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 152, 5, 4, generator=g)
+    xp = torch.cat([x, torch.zeros(2, 8, 5, 4)], 1)
+
+    def conv_bn_relu(inp, s, q):
+        y = torch.nn.functional.conv2d(inp, s[q + '.conv.weight'])
+        y = torch.nn.functional.batch_norm(y, s[q + '.bn.running_mean'], s[q + '.bn.running_var'], s[q + '.bn.weight'], s[q + '.bn.bias'], False, 0.0, 1e-5)
+        return torch.relu(y)
+
+    a, b = conv_bn_relu(x, ref, p + '.conv1.net'), conv_bn_relu(xp, sd, p + '.conv1.net')
+    assert torch.equal(b[:, :152], a) and float(b[:, 152:].abs().max()) == 0
